@@ -1,0 +1,21 @@
+"""pixlzr_b200 — B200-native (sm_100a) implementation of the pixlzr hot path.
+
+Layout
+  csrc/        hand-written CUDA kernels + the C ABI (include/pixlzr_b200.h) + the host container stage
+  _native.py   ctypes binding of libpixlzr_b200.so (fails loudly if the library is missing)
+  api.py       host-side mirror of the reference's public API (Pixlzr, PixlzrBlock, FilterType,
+               process, get_block_variance, ...) on top of the C ABI
+  build.py     in-tree nvcc build
+"""
+from .api import (  # noqa: F401
+    FilterType,
+    Pixlzr,
+    PixlzrBlock,
+    get_block_variance,
+    get_block_variance_directionally,
+    parse_shrinking_factor,
+    process,
+    process_custom,
+    reduce_image_section,
+)
+from . import _native as native  # noqa: F401

@@ -1,0 +1,314 @@
+"""ctypes binding of libpixlzr_b200.so — the C ABI declared in include/pixlzr_b200.h.
+
+There is no fallback: if the shared library is missing this module raises, and every compute
+call returns an error status when no B200 is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpixlzr_b200.so")
+
+OK, E_ARG, E_CUDA, E_OOM, E_NCCL, E_UNSUPPORTED, E_FORMAT = 0, -1, -2, -3, -4, -5, -6
+STATUS_NAMES = {0: "PXZ_OK", -1: "PXZ_E_ARG", -2: "PXZ_E_CUDA", -3: "PXZ_E_OOM", -4: "PXZ_E_NCCL",
+                -5: "PXZ_E_UNSUPPORTED", -6: "PXZ_E_FORMAT"}
+METRIC_OKLAB_MAD, METRIC_SOBEL_DIR = 0, 1
+FLAG_AFTER_IDENTITY, FLAG_NORMALISE_GLOBAL, FLAG_EXACT_VALUES = 1, 2, 4
+COMM_ID_BYTES = 128
+
+DESC_DTYPE = np.dtype([("offset", "<u8"), ("value", "<f4"), ("w", "<u2"), ("h", "<u2")])
+assert DESC_DTYPE.itemsize == 16
+
+# every symbol include/pixlzr_b200.h declares: name -> (restype, argtypes)
+_vp, _u32, _u64, _sz, _i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
+_P = C.POINTER
+SYMBOLS = {
+    "pxz_abi_version": (_i, []),
+    "pxz_device_count": (_i, []),
+    "pxz_ctx_create": (_i, [_i, _P(_vp)]),
+    "pxz_ctx_create_on_stream": (_i, [_i, _vp, _P(_vp)]),
+    "pxz_ctx_destroy": (None, [_vp]),
+    "pxz_last_error": (C.c_char_p, [_vp]),
+    "pxz_synchronize": (_i, [_vp]),
+    "pxz_launch_count": (_u64, [_vp]),
+    "pxz_host_alloc": (_i, [_sz, _P(_vp)]),
+    "pxz_host_free": (None, [_vp]),
+    "pxz_image_upload": (_i, [_vp, _vp, _u32, _u32, _u32, _sz, _P(_vp)]),
+    "pxz_image_alloc": (_i, [_vp, _u32, _u32, _u32, _P(_vp)]),
+    "pxz_image_wrap": (_i, [_vp, _vp, _u32, _u32, _u32, _sz, _P(_vp)]),
+    "pxz_image_info": (_i, [_vp, _P(_u32), _P(_u32), _P(_u32), _P(_sz), _P(_vp)]),
+    "pxz_image_download": (_i, [_vp, _vp, _vp, _sz]),
+    "pxz_image_free": (None, [_vp]),
+    "pxz_grid": (_i, [_u32, _u32, _u32, _u32, _P(_u32), _P(_u32)]),
+    "pxz_analyze": (_i, [_vp, _vp, _u32, _u32, _i, _u32, _vp, _vp]),
+    "pxz_shrink": (_i, [_vp, _vp, _u32, _u32, _i, C.c_float, _i, _u32, _P(_vp)]),
+    "pxz_reduce_dims": (_i, [C.c_float, C.c_float, _u32, _u32, _P(_u32), _P(_u32), _P(C.c_float)]),
+    "pxz_payload_info": (_i, [_vp, _vp] + [_P(_u32)] * 7 + [_P(_u64)]),
+    "pxz_payload_download": (_i, [_vp, _vp, _vp, _vp]),
+    "pxz_payload_upload": (_i, [_vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _u64, _P(_vp)]),
+    "pxz_payload_free": (None, [_vp]),
+    "pxz_expand": (_i, [_vp, _vp, _i, _vp, _sz]),
+    "pxz_expand_to_image": (_i, [_vp, _vp, _i, _vp]),
+    "pxz_comm_unique_id": (_i, [_vp]),
+    "pxz_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "pxz_comm_destroy": (None, [_vp]),
+    "pxz_container_bound": (C.c_int64, [_u32, _u32, _u32, _u32, _u32, _u64]),
+    "pxz_container_encode": (C.c_int64, [_u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _sz, _i]),
+    "pxz_container_decode": (_i, [_vp, _sz, _P(_u32), _P(_u32), _P(_u32), _P(_u32), _P(C.c_int32), _P(_u32),
+                                  _P(_u64), _vp, _vp]),
+}
+
+
+class PixlzrError(RuntimeError):
+    def __init__(self, status: int, message: str = ""):
+        self.status = status
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+
+
+_lib = None
+
+
+def lib():
+    """Loads libpixlzr_b200.so; raises if it has not been built (python pixlzr-rust_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python pixlzr-rust_b200/build.py` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        if L.pxz_abi_version() != 1:
+            raise ImportError("libpixlzr_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return a
+
+
+class Context:
+    """One device + one stream (pxz_ctx).  Not thread-safe; use one per thread."""
+
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+        self._h = C.c_void_p()
+        L = lib()
+        if cuda_stream is None:
+            st = L.pxz_ctx_create(device, C.byref(self._h))
+        else:
+            st = L.pxz_ctx_create_on_stream(device, C.c_void_p(cuda_stream), C.byref(self._h))
+        if st != OK:
+            self._h = C.c_void_p()
+            raise PixlzrError(st, "cannot create a context: no usable sm_100 (B200) device"
+                              if st == E_CUDA else "pxz_ctx_create")
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def check(self, st: int):
+        if st != OK:
+            raise PixlzrError(st, lib().pxz_last_error(self._h).decode(errors="replace"))
+
+    def synchronize(self):
+        self.check(lib().pxz_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(lib().pxz_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().pxz_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- images -------------------------------------------------------------------------------
+    def image_upload(self, img: np.ndarray) -> "Image":
+        assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] in (3, 4)
+        assert img.strides[2] == 1 and img.strides[1] == img.shape[2], "pixels must be interleaved"
+        h = C.c_void_p()
+        self.check(lib().pxz_image_upload(self._h, ptr(img), img.shape[1], img.shape[0], img.shape[2],
+                                          img.strides[0], C.byref(h)))
+        return Image(self, h, img.shape[1], img.shape[0], img.shape[2])
+
+    def image_alloc(self, w: int, h: int, c: int) -> "Image":
+        hd = C.c_void_p()
+        self.check(lib().pxz_image_alloc(self._h, w, h, c, C.byref(hd)))
+        return Image(self, hd, w, h, c)
+
+    def image_wrap(self, device_ptr: int, w: int, h: int, c: int, pitch: int) -> "Image":
+        hd = C.c_void_p()
+        self.check(lib().pxz_image_wrap(self._h, C.c_void_p(device_ptr), w, h, c, pitch, C.byref(hd)))
+        return Image(self, hd, w, h, c)
+
+    # ---- payload ------------------------------------------------------------------------------
+    def payload_upload(self, w, h, bw, bh, c, descs: np.ndarray, pixels: np.ndarray) -> "Payload":
+        assert descs.dtype == DESC_DTYPE and pixels.dtype == np.uint8
+        descs = np.ascontiguousarray(descs)
+        pixels = np.ascontiguousarray(pixels)
+        hd = C.c_void_p()
+        self.check(lib().pxz_payload_upload(self._h, w, h, bw, bh, c, ptr(descs), ptr(pixels), pixels.size, C.byref(hd)))
+        return Payload(self, hd)
+
+
+class Image:
+    def __init__(self, ctx: Context, handle, w, h, c):
+        self.ctx, self._h, self.w, self.h, self.c = ctx, handle, w, h, c
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        w, h, c, pitch, p = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_size_t(), C.c_void_p()
+        self.ctx.check(lib().pxz_image_info(self._h, C.byref(w), C.byref(h), C.byref(c), C.byref(pitch), C.byref(p)))
+        return dict(w=w.value, h=h.value, channels=c.value, pitch=pitch.value, device_ptr=p.value)
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.h, self.w, self.c), np.uint8)
+        self.ctx.check(lib().pxz_image_download(self.ctx.handle, self._h, ptr(out), out.strides[0]))
+        return out
+
+    def analyze(self, bw: int, bh: int, metric: int, flags: int = 0):
+        cols, rows = grid(self.w, self.h, bw, bh)
+        vx = np.empty(cols * rows, np.float32)
+        vy = np.empty(cols * rows, np.float32)
+        self.ctx.check(lib().pxz_analyze(self.ctx.handle, self._h, bw, bh, metric, flags, ptr(vx), ptr(vy)))
+        return vx, vy
+
+    def shrink(self, bw: int, bh: int, metric: int, factor: float, filter_down: int, flags: int = 0) -> "Payload":
+        h = C.c_void_p()
+        self.ctx.check(lib().pxz_shrink(self.ctx.handle, self._h, bw, bh, metric, factor, int(filter_down), flags,
+                                        C.byref(h)))
+        return Payload(self.ctx, h)
+
+    def free(self):
+        if self._h:
+            lib().pxz_image_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Payload:
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self._h = ctx, handle
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        v = [C.c_uint32() for _ in range(7)]
+        b = C.c_uint64()
+        self.ctx.check(lib().pxz_payload_info(self.ctx.handle, self._h, *[C.byref(x) for x in v], C.byref(b)))
+        keys = ["w", "h", "bw", "bh", "cols", "rows", "channels"]
+        d = {k: x.value for k, x in zip(keys, v)}
+        d["bytes"] = b.value
+        return d
+
+    def download(self):
+        i = self.info()
+        descs = np.empty(i["cols"] * i["rows"], DESC_DTYPE)
+        pixels = np.empty(max(1, i["bytes"]), np.uint8)
+        self.ctx.check(lib().pxz_payload_download(self.ctx.handle, self._h, ptr(descs), ptr(pixels)))
+        return descs, pixels[:i["bytes"]]
+
+    def expand(self, filter_up: int) -> np.ndarray:
+        i = self.info()
+        out = np.empty((i["h"], i["w"], i["channels"]), np.uint8)
+        self.ctx.check(lib().pxz_expand(self.ctx.handle, self._h, int(filter_up), ptr(out), out.strides[0]))
+        return out
+
+    def expand_to_image(self, filter_up: int, out: Image):
+        self.ctx.check(lib().pxz_expand_to_image(self.ctx.handle, self._h, int(filter_up), out.handle))
+
+    def free(self):
+        if self._h:
+            lib().pxz_payload_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def grid(w, h, bw, bh):
+    c, r = C.c_uint32(), C.c_uint32()
+    st = lib().pxz_grid(w, h, bw, bh, C.byref(c), C.byref(r))
+    if st != OK:
+        raise PixlzrError(st, "pxz_grid")
+    return c.value, r.value
+
+
+def reduce_dims(v0: float, v1: float, w: int, h: int):
+    ow, oh, st = C.c_uint32(), C.c_uint32(), C.c_float()
+    rc = lib().pxz_reduce_dims(v0, v1, w, h, C.byref(ow), C.byref(oh), C.byref(st))
+    if rc != OK:
+        raise PixlzrError(rc, "pxz_reduce_dims")
+    return ow.value, oh.value, st.value
+
+
+def device_count() -> int:
+    return int(lib().pxz_device_count())
+
+
+def container_encode(w, h, bw, bh, filter_byte, channels, descs, pixels, value_present=None, nthreads=0) -> bytes:
+    descs = np.ascontiguousarray(descs)
+    pixels = np.ascontiguousarray(pixels)
+    cap = lib().pxz_container_bound(w, h, bw, bh, channels, pixels.size)
+    if cap < 0:
+        raise PixlzrError(int(cap), "pxz_container_bound")
+    out = np.empty(cap, np.uint8)
+    if nthreads <= 0:
+        nthreads = os.cpu_count() or 1
+    vp = None if value_present is None else np.ascontiguousarray(value_present, dtype=np.uint8)
+    n = lib().pxz_container_encode(w, h, bw, bh, filter_byte, channels, ptr(descs), ptr(pixels), ptr(vp), ptr(out),
+                                   cap, nthreads)
+    if n < 0:
+        raise PixlzrError(int(n), "pxz_container_encode")
+    return out[:n].tobytes()
+
+
+def container_decode(data: bytes):
+    buf = np.frombuffer(data, np.uint8)
+    w, h, bw, bh, ch = (C.c_uint32() for _ in range(5))
+    filt, nbytes = C.c_int32(), C.c_uint64()
+    args = [ptr(buf), len(data), C.byref(w), C.byref(h), C.byref(bw), C.byref(bh), C.byref(filt), C.byref(ch),
+            C.byref(nbytes)]
+    st = lib().pxz_container_decode(*args, None, None)
+    if st != OK:
+        raise PixlzrError(st, "malformed .pxlzr container")
+    cols = int(np.ceil(np.float32(w.value) / np.float32(bw.value)))
+    rows = int(np.ceil(np.float32(h.value) / np.float32(bh.value)))
+    descs = np.zeros(cols * rows, DESC_DTYPE)
+    pixels = np.zeros(max(1, nbytes.value), np.uint8)
+    st = lib().pxz_container_decode(*args, ptr(descs), ptr(pixels))
+    if st != OK:
+        raise PixlzrError(st, "malformed .pxlzr container")
+    hdr = dict(w=w.value, h=h.value, bw=bw.value, bh=bh.value, filter=filt.value, channels=ch.value)
+    return hdr, descs, pixels[:nbytes.value]

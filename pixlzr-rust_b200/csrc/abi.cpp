@@ -1,0 +1,770 @@
+// abi.cpp — implementation of the C ABI in include/pixlzr_b200.h: context / stream / scratch
+// management, resample-table caching, and the stream-ordered pipelines
+//
+//   pxz_shrink : analyse -> [min/max (+ NCCL)] -> guard-band recompute -> plan (scan) -> resample
+//   pxz_expand : resample (payload -> tiles of the pitched image)
+//
+// which replace the bodies of Pixlzr::shrink_by / shrink_directionally / expand / to_image
+// (src/data_types/pixlzr.rs:77-205, pixlzr_image.rs:24-74).  No CPU fallback exists.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "pxz_host.h"
+
+using namespace pxz;
+
+// -------------------------------------------------------------------------------------------------
+// objects
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+// index-aligned list of (reduced size, tile size) pairs that a payload's tabidx refers to
+struct TabSpec {
+  std::vector<uint32_t> n_small, n_tile;
+};
+
+struct TabSet {  // device copy of the axis tables of one (spec, filter, direction)
+  AxisTab* d_tabs = nullptr;
+  uint32_t* d_pool = nullptr;
+};
+
+using TabKey = std::tuple<std::vector<uint32_t>, std::vector<uint32_t>, int, int>;
+
+}  // namespace
+
+struct pxz_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  size_t max_smem_optin = 0;
+  std::string err;
+  uint64_t launches = 0;
+  LevelThresholds thr{};
+  GuardBand band{};
+  // scratch, grown on demand
+  float* d_vx = nullptr;
+  float* d_vy = nullptr;
+  size_t values_cap = 0;
+  float* d_minmax = nullptr;
+  void* d_scan = nullptr;
+  size_t scan_cap = 0;
+  uint8_t* d_scratch = nullptr;
+  size_t scratch_cap = 0;
+  uint64_t* h_total = nullptr;  // pinned
+  std::map<TabKey, TabSet> tabs;
+  void* comm = nullptr;
+};
+
+struct pxz_image {
+  pxz_ctx* ctx;
+  uint8_t* d;
+  size_t pitch;
+  uint32_t w, h, c;
+  bool owned;
+};
+
+struct pxz_payload {
+  pxz_ctx* ctx;
+  Geom g;
+  pxz_block_desc* d_descs = nullptr;
+  uint32_t* d_tabidx = nullptr;
+  uint8_t* d_pixels = nullptr;
+  uint64_t capacity = 0;
+  uint64_t* d_total = nullptr;
+  bool bytes_known = false;
+  uint64_t bytes = 0;
+  std::shared_ptr<TabSpec> spec;
+  uint32_t max_small_px = 0;  // largest reduced block (pixels)
+  uint32_t max_tmp_down = 0;  // largest vertical-pass intermediate when shrinking / expanding (pixels)
+  uint32_t max_tmp_up = 0;
+};
+
+namespace {
+
+pxz_status fail(pxz_ctx* ctx, pxz_status st, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return st;
+}
+
+#define PXZ_CUDA(ctx, expr)                                                                             \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      cudaGetLastError();                                                                               \
+      return fail((ctx), _e == cudaErrorMemoryAllocation ? PXZ_E_OOM : PXZ_E_CUDA,                      \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                                  \
+    }                                                                                                   \
+  } while (0)
+
+inline uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a + b - 1) / b); }
+
+pxz_status make_geom(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t c, uint32_t bw, uint32_t bh, Geom* g) {
+  if (w == 0 || h == 0) return fail(ctx, PXZ_E_ARG, "empty image");
+  if (c != 3 && c != 4) return fail(ctx, PXZ_E_ARG, "channels must be 3 (RGB8) or 4 (RGBA8)");
+  if (bw == 0 || bh == 0) return fail(ctx, PXZ_E_ARG, "block size must be >= 1 (the reference divides by it)");
+  if (bw > 65535u || bh > 65535u) return fail(ctx, PXZ_E_UNSUPPORTED, "block size above 65535 is not supported");
+  g->W = w; g->H = h; g->bw = bw; g->bh = bh; g->C = c;
+  g->cols = ceil_div_u32(w, bw);  // == ceil(w as f64 / bw as f64), split.rs:45-46
+  g->rows = ceil_div_u32(h, bh);
+  g->trail_w = w % bw;
+  g->trail_h = h % bh;
+  if ((uint64_t)g->cols * g->rows > 0x7FFFFFFFull) return fail(ctx, PXZ_E_UNSUPPORTED, "more than 2^31 blocks");
+  return PXZ_OK;
+}
+
+pxz_status dev_alloc(pxz_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  PXZ_CUDA(ctx, cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream));
+  return PXZ_OK;
+}
+void dev_free(pxz_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+pxz_status ensure_scratch(pxz_ctx* ctx, uint32_t nblocks) {
+  if (ctx->values_cap < nblocks) {
+    dev_free(ctx, ctx->d_vx);
+    dev_free(ctx, ctx->d_vy);
+    ctx->d_vx = ctx->d_vy = nullptr;
+    ctx->values_cap = 0;
+    pxz_status st;
+    if ((st = dev_alloc(ctx, (void**)&ctx->d_vx, (size_t)nblocks * 4)) != PXZ_OK) return st;
+    if ((st = dev_alloc(ctx, (void**)&ctx->d_vy, (size_t)nblocks * 4)) != PXZ_OK) return st;
+    ctx->values_cap = nblocks;
+  }
+  const size_t need = plan_scan_state_bytes(nblocks);
+  if (ctx->scan_cap < need) {
+    dev_free(ctx, ctx->d_scan);
+    ctx->d_scan = nullptr;
+    ctx->scan_cap = 0;
+    pxz_status st;
+    if ((st = dev_alloc(ctx, &ctx->d_scan, need)) != PXZ_OK) return st;
+    ctx->scan_cap = need;
+  }
+  return PXZ_OK;
+}
+
+// table index layout of payloads produced by pxz_shrink: (axis * 2 + trailing) * 17 + level
+std::shared_ptr<TabSpec> spec_for_geom(const Geom& g) {
+  auto sp = std::make_shared<TabSpec>();
+  const uint32_t n_of[4] = {g.bw, g.trail_w ? g.trail_w : g.bw, g.bh, g.trail_h ? g.trail_h : g.bh};
+  for (int a = 0; a < 4; ++a) {
+    for (int k = 0; k <= kMaxLevel; ++k) {
+      const uint32_t n = n_of[a];
+      uint32_t nn = (uint32_t)(((uint64_t)n + ((1ull << k) - 1)) >> k);
+      if (nn < 1) nn = 1;
+      sp->n_small.push_back(nn);
+      sp->n_tile.push_back(n);
+    }
+  }
+  return sp;
+}
+
+// direction 0: tile -> reduced (filter_down); 1: reduced -> tile (filter_up)
+pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int direction, TabSet* out) {
+  TabKey key(spec.n_small, spec.n_tile, filter, direction);
+  auto it = ctx->tabs.find(key);
+  if (it != ctx->tabs.end()) {
+    *out = it->second;
+    return PXZ_OK;
+  }
+  std::vector<AxisTab> tabs(spec.n_small.size());
+  std::vector<uint32_t> pool;
+  std::map<std::pair<uint32_t, uint32_t>, AxisTab> seen;
+  for (size_t i = 0; i < tabs.size(); ++i) {
+    const uint32_t n_in = direction == 0 ? spec.n_tile[i] : spec.n_small[i];
+    const uint32_t n_out = direction == 0 ? spec.n_small[i] : spec.n_tile[i];
+    auto s = seen.find({n_in, n_out});
+    if (s != seen.end()) {
+      tabs[i] = s->second;
+      continue;
+    }
+    if (!build_axis_table(n_in, n_out, filter, &pool, &tabs[i])) return fail(ctx, PXZ_E_ARG, "bad resample table request");
+    seen[{n_in, n_out}] = tabs[i];
+  }
+  TabSet ts;
+  pxz_status st;
+  if ((st = dev_alloc(ctx, (void**)&ts.d_tabs, tabs.size() * sizeof(AxisTab))) != PXZ_OK) return st;
+  if ((st = dev_alloc(ctx, (void**)&ts.d_pool, pool.size() * 4)) != PXZ_OK) return st;
+  // pageable -> device copies are staged by the runtime before returning, so the vectors may die
+  PXZ_CUDA(ctx, cudaMemcpyAsync(ts.d_tabs, tabs.data(), tabs.size() * sizeof(AxisTab), cudaMemcpyHostToDevice, ctx->stream));
+  PXZ_CUDA(ctx, cudaMemcpyAsync(ts.d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->tabs[key] = ts;
+  *out = ts;
+  return PXZ_OK;
+}
+
+pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch, const pxz_payload* p, const TabSet& ts,
+                        uint32_t max_src_px, uint32_t max_tmp_px) {
+  const Geom& g = p->g;
+  const uint32_t nblocks = g.cols * g.rows;
+  size_t smem = resample_smem_bytes(max_src_px, max_tmp_px, g.C);
+  int grid = resample_grid(ctx->sm_count, nblocks);
+  uint8_t* scratch = nullptr;
+  size_t per_cta = 0;
+  if (smem > ctx->max_smem_optin) {  // tiles too large for shared memory
+    per_cta = (smem + 255) & ~(size_t)255;
+    grid = std::min<int>(grid, ctx->sm_count * 2);
+    const size_t need = per_cta * (size_t)grid;
+    if (ctx->scratch_cap < need) {
+      dev_free(ctx, ctx->d_scratch);
+      ctx->d_scratch = nullptr;
+      ctx->scratch_cap = 0;
+      pxz_status st;
+      if ((st = dev_alloc(ctx, (void**)&ctx->d_scratch, need)) != PXZ_OK) return st;
+      ctx->scratch_cap = need;
+    }
+    scratch = ctx->d_scratch;
+  }
+  PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
+                                max_src_px, max_tmp_px, scratch, per_cta, grid, ctx->stream, ctx->sm_count, &ctx->launches));
+  return PXZ_OK;
+}
+
+void payload_release(pxz_payload* p) {
+  if (!p) return;
+  dev_free(p->ctx, p->d_descs);
+  dev_free(p->ctx, p->d_tabidx);
+  dev_free(p->ctx, p->d_pixels);
+  dev_free(p->ctx, p->d_total);
+  delete p;
+}
+
+pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx** out) {
+  if (!out) return PXZ_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return PXZ_E_CUDA;
+  }
+  if (device < 0 || device >= n) return PXZ_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return PXZ_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PXZ_E_CUDA;
+  pxz_ctx* ctx = new (std::nothrow) pxz_ctx();
+  if (!ctx) return PXZ_E_OOM;
+  ctx->device = device;
+  if (prop.major != 10) {
+    // the library only carries sm_100a code; refuse loudly instead of failing at the first launch
+    fprintf(stderr, "pixlzr_b200: device %d is sm_%d%d, need sm_100 (B200)\n", device, prop.major, prop.minor);
+    delete ctx;
+    return PXZ_E_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
+  if (own) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PXZ_E_CUDA; }
+    ctx->own_stream = true;
+  } else {
+    ctx->stream = stream;
+  }
+  // keep freed blocks in the stream-ordered pool: alloc/free per call must not hit the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thresh = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+  }
+  build_level_thresholds(&ctx->thr);
+  ctx->band.rel = 1.0e-3f;
+  ctx->band.abs_raw = 5.0e-5f;
+  if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
+  if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
+  if (cudaMalloc((void**)&ctx->d_minmax, 4 * sizeof(float)) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_total, 64) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return PXZ_E_OOM;
+  }
+  *out = ctx;
+  return PXZ_OK;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pxz_abi_version(void) { return PXZ_ABI_VERSION; }
+
+int pxz_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+pxz_status pxz_ctx_create(int device, pxz_ctx** out) { return ctx_create_common(device, nullptr, true, out); }
+
+pxz_status pxz_ctx_create_on_stream(int device, void* cuda_stream, pxz_ctx** out) {
+  return ctx_create_common(device, (cudaStream_t)cuda_stream, false, out);
+}
+
+void pxz_ctx_destroy(pxz_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) nccl_comm_destroy(ctx->comm);
+  for (auto& kv : ctx->tabs) {
+    dev_free(ctx, kv.second.d_tabs);
+    dev_free(ctx, kv.second.d_pool);
+  }
+  dev_free(ctx, ctx->d_vx);
+  dev_free(ctx, ctx->d_vy);
+  dev_free(ctx, ctx->d_scan);
+  dev_free(ctx, ctx->d_scratch);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_minmax);
+  cudaFreeHost(ctx->h_total);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* pxz_last_error(const pxz_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+pxz_status pxz_synchronize(pxz_ctx* ctx) {
+  if (!ctx) return PXZ_E_ARG;
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PXZ_OK;
+}
+
+uint64_t pxz_launch_count(const pxz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+pxz_status pxz_host_alloc(size_t bytes, void** out) {
+  if (!out) return PXZ_E_ARG;
+  if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return PXZ_E_OOM;
+  }
+  return PXZ_OK;
+}
+void pxz_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+pxz_status pxz_grid(uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t* cols, uint32_t* rows) {
+  if (!cols || !rows || bw == 0 || bh == 0) return PXZ_E_ARG;
+  *cols = ceil_div_u32(w, bw);
+  *rows = ceil_div_u32(h, bh);
+  return PXZ_OK;
+}
+
+// ---- images ---------------------------------------------------------------------------------------
+pxz_status pxz_image_alloc(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t channels, pxz_image** out) {
+  if (!ctx || !out) return PXZ_E_ARG;
+  *out = nullptr;
+  if (w == 0 || h == 0) return fail(ctx, PXZ_E_ARG, "empty image");
+  if (channels != 3 && channels != 4) return fail(ctx, PXZ_E_ARG, "channels must be 3 or 4");
+  cudaSetDevice(ctx->device);
+  pxz_image* im = new (std::nothrow) pxz_image();
+  if (!im) return fail(ctx, PXZ_E_OOM, "host allocation failed");
+  im->ctx = ctx; im->w = w; im->h = h; im->c = channels; im->owned = true;
+  im->pitch = (((size_t)w * channels) + 127) & ~(size_t)127;  // 128-byte rows: every tile row starts 16 B aligned for RGBA
+  pxz_status st = dev_alloc(ctx, (void**)&im->d, im->pitch * h);
+  if (st != PXZ_OK) { delete im; return st; }
+  *out = im;
+  return PXZ_OK;
+}
+
+pxz_status pxz_image_upload(pxz_ctx* ctx, const uint8_t* host, uint32_t w, uint32_t h, uint32_t channels, size_t host_pitch,
+                            pxz_image** out) {
+  if (!ctx || !host || !out) return PXZ_E_ARG;
+  if (host_pitch < (size_t)w * channels) return fail(ctx, PXZ_E_ARG, "host pitch smaller than a row");
+  pxz_status st = pxz_image_alloc(ctx, w, h, channels, out);
+  if (st != PXZ_OK) return st;
+  cudaError_t e = cudaMemcpy2DAsync((*out)->d, (*out)->pitch, host, host_pitch, (size_t)w * channels, h,
+                                    cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    pxz_image_free(*out);
+    *out = nullptr;
+    return fail(ctx, PXZ_E_CUDA, std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(e));
+  }
+  return PXZ_OK;
+}
+
+pxz_status pxz_image_wrap(pxz_ctx* ctx, void* device_ptr, uint32_t w, uint32_t h, uint32_t channels, size_t pitch,
+                          pxz_image** out) {
+  if (!ctx || !device_ptr || !out) return PXZ_E_ARG;
+  if (w == 0 || h == 0 || (channels != 3 && channels != 4) || pitch < (size_t)w * channels)
+    return fail(ctx, PXZ_E_ARG, "bad image geometry");
+  pxz_image* im = new (std::nothrow) pxz_image();
+  if (!im) return fail(ctx, PXZ_E_OOM, "host allocation failed");
+  im->ctx = ctx; im->d = (uint8_t*)device_ptr; im->pitch = pitch; im->w = w; im->h = h; im->c = channels; im->owned = false;
+  *out = im;
+  return PXZ_OK;
+}
+
+pxz_status pxz_image_info(const pxz_image* img, uint32_t* w, uint32_t* h, uint32_t* channels, size_t* pitch, void** device_ptr) {
+  if (!img) return PXZ_E_ARG;
+  if (w) *w = img->w;
+  if (h) *h = img->h;
+  if (channels) *channels = img->c;
+  if (pitch) *pitch = img->pitch;
+  if (device_ptr) *device_ptr = img->d;
+  return PXZ_OK;
+}
+
+pxz_status pxz_image_download(pxz_ctx* ctx, const pxz_image* img, uint8_t* host, size_t host_pitch) {
+  if (!ctx || !img || !host) return PXZ_E_ARG;
+  if (host_pitch < (size_t)img->w * img->c) return fail(ctx, PXZ_E_ARG, "host pitch smaller than a row");
+  PXZ_CUDA(ctx, cudaMemcpy2DAsync(host, host_pitch, img->d, img->pitch, (size_t)img->w * img->c, img->h,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PXZ_OK;
+}
+
+void pxz_image_free(pxz_image* img) {
+  if (!img) return;
+  if (img->owned) dev_free(img->ctx, img->d);
+  delete img;
+}
+
+// ---- analysis -----------------------------------------------------------------------------------------
+static pxz_status run_analysis(pxz_ctx* ctx, const pxz_image* img, const Geom& g, pxz_metric metric, bool exact_all,
+                               const ValueMap* vm_for_band) {
+  const uint32_t nblocks = g.cols * g.rows;
+  pxz_status st = ensure_scratch(ctx, nblocks);
+  if (st != PXZ_OK) return st;
+  if (metric == PXZ_METRIC_OKLAB_MAD) {
+    if (exact_all) {
+      PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                             ctx->stream, ctx->sm_count, &ctx->launches));
+    } else {
+      PXZ_CUDA(ctx, launch_analyze_mad_fast(img->d, img->pitch, g, ctx->d_vx, ctx->stream, ctx->sm_count, &ctx->launches));
+      if (vm_for_band) {
+        // recompute, in reference order, the tiles whose level could differ from the CPU result
+        PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, ctx->d_vx, vm_for_band, &ctx->thr,
+                                               &ctx->band, ctx->d_minmax, ctx->stream, ctx->sm_count, &ctx->launches));
+      }
+    }
+  } else if (metric == PXZ_METRIC_SOBEL_DIR) {
+    // operations.rs:220-221: `height - 2` / `width - 2` underflow -> the reference panics
+    const uint32_t min_w = g.trail_w ? std::min(g.bw, g.trail_w) : std::min(g.bw, g.W);
+    const uint32_t min_h = g.trail_h ? std::min(g.bh, g.trail_h) : std::min(g.bh, g.H);
+    if (min_w < 2 || min_h < 2)
+      return fail(ctx, PXZ_E_ARG, "directional metric needs every block to be at least 2x2 (the reference panics)");
+    PXZ_CUDA(ctx, launch_analyze_sobel(img->d, img->pitch, g, ctx->d_vx, ctx->d_vy, ctx->stream, ctx->sm_count, &ctx->launches));
+  } else {
+    return fail(ctx, PXZ_E_ARG, "unknown metric");
+  }
+  return PXZ_OK;
+}
+
+pxz_status pxz_analyze(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t bh, pxz_metric metric, uint32_t flags,
+                       float* host_values_x, float* host_values_y) {
+  if (!ctx || !img || !host_values_x) return PXZ_E_ARG;
+  cudaSetDevice(ctx->device);
+  Geom g;
+  pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw, bh, &g);
+  if (st != PXZ_OK) return st;
+  st = run_analysis(ctx, img, g, metric, (flags & PXZ_FLAG_EXACT_VALUES) != 0, nullptr);
+  if (st != PXZ_OK) return st;
+  const size_t n = (size_t)g.cols * g.rows;
+  PXZ_CUDA(ctx, cudaMemcpyAsync(host_values_x, ctx->d_vx, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (host_values_y) {
+    const float* src = metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : ctx->d_vx;
+    PXZ_CUDA(ctx, cudaMemcpyAsync(host_values_y, src, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PXZ_OK;
+}
+
+// ---- encode -------------------------------------------------------------------------------------------
+static pxz_status payload_new(pxz_ctx* ctx, const Geom& g, uint64_t capacity, pxz_payload** out) {
+  pxz_payload* p = new (std::nothrow) pxz_payload();
+  if (!p) return fail(ctx, PXZ_E_OOM, "host allocation failed");
+  p->ctx = ctx;
+  p->g = g;
+  p->capacity = capacity;
+  const size_t nblocks = (size_t)g.cols * g.rows;
+  pxz_status st;
+  if ((st = dev_alloc(ctx, (void**)&p->d_descs, nblocks * sizeof(pxz_block_desc))) != PXZ_OK ||
+      (st = dev_alloc(ctx, (void**)&p->d_tabidx, nblocks * 4)) != PXZ_OK ||
+      (st = dev_alloc(ctx, (void**)&p->d_pixels, capacity)) != PXZ_OK ||
+      (st = dev_alloc(ctx, (void**)&p->d_total, 8)) != PXZ_OK) {
+    payload_release(p);
+    return st;
+  }
+  *out = p;
+  return PXZ_OK;
+}
+
+pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t bh, pxz_metric metric, float factor,
+                      pxz_filter filter_down, uint32_t flags, pxz_payload** out) {
+  if (!ctx || !img || !out) return PXZ_E_ARG;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  if ((int)filter_down < 0 || (int)filter_down > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
+  Geom g;
+  pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw, bh, &g);
+  if (st != PXZ_OK) return st;
+  const uint32_t nblocks = g.cols * g.rows;
+  const bool normalise = (flags & PXZ_FLAG_NORMALISE_GLOBAL) != 0;
+
+  ValueMap vm;
+  vm.factor = factor;
+  vm.mode = (metric == PXZ_METRIC_SOBEL_DIR) ? 2 : ((flags & PXZ_FLAG_AFTER_IDENTITY) ? 1 : 0);
+  vm.normalise = normalise ? 1 : 0;
+
+  // with global normalisation every value depends on the exact min and max, so the Oklab path
+  // runs in reference order for all blocks
+  const bool exact_all = (flags & PXZ_FLAG_EXACT_VALUES) != 0 || (normalise && metric == PXZ_METRIC_OKLAB_MAD);
+  st = run_analysis(ctx, img, g, metric, exact_all, (metric == PXZ_METRIC_OKLAB_MAD && !exact_all) ? &vm : nullptr);
+  if (st != PXZ_OK) return st;
+
+  if (normalise) {
+    PXZ_CUDA(ctx, launch_minmax(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, nblocks, ctx->d_minmax,
+                                ctx->stream, &ctx->launches));
+    if (ctx->comm) {
+      std::string err;
+      if (nccl_allreduce_min_f32(ctx->comm, ctx->d_minmax, 4, ctx->stream, &err) != 0) return fail(ctx, PXZ_E_NCCL, err);
+    }
+  }
+
+  pxz_payload* p = nullptr;
+  st = payload_new(ctx, g, (uint64_t)g.W * g.H * g.C, &p);
+  if (st != PXZ_OK) return st;
+  p->spec = spec_for_geom(g);
+  {
+    // shared-memory bounds of the two resample directions for this geometry
+    const bool coupled = metric == PXZ_METRIC_OKLAB_MAD;  // both axes share the level
+    const uint32_t tw_max = g.bw, th_max = g.bh;
+    p->max_small_px = tw_max * th_max;
+    if (coupled) {
+      p->max_tmp_down = ((th_max + 1) / 2) * tw_max;  // dh <= ceil(th/2), sw = tw
+      p->max_tmp_up = th_max * ((tw_max + 1) / 2);    // dh = th, sw <= ceil(tw/2)
+      p->max_small_px = ((th_max + 1) / 2) * ((tw_max + 1) / 2);
+      // a 1-px-wide/-high trailing tile keeps that axis while the other shrinks: still within the bounds
+    } else {
+      p->max_tmp_down = th_max * tw_max;
+      p->max_tmp_up = th_max * tw_max;
+    }
+  }
+  cudaError_t e = launch_plan(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, g, vm, ctx->d_minmax, ctx->thr,
+                              p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, ctx->stream, &ctx->launches);
+  if (e != cudaSuccess) {
+    payload_release(p);
+    return fail(ctx, PXZ_E_CUDA, std::string("plan: ") + cudaGetErrorString(e));
+  }
+  TabSet ts;
+  st = get_tabset(ctx, *p->spec, (int)filter_down, 0, &ts);
+  if (st == PXZ_OK) st = run_resample(ctx, 0, img->d, img->pitch, p, ts, g.bw * g.bh, p->max_tmp_down);
+  if (st != PXZ_OK) {
+    payload_release(p);
+    return st;
+  }
+  *out = p;
+  return PXZ_OK;
+}
+
+// host restatement of the plan kernel's scalar path (same threshold table)
+pxz_status pxz_reduce_dims(float v0, float v1, uint32_t w, uint32_t h, uint32_t* out_w, uint32_t* out_h, float* stored) {
+  if (!out_w || !out_h || w == 0 || h == 0) return PXZ_E_ARG;
+  static LevelThresholds thr;
+  static bool init = false;
+  if (!init) {
+    build_level_thresholds(&thr);
+    init = true;
+  }
+  auto parse = [](float v) -> float {  // operations.rs:128-138
+    if (!signbit(v)) return v;
+    float x = 1.0f + v;
+    return (x != x) ? 0.0f : (x > 0.0f ? x : 0.0f);
+  };
+  auto level = [&](float pv) -> uint32_t {
+    if (pv != pv) return 0;
+    if (pv >= thr.thr[0]) return 0;
+    for (int k = 1; k < kThresholds; ++k)
+      if (pv >= thr.thr[k]) return (uint32_t)k;
+    return kLevelOnePixel;
+  };
+  auto dim = [](uint32_t n, uint32_t k) -> uint32_t {
+    if (k >= 32) return 1;
+    uint32_t d = (uint32_t)(((uint64_t)n + ((1ull << k) - 1)) >> k);
+    return d < 1 ? 1 : d;
+  };
+  const float p0 = parse(v0), p1 = parse(v1);
+  *out_w = dim(w, level(p0));
+  *out_h = dim(h, level(p1));
+  if (stored) *stored = (isinf(p0) || isinf(p1)) ? INFINITY : (float)sqrt((double)p0 * (double)p0 + (double)p1 * (double)p1);
+  return PXZ_OK;
+}
+
+// ---- payload ------------------------------------------------------------------------------------------
+static pxz_status payload_bytes(pxz_ctx* ctx, const pxz_payload* cp, uint64_t* bytes) {
+  pxz_payload* p = const_cast<pxz_payload*>(cp);
+  if (!p->bytes_known) {
+    PXZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_total, p->d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    p->bytes = *ctx->h_total;
+    p->bytes_known = true;
+  }
+  *bytes = p->bytes;
+  return PXZ_OK;
+}
+
+pxz_status pxz_payload_info(pxz_ctx* ctx, const pxz_payload* p, uint32_t* w, uint32_t* h, uint32_t* bw, uint32_t* bh,
+                            uint32_t* cols, uint32_t* rows, uint32_t* channels, uint64_t* bytes) {
+  if (!ctx || !p) return PXZ_E_ARG;
+  if (w) *w = p->g.W;
+  if (h) *h = p->g.H;
+  if (bw) *bw = p->g.bw;
+  if (bh) *bh = p->g.bh;
+  if (cols) *cols = p->g.cols;
+  if (rows) *rows = p->g.rows;
+  if (channels) *channels = p->g.C;
+  if (bytes) return payload_bytes(ctx, p, bytes);
+  return PXZ_OK;
+}
+
+pxz_status pxz_payload_download(pxz_ctx* ctx, const pxz_payload* p, pxz_block_desc* host_descs, uint8_t* host_pixels) {
+  if (!ctx || !p || !host_descs || !host_pixels) return PXZ_E_ARG;
+  cudaSetDevice(ctx->device);
+  uint64_t bytes = 0;
+  pxz_status st = payload_bytes(ctx, p, &bytes);
+  if (st != PXZ_OK) return st;
+  const size_t nblocks = (size_t)p->g.cols * p->g.rows;
+  PXZ_CUDA(ctx, cudaMemcpyAsync(host_descs, p->d_descs, nblocks * sizeof(pxz_block_desc), cudaMemcpyDeviceToHost, ctx->stream));
+  if (bytes) PXZ_CUDA(ctx, cudaMemcpyAsync(host_pixels, p->d_pixels, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PXZ_OK;
+}
+
+pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t channels,
+                              const pxz_block_desc* descs, const uint8_t* pixels, uint64_t bytes, pxz_payload** out) {
+  if (!ctx || !descs || (!pixels && bytes) || !out) return PXZ_E_ARG;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  Geom g;
+  pxz_status st = make_geom(ctx, w, h, channels, bw, bh, &g);
+  if (st != PXZ_OK) return st;
+  // the decoder sizes the grid in f32 (encoding/mod.rs:118-119); identical to the integer ceil below 2^24
+  const size_t nblocks = (size_t)g.cols * g.rows;
+  // distinct (reduced, tile) size pairs -> table indices
+  auto spec = std::make_shared<TabSpec>();
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> index;
+  std::vector<uint32_t> tabidx(nblocks);
+  uint32_t max_small = 1, max_tmp_up = 1, max_tmp_down = 1;
+  auto idx_of = [&](uint32_t small, uint32_t tile) -> uint32_t {
+    auto it = index.find({small, tile});
+    if (it != index.end()) return it->second;
+    const uint32_t id = (uint32_t)spec->n_small.size();
+    spec->n_small.push_back(small);
+    spec->n_tile.push_back(tile);
+    index[{small, tile}] = id;
+    return id;
+  };
+  for (size_t b = 0; b < nblocks; ++b) {
+    const uint32_t by = (uint32_t)(b / g.cols), bx = (uint32_t)(b % g.cols);
+    // target size as Pixlzr::expand computes it (pixlzr.rs:92-107)
+    const uint32_t tw = (bx == g.cols - 1 && g.trail_w) ? g.trail_w : g.bw;
+    const uint32_t th = (by == g.rows - 1 && g.trail_h) ? g.trail_h : g.bh;
+    const pxz_block_desc& d = descs[b];
+    if (d.w == 0 || d.h == 0) return fail(ctx, PXZ_E_ARG, "block with zero size");
+    const uint64_t sz = (uint64_t)d.w * d.h * channels;
+    if (d.offset + sz > bytes) return fail(ctx, PXZ_E_ARG, "block descriptor points outside the payload");
+    if (channels == 4 && (d.offset & 3u)) return fail(ctx, PXZ_E_ARG, "RGBA block offsets must be 4-byte aligned");
+    const uint32_t ix = idx_of(d.w, tw), iy = idx_of(d.h, th);
+    if (ix > 0xFFFFu || iy > 0xFFFFu) return fail(ctx, PXZ_E_UNSUPPORTED, "more than 65536 distinct block sizes");
+    tabidx[b] = ix | (iy << 16);
+    max_small = std::max(max_small, (uint32_t)d.w * d.h);
+    max_tmp_up = std::max(max_tmp_up, th * (uint32_t)d.w);
+    max_tmp_down = std::max(max_tmp_down, (uint32_t)d.h * tw);
+  }
+  pxz_payload* p = nullptr;
+  st = payload_new(ctx, g, bytes, &p);
+  if (st != PXZ_OK) return st;
+  p->spec = spec;
+  p->max_small_px = max_small;
+  p->max_tmp_up = max_tmp_up;
+  p->max_tmp_down = max_tmp_down;
+  p->bytes = bytes;
+  p->bytes_known = true;
+  cudaError_t e = cudaMemcpyAsync(p->d_descs, descs, nblocks * sizeof(pxz_block_desc), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_tabidx, tabidx.data(), nblocks * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(p->d_pixels, pixels, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_total, &p->bytes, 8, cudaMemcpyHostToDevice, ctx->stream);
+  // tabidx is a pageable temporary and `pixels` may be reused by the caller right away
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    payload_release(p);
+    return fail(ctx, PXZ_E_CUDA, std::string("payload upload: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return PXZ_OK;
+}
+
+void pxz_payload_free(pxz_payload* p) { payload_release(p); }
+
+// ---- decode -------------------------------------------------------------------------------------------
+pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, pxz_image* out) {
+  if (!ctx || !p || !out) return PXZ_E_ARG;
+  cudaSetDevice(ctx->device);
+  if ((int)filter_up < 0 || (int)filter_up > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
+  if (out->w != p->g.W || out->h != p->g.H || out->c != p->g.C) return fail(ctx, PXZ_E_ARG, "output image geometry mismatch");
+  TabSet ts;
+  pxz_status st = get_tabset(ctx, *p->spec, (int)filter_up, 1, &ts);
+  if (st != PXZ_OK) return st;
+  return run_resample(ctx, 1, out->d, out->pitch, p, ts, p->max_small_px, p->max_tmp_up);
+}
+
+pxz_status pxz_expand(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, uint8_t* host_out, size_t host_pitch) {
+  if (!ctx || !p || !host_out) return PXZ_E_ARG;
+  pxz_image* im = nullptr;
+  pxz_status st = pxz_image_alloc(ctx, p->g.W, p->g.H, p->g.C, &im);
+  if (st != PXZ_OK) return st;
+  st = pxz_expand_to_image(ctx, p, filter_up, im);
+  if (st == PXZ_OK) st = pxz_image_download(ctx, im, host_out, host_pitch);
+  pxz_image_free(im);
+  return st;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------
+pxz_status pxz_comm_unique_id(uint8_t id[PXZ_COMM_ID_BYTES]) {
+  if (!id) return PXZ_E_ARG;
+  std::string err;
+  if (nccl_get_unique_id(id, &err) != 0) {
+    fprintf(stderr, "pixlzr_b200: %s\n", err.c_str());
+    return PXZ_E_NCCL;
+  }
+  return PXZ_OK;
+}
+
+pxz_status pxz_comm_init(pxz_ctx* ctx, int nranks, int rank, const uint8_t id[PXZ_COMM_ID_BYTES]) {
+  if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return PXZ_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm) {
+    nccl_comm_destroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  std::string err;
+  if (nccl_comm_init(&ctx->comm, nranks, rank, id, &err) != 0) return fail(ctx, PXZ_E_NCCL, err);
+  return PXZ_OK;
+}
+
+void pxz_comm_destroy(pxz_ctx* ctx) {
+  if (ctx && ctx->comm) {
+    nccl_comm_destroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+}
+
+}  // extern "C"

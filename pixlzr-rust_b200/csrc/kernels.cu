@@ -1,0 +1,1033 @@
+// kernels.cu — hand-written sm_100a kernels of the pixlzr hot path.
+//
+//   k_analyze_mad_rgba   Oklab mean-absolute-deviation per tile, fast arithmetic (operations.rs:26-126)
+//   k_analyze_mad_any    same, any channel count / alignment
+//   k_mad_exact          reference-order (sequential f32, no fma, glibc cbrtf) recomputation of the
+//                        tiles whose fast value lies in the guard band of a level threshold
+//   k_analyze_sobel      directional Sobel metric, integer exact (operations.rs:192-259)
+//   k_minmax             global min / -max of the raw values (normalise extension)
+//   k_plan               value -> parse_value -> level -> dims -> payload offsets (single-pass scan)
+//                        (operations.rs:128-156)
+//   k_resample           per-block separable resample, image-crate order (block.rs:273-290):
+//                        image tiles -> packed payload (shrink) or payload -> image tiles (expand+paste)
+//
+// Nothing here is a dense contraction, so no tensor cores: the kernels are HBM / FP32-pipe work with
+// 16-byte coalesced loads, shared-memory staging and warp-shuffle reductions.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "pxz_internal.h"
+
+namespace pxz {
+
+// ------------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_srgb_lut[256] = {
+#include "srgb_lut.inc"
+};
+
+// palette 0.7.6 Oklab matrices (linear sRGB -> LMS, LMS' -> Lab), f32
+#define M1_00 0.4122214708f
+#define M1_01 0.5363325363f
+#define M1_02 0.0514459929f
+#define M1_10 0.2119034982f
+#define M1_11 0.6806995451f
+#define M1_12 0.1073969566f
+#define M1_20 0.0883024619f
+#define M1_21 0.2817188376f
+#define M1_22 0.6299787005f
+#define M2_00 0.2104542553f
+#define M2_01 0.7936177850f
+#define M2_02 (-0.0040720468f)
+#define M2_10 1.9779984951f
+#define M2_11 (-2.4285922050f)
+#define M2_12 0.4505937099f
+#define M2_20 0.0259040371f
+#define M2_21 0.7827717662f
+#define M2_22 (-0.8086757660f)
+
+constexpr float kInv255 = (float)(1.0 / 255.0);
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// x >= 0.  cube root through the SFU: 2^(log2(x)/3); ~4e-7 relative error (fast path only).
+__device__ __forceinline__ float cbrt_fast(float x) {
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  l *= 0.333333343f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+  return r;
+}
+
+// u8 -> f32 without the conversion pipe: splice the byte into the mantissa of 2^23.
+template <int BYTE>
+__device__ __forceinline__ float byte_to_float(uint32_t word) {
+  uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7440 | BYTE);  // {b, 0, 0, 0x4B}
+  return __uint_as_float(bits) - 8388608.0f;
+}
+
+// tile geometry of block index b
+struct Tile {
+  uint32_t x0, y0, tw, th;
+};
+__device__ __forceinline__ Tile tile_of(const Geom& g, uint32_t b) {
+  Tile t;
+  uint32_t by = b / g.cols, bx = b - by * g.cols;
+  t.x0 = bx * g.bw;
+  t.y0 = by * g.bh;
+  t.tw = min(g.bw, g.W - t.x0);  // split.rs:18-19
+  t.th = min(g.bh, g.H - t.y0);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Oklab MAD, fast path.
+// One group of G threads per tile, 256/G tiles per CTA iteration, persistent CTAs (grid-stride over
+// tiles) so the 32 KB bank-conflict-free sRGB table is built once per CTA.  Each thread keeps the
+// cube-rooted LMS of its <= 16 pixels in registers, so pass 2 (|c - mean|) does not redo the cube
+// roots the reference computes twice (operations.rs:75-84 / 111-119).
+// ------------------------------------------------------------------------------------------------
+struct OklabFast {
+  float l, m, s;  // cube-rooted LMS
+};
+
+__device__ __forceinline__ OklabFast lms_fast(uint32_t px, const float* lut_lane) {
+  // lut_lane = s_lut + lane; entry v at lut_lane[v * 32] -> bank == lane, conflict free
+  const float r = lut_lane[(px & 0xFFu) << 5];
+  const float g = lut_lane[((px >> 8) & 0xFFu) << 5];
+  const float b = lut_lane[((px >> 16) & 0xFFu) << 5];
+  OklabFast o;
+  o.l = cbrt_fast(fmaf(M1_02, b, fmaf(M1_01, g, M1_00 * r)));
+  o.m = cbrt_fast(fmaf(M1_12, b, fmaf(M1_11, g, M1_10 * r)));
+  o.s = cbrt_fast(fmaf(M1_22, b, fmaf(M1_21, g, M1_20 * r)));
+  return o;
+}
+
+template <int G, int QPT>
+__global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                               float* __restrict__ vx) {
+  constexpr int TPC = kThreads / G;  // tiles per CTA iteration
+  constexpr int WPG = G / 32;        // warps per group
+  extern __shared__ float s_lut[];   // [256][32]
+  __shared__ float s_r1[2][kThreads / 32][4];
+  __shared__ float s_r2[2][kThreads / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid / G, gt = tid % G, gwarp0 = grp * WPG;
+  for (int i = tid; i < 256 * 32; i += kThreads) s_lut[i] = c_srgb_lut[i >> 5];
+  __syncthreads();
+  const float* lut_lane = s_lut + lane;
+
+  const uint32_t ntiles = g.cols * g.rows;
+  const uint32_t qpr = g.bw >> 2;  // quads (4 px = 16 B) per full tile row
+  uint32_t it = 0;
+
+  uint4 cur[QPT];
+  // ---- load helper (as a lambda to keep cur/next symmetric) ----
+  auto load_tile = [&](uint32_t tile, uint4(&v)[QPT]) {
+    if (tile < ntiles) {
+      Tile t = tile_of(g, tile);
+      const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
+#pragma unroll
+      for (int j = 0; j < QPT; ++j) {
+        uint32_t q = gt + j * G;
+        uint32_t row = q / qpr, c4 = q - row * qpr;
+        if (row < t.th && c4 * 4 < t.tw) {
+          v[j] = ldg_nc_v4(base + (size_t)row * pitch + (size_t)c4 * 16);
+        } else {
+          v[j] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  };
+
+  uint32_t base_tile = blockIdx.x * TPC;
+  load_tile(base_tile + grp, cur);
+  for (; base_tile < ntiles; base_tile += gridDim.x * TPC, ++it) {
+    const uint32_t tile = base_tile + grp;
+    const bool valid = tile < ntiles;
+    Tile t = valid ? tile_of(g, tile) : Tile{0, 0, 0, 0};
+    // prefetch the next tile of this group while this one is being chewed on
+    uint4 nxt[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) nxt[j] = make_uint4(0, 0, 0, 0);
+    load_tile(tile + gridDim.x * TPC, nxt);
+
+    OklabFast c[QPT * 4];
+    float al[QPT * 4];
+    float sl = 0.f, sm = 0.f, ss = 0.f, sa = 0.f;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      uint32_t q = gt + j * G;
+      uint32_t row = q / qpr, c4 = q - row * qpr;
+      const bool inq = valid && row < t.th && c4 * 4 < t.tw;
+      const uint32_t w4[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        OklabFast o = lms_fast(w4[k], lut_lane);
+        float a = byte_to_float<3>(w4[k]) * kInv255;
+        const bool in = inq && (c4 * 4 + k) < t.tw;
+        if (!in) { o.l = 0.f; o.m = 0.f; o.s = 0.f; a = 0.f; }
+        c[j * 4 + k] = o;
+        al[j * 4 + k] = a;
+        sl += o.l; sm += o.m; ss += o.s; sa += a;
+      }
+    }
+    // ---- group reduction 1: sums of l', m', s', alpha ----
+    sl = warp_sum(sl); sm = warp_sum(sm); ss = warp_sum(ss); sa = warp_sum(sa);
+    const int buf = it & 1;
+    if (WPG > 1) {
+      if (lane == 0) { s_r1[buf][warp][0] = sl; s_r1[buf][warp][1] = sm; s_r1[buf][warp][2] = ss; s_r1[buf][warp][3] = sa; }
+      __syncthreads();
+      sl = sm = ss = sa = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPG; ++w) {
+        sl += s_r1[buf][gwarp0 + w][0]; sm += s_r1[buf][gwarp0 + w][1];
+        ss += s_r1[buf][gwarp0 + w][2]; sa += s_r1[buf][gwarp0 + w][3];
+      }
+    }
+    const float count = (float)(t.tw * t.th);
+    const float inv = valid ? 1.0f / count : 0.f;
+    sl *= inv; sm *= inv; ss *= inv; sa *= inv;
+    // the Lab transform is linear: mean(Lab) = M2 * mean(l', m', s')
+    const float nL = -(M2_00 * sl + M2_01 * sm + M2_02 * ss);
+    const float nA = -(M2_10 * sl + M2_11 * sm + M2_12 * ss);
+    const float nB = -(M2_20 * sl + M2_21 * sm + M2_22 * ss);
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      uint32_t q = gt + j * G;
+      uint32_t row = q / qpr, c4 = q - row * qpr;
+      const bool inq = valid && row < t.th && c4 * 4 < t.tw;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const OklabFast o = c[j * 4 + k];
+        const float dL = fmaf(M2_02, o.s, fmaf(M2_01, o.m, fmaf(M2_00, o.l, nL)));
+        const float dA = fmaf(M2_12, o.s, fmaf(M2_11, o.m, fmaf(M2_10, o.l, nA)));
+        const float dB = fmaf(M2_22, o.s, fmaf(M2_21, o.m, fmaf(M2_20, o.l, nB)));
+        const float dAl = al[j * 4 + k] - sa;
+        const bool in = inq && (c4 * 4 + k) < t.tw;
+        const float e = (fabsf(dA) + fabsf(dB)) + (fabsf(dL) + fabsf(dAl));
+        d += in ? e : 0.f;
+      }
+    }
+    d = warp_sum(d);
+    if (WPG > 1) {
+      if (lane == 0) s_r2[buf][warp] = d;
+      __syncthreads();
+      d = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPG; ++w) d += s_r2[buf][gwarp0 + w];
+    }
+    if (valid && gt == 0) vx[tile] = d * inv;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) cur[j] = nxt[j];
+  }
+}
+
+// Any channel count / alignment / tile size: one CTA per tile (grid-stride), byte loads, same fast
+// arithmetic.  The first 16 pixels of every thread stay in registers; a tile with more than
+// 16 * 256 pixels recomputes the rest in pass 2.
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_analyze_mad_any(const uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                              float* __restrict__ vx) {
+  extern __shared__ float s_lut[];
+  __shared__ float s_r1[kThreads / 32][4];
+  __shared__ float s_r2[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 256 * 32; i += kThreads) s_lut[i] = c_srgb_lut[i >> 5];
+  __syncthreads();
+  const float* lut_lane = s_lut + lane;
+  constexpr int KEEP = 16;
+  const uint32_t ntiles = g.cols * g.rows;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const Tile t = tile_of(g, tile);
+    const uint32_t npx = t.tw * t.th;
+    const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
+    auto fetch = [&](uint32_t idx, float& a) -> OklabFast {
+      uint32_t y = idx / t.tw, x = idx - y * t.tw;
+      const uint8_t* p = base + (size_t)y * pitch + (size_t)x * C;
+      uint32_t px = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+      a = (C == 4) ? (float)p[3] * kInv255 : 0.f;
+      return lms_fast(px, lut_lane);
+    };
+    OklabFast c[KEEP];
+    float al[KEEP];
+    float sl = 0.f, sm = 0.f, ss = 0.f, sa = 0.f;
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) {
+      uint32_t idx = tid + k * kThreads;
+      if (idx < npx) {
+        c[k] = fetch(idx, al[k]);
+        sl += c[k].l; sm += c[k].m; ss += c[k].s; sa += al[k];
+      }
+    }
+    for (uint32_t idx = tid + KEEP * kThreads; idx < npx; idx += kThreads) {
+      float a;
+      OklabFast o = fetch(idx, a);
+      sl += o.l; sm += o.m; ss += o.s; sa += a;
+    }
+    sl = warp_sum(sl); sm = warp_sum(sm); ss = warp_sum(ss); sa = warp_sum(sa);
+    if (lane == 0) { s_r1[warp][0] = sl; s_r1[warp][1] = sm; s_r1[warp][2] = ss; s_r1[warp][3] = sa; }
+    __syncthreads();
+    sl = sm = ss = sa = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { sl += s_r1[w][0]; sm += s_r1[w][1]; ss += s_r1[w][2]; sa += s_r1[w][3]; }
+    const float inv = 1.0f / (float)npx;
+    sl *= inv; sm *= inv; ss *= inv; sa *= inv;
+    const float nL = -(M2_00 * sl + M2_01 * sm + M2_02 * ss);
+    const float nA = -(M2_10 * sl + M2_11 * sm + M2_12 * ss);
+    const float nB = -(M2_20 * sl + M2_21 * sm + M2_22 * ss);
+    auto dev = [&](const OklabFast& o, float a) -> float {
+      const float dL = fmaf(M2_02, o.s, fmaf(M2_01, o.m, fmaf(M2_00, o.l, nL)));
+      const float dA = fmaf(M2_12, o.s, fmaf(M2_11, o.m, fmaf(M2_10, o.l, nA)));
+      const float dB = fmaf(M2_22, o.s, fmaf(M2_21, o.m, fmaf(M2_20, o.l, nB)));
+      float e = (fabsf(dA) + fabsf(dB)) + fabsf(dL);
+      if (C == 4) e += fabsf(a - sa);
+      return e;
+    };
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) {
+      uint32_t idx = tid + k * kThreads;
+      if (idx < npx) d += dev(c[k], al[k]);
+    }
+    for (uint32_t idx = tid + KEEP * kThreads; idx < npx; idx += kThreads) {
+      float a;
+      OklabFast o = fetch(idx, a);
+      d += dev(o, a);
+    }
+    d = warp_sum(d);
+    if (lane == 0) s_r2[warp] = d;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) tot += s_r2[w];
+      vx[tile] = tot * inv;
+    }
+    __syncthreads();  // s_r1 / s_r2 reuse
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// value -> level (operations.rs:128-148), shared by the guard-band test and the plan kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float parse_value_dev(float value) {  // operations.rs:128-138
+  if (!signbit(value)) return value;
+  float v = __fadd_rn(1.0f, value);
+  v = (v != v) ? 0.0f : (v > 0.0f ? v : 0.0f);  // f32::max(NaN, 0) = 0; -0 -> +0
+  return v;
+}
+
+// k such that level = 2^-k; kLevelOnePixel when level * n < 1 for every n < 2^40.
+__device__ __forceinline__ uint32_t level_k(float pv, const LevelThresholds& thr) {
+  if (pv != pv) return 0;           // NaN.min(0) = 0 -> exp2(0) = 1
+  if (pv >= thr.thr[0]) return 0;   // includes +inf
+  if (!(pv >= thr.thr[kThresholds - 1])) return kLevelOnePixel;  // 0, denormals, tiny
+  // thr is decreasing in k; the answer is within one of the binade estimate
+  int e = (int)((__float_as_uint(pv) >> 23) & 0xFF) - 127;  // floor(log2 pv) for normals
+  int k = -e - 1;                                             // candidate: round(log2) in {e, e+1}
+  if (k < 0) k = 0;
+  if (k > kThresholds - 1) k = kThresholds - 1;
+  while (k > 0 && pv >= thr.thr[k - 1]) --k;
+  while (k < kThresholds - 1 && !(pv >= thr.thr[k])) ++k;
+  return (uint32_t)k;
+}
+
+__device__ __forceinline__ uint32_t scaled_dim(uint32_t n, uint32_t k) {  // operations.rs:150-151
+  if (k >= 32) return 1;
+  uint32_t d = (uint32_t)(((uint64_t)n + ((1ull << k) - 1)) >> k);
+  return d < 1 ? 1 : d;
+}
+
+__device__ __forceinline__ void map_values(const ValueMap& vm, const float* minmax, float rx, float ry, float& v0,
+                                           float& v1) {
+  if (vm.normalise) {
+    // extension: v' = (v - min) / (max - min), 0 when the range is empty
+    const float mnx = minmax[0], mxx = -minmax[1];
+    const float rgx = __fsub_rn(mxx, mnx);
+    rx = (rgx > 0.f) ? __fdiv_rn(__fsub_rn(rx, mnx), rgx) : 0.f;
+    if (vm.mode == 2) {
+      const float mny = minmax[2], mxy = -minmax[3];
+      const float rgy = __fsub_rn(mxy, mny);
+      ry = (rgy > 0.f) ? __fdiv_rn(__fsub_rn(ry, mny), rgy) : 0.f;
+    }
+  }
+  if (vm.mode == 0) {
+    v0 = v1 = __fmul_rn(__fmul_rn(rx, vm.factor), 10.0f);  // pixlzr.rs:162
+  } else if (vm.mode == 1) {
+    v0 = v1 = rx;  // process/mod.rs:110
+  } else {
+    v0 = __fmul_rn(rx, vm.factor);  // pixlzr.rs:199
+    v1 = __fmul_rn(ry, vm.factor);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Oklab MAD, reference-order path: plain IEEE f32 evaluated exactly as the reference does —
+// no fma, pre-2.41 glibc cbrtf (double polynomial + one Halley step), sequential running sums in
+// block scan order — so the value is bit-identical to the CPU result.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cbrtf_ref(float x) {  // x >= 0, finite
+  if (x == 0.0f) return 0.0f;
+  int xe;
+  const float xm = frexpf(x, &xe);
+  const double dxm = (double)xm;
+  const float u = __double2float_rn(__dadd_rn(
+      0.492659620528969547, __dmul_rn(__dsub_rn(0.697570460207922770, __dmul_rn(0.191502161678719066, dxm)), dxm)));
+  const float t2 = __fmul_rn(__fmul_rn(u, u), u);
+  const double dt2 = (double)t2;
+  const int rem = xe % 3;  // C truncation, as glibc
+  const double factor = rem == -2 ? 0.62996052494743658238361
+                      : rem == -1 ? 0.79370052598409973737585
+                      : rem == 0  ? 1.0
+                      : rem == 1  ? 1.2599210498948731647672
+                                  : 1.5874010519681994747517;
+  const double num = __dmul_rn((double)u, __dadd_rn(dt2, __dmul_rn(2.0, dxm)));
+  const double den = __dadd_rn(__dmul_rn(2.0, dt2), dxm);
+  const float ym = __double2float_rn(__dmul_rn(__ddiv_rn(num, den), factor));
+  return ldexpf(ym, xe / 3);
+}
+
+__device__ __forceinline__ void oklab_ref(const float* lut, uint32_t r8, uint32_t g8, uint32_t b8, float& L, float& A,
+                                          float& B) {
+  const float r = lut[r8], g = lut[g8], b = lut[b8];
+  const float l = __fadd_rn(__fadd_rn(__fmul_rn(M1_00, r), __fmul_rn(M1_01, g)), __fmul_rn(M1_02, b));
+  const float m = __fadd_rn(__fadd_rn(__fmul_rn(M1_10, r), __fmul_rn(M1_11, g)), __fmul_rn(M1_12, b));
+  const float s = __fadd_rn(__fadd_rn(__fmul_rn(M1_20, r), __fmul_rn(M1_21, g)), __fmul_rn(M1_22, b));
+  const float l_ = cbrtf_ref(l), m_ = cbrtf_ref(m), s_ = cbrtf_ref(s);
+  // `a*x + b*y - c*z` in the reference's source; the negative constants are written as subtractions
+  L = __fsub_rn(__fadd_rn(__fmul_rn(M2_00, l_), __fmul_rn(M2_01, m_)), __fmul_rn(0.0040720468f, s_));
+  A = __fadd_rn(__fsub_rn(__fmul_rn(M2_10, l_), __fmul_rn(2.4285922050f, m_)), __fmul_rn(M2_12, s_));
+  B = __fsub_rn(__fadd_rn(__fmul_rn(M2_20, l_), __fmul_rn(M2_21, m_)), __fmul_rn(0.8086757660f, s_));
+}
+
+constexpr int kExactChunk = 4096;             // pixels staged per pass
+constexpr int kExactStride = kExactChunk + 1; // +1: the 4 channel lanes hit different banks
+
+template <int C>
+__device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, const Tile& t, float* s_val /*[4][stride]*/,
+                                const float* s_lut256, float* s_avg /*[4]*/) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t npx = t.tw * t.th;
+  const float count = (float)npx;
+  const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
+  float run = 0.0f;  // lane c of warp 0 carries channel c: 0 = a, 1 = b, 2 = l, 3 = alpha
+  for (int pass = 0; pass < 2; ++pass) {
+    run = 0.0f;
+    for (uint32_t c0 = 0; c0 < npx; c0 += kExactChunk) {
+      const uint32_t n = min((uint32_t)kExactChunk, npx - c0);
+      // stage the chunk (skipped in pass 2 when the whole tile is still resident)
+      if (pass == 0 || npx > (uint32_t)kExactChunk) {
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+          const uint32_t idx = c0 + i;
+          const uint32_t y = idx / t.tw, x = idx - y * t.tw;
+          const uint8_t* p = base + (size_t)y * pitch + (size_t)x * C;
+          float L, A, B;
+          oklab_ref(s_lut256, p[0], p[1], p[2], L, A, B);
+          s_val[0 * kExactStride + i] = A;
+          s_val[1 * kExactStride + i] = B;
+          s_val[2 * kExactStride + i] = L;
+          if (C == 4) s_val[3 * kExactStride + i] = __fmul_rn((float)p[3], kInv255);
+        }
+        __syncthreads();
+      }
+      if (pass == 1) {
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) s_val[c * kExactStride + i] = fabsf(__fsub_rn(s_val[c * kExactStride + i], s_avg[c]));
+        }
+        __syncthreads();
+      }
+      if (warp == 0 && lane < C) {
+        const float* p = s_val + lane * kExactStride;
+        float s = run;
+        uint32_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+          const float a0 = p[i], a1 = p[i + 1], a2 = p[i + 2], a3 = p[i + 3];
+          const float a4 = p[i + 4], a5 = p[i + 5], a6 = p[i + 6], a7 = p[i + 7];
+          s = __fadd_rn(s, a0); s = __fadd_rn(s, a1); s = __fadd_rn(s, a2); s = __fadd_rn(s, a3);
+          s = __fadd_rn(s, a4); s = __fadd_rn(s, a5); s = __fadd_rn(s, a6); s = __fadd_rn(s, a7);
+        }
+        for (; i < n; ++i) s = __fadd_rn(s, p[i]);
+        run = s;
+      }
+      __syncthreads();
+    }
+    if (pass == 0) {
+      if (warp == 0 && lane < C) s_avg[lane] = __fdiv_rn(run, count);  // operations.rs:65-68
+      __syncthreads();
+    }
+  }
+  // operations.rs:89 / :124  (d_a + d_b + d_l [+ d_alpha]) / count, left to right
+  float result = 0.f;
+  if (warp == 0) {
+    const float d0 = __shfl_sync(0xffffffffu, run, 0), d1 = __shfl_sync(0xffffffffu, run, 1);
+    const float d2 = __shfl_sync(0xffffffffu, run, 2), d3 = __shfl_sync(0xffffffffu, run, 3);
+    float tot = __fadd_rn(__fadd_rn(d0, d1), d2);
+    if (C == 4) tot = __fadd_rn(tot, d3);
+    result = __fdiv_rn(tot, count);
+  }
+  return result;  // valid in warp 0
+}
+
+// tiles whose fast value could round to a different level than the reference-order value
+__device__ __forceinline__ bool in_guard_band(float raw, const Tile& t, const ValueMap& vm, const LevelThresholds& thr,
+                                              const GuardBand& band, const float* minmax) {
+  float v0, v1;
+  map_values(vm, minmax, raw, raw, v0, v1);
+  const float pv = parse_value_dev(v0);
+  if (pv != pv) return true;
+  const float scale = (vm.mode == 0) ? fabsf(vm.factor) * 10.0f : 1.0f;
+  const float tol = band.rel * fabsf(pv) + band.abs_raw * scale;
+  // only thresholds that change the size of this tile matter
+  uint32_t n = max(t.tw, t.th);
+  int kmax = 0;
+  while ((1u << kmax) < n) ++kmax;  // dims are 1 for every k >= ceil(log2 n)
+  if (kmax > kThresholds - 1) kmax = kThresholds - 1;
+  for (int k = 0; k < kmax; ++k) {  // thr[k] separates level k+1 (below) from k (at or above)
+    if (fabsf(pv - thr.thr[k]) <= tol) return true;
+  }
+  // the kink of parse_value at v = -1 (1 + v = 0) maps to 1 px on both sides; v = -0 is exact
+  return false;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_mad_exact(const uint8_t* __restrict__ img, size_t pitch, Geom g, float* vx,
+                                                        const float* vx_fast, ValueMap vm, LevelThresholds thr,
+                                                        GuardBand band, const float* minmax) {
+  extern __shared__ float s_dyn[];
+  float* s_val = s_dyn;  // 4 * kExactStride
+  __shared__ float s_lut256[256];
+  __shared__ float s_avg[4];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut256[i] = c_srgb_lut[i];
+  __syncthreads();
+  const uint32_t ntiles = g.cols * g.rows;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const Tile t = tile_of(g, tile);
+    if (vx_fast != nullptr) {
+      if (!in_guard_band(vx_fast[tile], t, vm, thr, band, minmax)) continue;  // CTA-uniform
+    }
+    const float v = mad_exact_tile<C>(img, pitch, t, s_val, s_lut256, s_avg);
+    if (threadIdx.x == 0) vx[tile] = v;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Directional Sobel metric (operations.rs:192-259): integer sums, one f64 divide.  Alpha ignored.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_analyze_sobel(const uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                            float* __restrict__ vx, float* __restrict__ vy) {
+  __shared__ unsigned long long s_red[kThreads / 32][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ntiles = g.cols * g.rows;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const Tile t = tile_of(g, tile);
+    const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
+    unsigned long long shz = 0, svr = 0;
+    if (t.tw >= 3 && t.th >= 3) {
+      const uint32_t ww = t.tw - 2, wh = t.th - 2;
+      // one thread per window column, walking down: the three rows are kept in registers
+      for (uint32_t x = tid; x < ww; x += kThreads) {
+        int r0[3][3], r1[3][3];  // [dx][channel] of rows y, y+1
+        const uint8_t* p = base + (size_t)x * C;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { r0[dx][c] = p[dx * C + c]; r1[dx][c] = p[pitch + dx * C + c]; }
+        uint32_t ahz = 0, avr = 0;
+        for (uint32_t y = 0; y < wh; ++y) {
+          const uint8_t* q = p + (size_t)(y + 2) * pitch;
+          int r2[3][3];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) r2[dx][c] = q[dx * C + c];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int hz = -r0[0][c] - 2 * r0[1][c] - r0[2][c] + r2[0][c] + 2 * r2[1][c] + r2[2][c];  // :240-241
+            const int vr = -r0[0][c] - 2 * r1[0][c] - r2[0][c] + r0[2][c] + 2 * r1[2][c] + r2[2][c];  // :244-245
+            ahz += (uint32_t)abs(hz);
+            avr += (uint32_t)abs(vr);
+          }
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { r0[dx][c] = r1[dx][c]; r1[dx][c] = r2[dx][c]; }
+          if ((y & 1023u) == 1023u) { shz += ahz; svr += avr; ahz = avr = 0; }  // u32 cannot overflow in 1024 rows
+        }
+        shz += ahz;
+        svr += avr;
+      }
+    }
+    shz = warp_sum_u64(shz);
+    svr = warp_sum_u64(svr);
+    if (lane == 0) { s_red[warp][0] = shz; s_red[warp][1] = svr; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long a = 0, b = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) { a += s_red[w][0]; b += s_red[w][1]; }
+      const unsigned long long f = (unsigned long long)(t.tw - 2) * (unsigned long long)(t.th - 2) * 4096ull;  // :158,:253-254
+      if (t.tw < 3 || t.th < 3 || f == 0) {
+        // width or height == 2: the reference divides 0/0 (x86: negative quiet NaN)
+        vx[tile] = __uint_as_float(0xFFC00000u);
+        vy[tile] = __uint_as_float(0xFFC00000u);
+      } else {
+        vx[tile] = __double2float_rn(__ddiv_rn((double)a, (double)f));
+        vy[tile] = __double2float_rn(__ddiv_rn((double)b, (double)f));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// min / -max of the raw values (normalise extension).  out = {min_x, -max_x, min_y, -max_y}, so a
+// single ncclMin all-reduce of 4 floats finishes the job across ranks.  NaNs are ignored.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_minmax(const float* __restrict__ vx, const float* __restrict__ vy, uint32_t n,
+                                                 float* __restrict__ out4) {
+  __shared__ float s[32][4];
+  float m[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = vx[i], b = vy ? vy[i] : a;
+    if (a == a) { m[0] = fminf(m[0], a); m[1] = fminf(m[1], -a); }
+    if (b == b) { m[2] = fminf(m[2], b); m[3] = fminf(m[3], -b); }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[k] = fminf(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < 4; ++k) s[warp][k] = m[k];
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float r = INFINITY;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fminf(r, s[w][threadIdx.x]);
+    out4[threadIdx.x] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: reduce_image_section minus the resize (operations.rs:140-156) + exclusive scan of the
+// payload sizes (single pass, decoupled look-back), producing the descriptor table.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlanItems = 4;
+constexpr int kPlanTile = kThreads * kPlanItems;
+
+struct ScanState {
+  unsigned int ticket;
+  unsigned int pad;
+  unsigned long long status[1];  // [num_tiles]: flag << 62 | value ; flag 1 = aggregate, 2 = inclusive prefix
+};
+
+__global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx, const float* __restrict__ vy, Geom g,
+                                                   ValueMap vm, const float* __restrict__ minmax, LevelThresholds thr,
+                                                   pxz_block_desc* __restrict__ descs, uint32_t* __restrict__ tabidx,
+                                                   unsigned long long* __restrict__ total, ScanState* st) {
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_warp[kThreads / 32];
+  __shared__ unsigned long long s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&st->ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t nblocks = g.cols * g.rows;
+  const uint32_t first = tile * kPlanTile + tid * kPlanItems;
+
+  uint32_t dw[kPlanItems], dh[kPlanItems], tix[kPlanItems];
+  float val[kPlanItems];
+  unsigned long long sz[kPlanItems];
+  unsigned long long tsum = 0;
+#pragma unroll
+  for (int j = 0; j < kPlanItems; ++j) {
+    const uint32_t b = first + j;
+    sz[j] = 0;
+    if (b < nblocks) {
+      const Tile t = tile_of(g, b);
+      float v0, v1;
+      map_values(vm, minmax, vx[b], vy ? vy[b] : vx[b], v0, v1);
+      const float p0 = parse_value_dev(v0), p1 = parse_value_dev(v1);
+      const uint32_t k0 = level_k(p0, thr), k1 = level_k(p1, thr);
+      dw[j] = scaled_dim(t.tw, k0);
+      dh[j] = scaled_dim(t.th, k1);
+      // f32::hypot (operations.rs:154)
+      val[j] = (isinf(p0) || isinf(p1)) ? INFINITY
+                                        : __double2float_rn(sqrt(__dadd_rn(__dmul_rn((double)p0, (double)p0),
+                                                                           __dmul_rn((double)p1, (double)p1))));
+      const uint32_t cx = (t.tw != g.bw) ? 1u : 0u, cy = (t.th != g.bh) ? 1u : 0u;
+      const uint32_t ix = (0u * 2u + cx) * kLevelsPerClass + min(k0, (uint32_t)kMaxLevel);
+      const uint32_t iy = (1u * 2u + cy) * kLevelsPerClass + min(k1, (uint32_t)kMaxLevel);
+      tix[j] = ix | (iy << 16);
+      sz[j] = (unsigned long long)dw[j] * dh[j] * g.C;
+      tsum += sz[j];
+    }
+  }
+  // block-wide exclusive scan of tsum
+  unsigned long long inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned long long wbase = 0, agg = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    if (w < warp) wbase += s_warp[w];
+    agg += s_warp[w];
+  }
+  unsigned long long excl = wbase + inc - tsum;
+
+  if (tid == 0) {
+    unsigned long long prefix = 0;
+    volatile unsigned long long* status = st->status;
+    if (tile == 0) {
+      __threadfence();
+      status[0] = (2ull << 62) | agg;
+    } else {
+      status[tile] = (1ull << 62) | agg;
+      __threadfence();
+      int p = (int)tile - 1;
+      while (true) {
+        unsigned long long s;
+        do { s = status[p]; } while ((s >> 62) == 0ull);
+        prefix += s & ((1ull << 62) - 1);
+        if ((s >> 62) == 2ull) break;
+        --p;
+      }
+      __threadfence();
+      status[tile] = (2ull << 62) | (prefix + agg);
+    }
+    s_prefix = prefix;
+    if ((tile + 1) * (uint32_t)kPlanTile >= nblocks) *total = prefix + agg;
+  }
+  __syncthreads();
+  excl += s_prefix;
+#pragma unroll
+  for (int j = 0; j < kPlanItems; ++j) {
+    const uint32_t b = first + j;
+    if (b < nblocks) {
+      pxz_block_desc d;
+      d.offset = excl;
+      d.value = val[j];
+      d.w = (uint16_t)dw[j];
+      d.h = (uint16_t)dh[j];
+      descs[b] = d;
+      tabidx[b] = tix[j];
+      excl += sz[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// resample: image 0.25.5 imageops::resize restated for one block — vertical pass into an unrounded
+// f32 intermediate, then horizontal pass, sequential f32 accumulation (no fma) with host-built
+// normalised weights, clamp + round half away from zero.  Same-size blocks are copied
+// (block.rs:279-281).  direction 0: tile of the image -> payload; 1: payload -> tile of the image.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_u8(float t) {
+  t = fminf(fmaxf(t, 0.0f), 255.0f);
+  const int r = (int)t;
+  return (uint32_t)(r + ((t - (float)r) >= 0.5f ? 1 : 0));
+}
+
+template <int C>
+__device__ __forceinline__ void load_px(const uint8_t* p, float (&f)[C]) {
+  if (C == 4) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+    f[0] = byte_to_float<0>(w);
+    f[1] = byte_to_float<1>(w);
+    f[2] = byte_to_float<2>(w);
+    f[3] = byte_to_float<3>(w);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) f[c] = (float)p[c];
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_resample(int direction, uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                       const pxz_block_desc* __restrict__ descs,
+                                                       const uint32_t* __restrict__ tabidx, uint8_t* __restrict__ payload,
+                                                       const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool,
+                                                       uint32_t max_src_px, uint32_t max_tmp_px, uint8_t* scratch,
+                                                       size_t scratch_per_cta) {
+  extern __shared__ float s_dyn[];
+  float* s_src;
+  float* s_tmp;
+  if (scratch != nullptr) {  // tiles too large for shared memory: per-CTA global scratch
+    s_src = reinterpret_cast<float*>(scratch + (size_t)blockIdx.x * scratch_per_cta);
+    s_tmp = s_src + (size_t)max_src_px * C;
+  } else {
+    s_src = s_dyn;
+    s_tmp = s_dyn + (size_t)max_src_px * C;
+  }
+  const int tid = threadIdx.x;
+  const uint32_t nblocks = g.cols * g.rows;
+  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const Tile t = tile_of(g, b);
+    const pxz_block_desc d = descs[b];
+    uint8_t* tile_ptr = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
+    uint8_t* blk_ptr = payload + d.offset;
+    const uint8_t* src;
+    uint8_t* dst;
+    size_t spitch, dpitch;
+    uint32_t sw, sh, dw, dh;
+    if (direction == 0) {
+      src = tile_ptr; spitch = pitch; sw = t.tw; sh = t.th;
+      dst = blk_ptr; dpitch = (size_t)d.w * C; dw = d.w; dh = d.h;
+    } else {
+      src = blk_ptr; spitch = (size_t)d.w * C; sw = d.w; sh = d.h;
+      dst = tile_ptr; dpitch = pitch; dw = t.tw; dh = t.th;
+    }
+    if (sw == dw && sh == dh) {  // block.rs:279-281
+      if (C == 4) {
+        for (uint32_t i = tid; i < sw * sh; i += kThreads) {
+          const uint32_t y = i / sw, x = i - y * sw;
+          *reinterpret_cast<uint32_t*>(dst + (size_t)y * dpitch + (size_t)x * 4) =
+              *reinterpret_cast<const uint32_t*>(src + (size_t)y * spitch + (size_t)x * 4);
+        }
+      } else {
+        const uint32_t rb = sw * C;
+        for (uint32_t i = tid; i < rb * sh; i += kThreads) {
+          const uint32_t y = i / rb, x = i - y * rb;
+          dst[(size_t)y * dpitch + x] = src[(size_t)y * spitch + x];
+        }
+      }
+      continue;
+    }
+    const uint32_t ti = tabidx[b];
+    const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
+    const uint32_t* ly = pool + ty.off;
+    const uint32_t* cy = ly + ty.n_out;
+    const float* wy = reinterpret_cast<const float*>(cy + ty.n_out);
+    const uint32_t* lx = pool + tx.off;
+    const uint32_t* cx = lx + tx.n_out;
+    const float* wx = reinterpret_cast<const float*>(cx + tx.n_out);
+
+    // phase 0: stage the source block as f32
+    for (uint32_t i = tid; i < sw * sh; i += kThreads) {
+      const uint32_t y = i / sw, x = i - y * sw;
+      float f[C];
+      load_px<C>(src + (size_t)y * spitch + (size_t)x * C, f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) s_src[(size_t)i * C + c] = f[c];
+    }
+    __syncthreads();
+    // phase 1: vertical_sample -> f32 [dh][sw]
+    for (uint32_t i = tid; i < dh * sw; i += kThreads) {
+      const uint32_t oy = i / sw, x = i - oy * sw;
+      const uint32_t left = ly[oy], cnt = cy[oy];
+      const float* w = wy + (size_t)oy * ty.stride;
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+      const float* sp = s_src + ((size_t)left * sw + x) * C;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const float wk = w[k];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(sp[c], wk));
+        sp += (size_t)sw * C;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) s_tmp[(size_t)i * C + c] = acc[c];
+    }
+    __syncthreads();
+    // phase 2: horizontal_sample -> u8 [dh][dw]
+    for (uint32_t i = tid; i < dh * dw; i += kThreads) {
+      const uint32_t oy = i / dw, ox = i - oy * dw;
+      const uint32_t left = lx[ox], cnt = cx[ox];
+      const float* w = wx + (size_t)ox * tx.stride;
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+      const float* sp = s_tmp + ((size_t)oy * sw + left) * C;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const float wk = w[k];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(sp[c], wk));
+        sp += C;
+      }
+      uint8_t* o = dst + (size_t)oy * dpitch + (size_t)ox * C;
+      if (C == 4) {
+        *reinterpret_cast<uint32_t*>(o) = to_u8(acc[0]) | (to_u8(acc[1]) << 8) | (to_u8(acc[2]) << 16) | (to_u8(acc[3]) << 24);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[c] = (uint8_t)to_u8(acc[c]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static inline int clamp_grid(long long want, long long cap) { return (int)(want < 1 ? 1 : (want > cap ? cap : want)); }
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, cudaStream_t s,
+                                    int sm_count, uint64_t* launches) {
+  const uint32_t ntiles = g.cols * g.rows;
+  const size_t smem = 256 * 32 * sizeof(float);
+  const bool aligned = g.C == 4 && (g.bw % 4 == 0) && (g.W % 4 == 0) && (pitch % 16 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
+  const uint32_t quads = (g.bw / 4) * g.bh;
+  cudaError_t e = cudaSuccess;
+  ++*launches;
+  if (aligned && quads <= 1024) {
+    // G threads per tile, <= 4 quads (16 px) per thread
+    if (quads > 512) {
+      e = set_smem(k_analyze_mad_rgba<256, 4>, smem);
+      if (e != cudaSuccess) return e;
+      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+    } else if (quads > 256) {
+      e = set_smem(k_analyze_mad_rgba<128, 4>, smem);
+      if (e != cudaSuccess) return e;
+      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+    } else if (quads > 128) {
+      e = set_smem(k_analyze_mad_rgba<64, 4>, smem);
+      if (e != cudaSuccess) return e;
+      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+    } else {
+      e = set_smem(k_analyze_mad_rgba<32, 4>, smem);
+      if (e != cudaSuccess) return e;
+      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+    }
+  } else if (g.C == 4) {
+    e = set_smem(k_analyze_mad_any<4>, smem);
+    if (e != cudaSuccess) return e;
+    k_analyze_mad_any<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+  } else {
+    e = set_smem(k_analyze_mad_any<3>, smem);
+    if (e != cudaSuccess) return e;
+    k_analyze_mad_any<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
+                                     const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
+                                     const float* minmax, cudaStream_t s, int sm_count, uint64_t* launches) {
+  const uint32_t ntiles = g.cols * g.rows;
+  const size_t smem = (size_t)4 * kExactStride * sizeof(float);
+  ValueMap v{1.0f, 1, 0};
+  LevelThresholds t{};
+  GuardBand b{0.f, 0.f};
+  if (vm) v = *vm;
+  if (thr) t = *thr;
+  if (band) b = *band;
+  cudaError_t e;
+  ++*launches;
+  if (g.C == 4) {
+    e = set_smem(k_mad_exact<4>, smem);
+    if (e != cudaSuccess) return e;
+    k_mad_exact<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, v, t, b, minmax);
+  } else {
+    e = set_smem(k_mad_exact<3>, smem);
+    if (e != cudaSuccess) return e;
+    k_mad_exact<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, v, t, b, minmax);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g, float* vx, float* vy, cudaStream_t s,
+                                 int sm_count, uint64_t* launches) {
+  const uint32_t ntiles = g.cols * g.rows;
+  ++*launches;
+  if (g.C == 4)
+    k_analyze_sobel<4><<<clamp_grid(ntiles, sm_count * 8), kThreads, 0, s>>>(img, pitch, g, vx, vy);
+  else
+    k_analyze_sobel<3><<<clamp_grid(ntiles, sm_count * 8), kThreads, 0, s>>>(img, pitch, g, vx, vy);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* minmax4, cudaStream_t s, uint64_t* launches) {
+  ++*launches;
+  k_minmax<<<1, 1024, 0, s>>>(vx, vy, n, minmax4);
+  return cudaGetLastError();
+}
+
+size_t plan_scan_state_bytes(uint32_t nblocks) {
+  const uint32_t tiles = (nblocks + kPlanTile - 1) / kPlanTile;
+  return sizeof(ScanState) + (size_t)tiles * sizeof(unsigned long long);
+}
+
+cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
+                        const LevelThresholds& thr, pxz_block_desc* descs, uint32_t* tabidx, uint64_t* total_bytes,
+                        void* scan_state, cudaStream_t s, uint64_t* launches) {
+  const uint32_t nblocks = g.cols * g.rows;
+  const uint32_t tiles = (nblocks + kPlanTile - 1) / kPlanTile;
+  cudaError_t e = cudaMemsetAsync(scan_state, 0, plan_scan_state_bytes(nblocks), s);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  k_plan<<<tiles, kThreads, 0, s>>>(vx, vy, g, vm, minmax, thr, descs, tabidx,
+                                    reinterpret_cast<unsigned long long*>(total_bytes),
+                                    reinterpret_cast<ScanState*>(scan_state));
+  return cudaGetLastError();
+}
+
+size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C) {
+  return ((size_t)max_src_px + max_tmp_px) * C * sizeof(float);
+}
+
+int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (long long)sm_count * 8); }
+
+cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
+                            const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
+                            uint32_t max_src_px, uint32_t max_tmp_px, uint8_t* scratch, size_t scratch_per_cta,
+                            int grid, cudaStream_t s, int sm_count, uint64_t* launches) {
+  (void)sm_count;
+  const size_t smem = scratch ? 0 : resample_smem_bytes(max_src_px, max_tmp_px, g.C);
+  cudaError_t e;
+  ++*launches;
+  if (g.C == 4) {
+    e = set_smem(k_resample<4>, smem);
+    if (e != cudaSuccess) return e;
+    k_resample<4><<<grid, kThreads, smem, s>>>(direction, img, pitch, g, descs, tabidx, payload, tabs, pool, max_src_px,
+                                              max_tmp_px, scratch, scratch_per_cta);
+  } else {
+    e = set_smem(k_resample<3>, smem);
+    if (e != cudaSuccess) return e;
+    k_resample<3><<<grid, kThreads, smem, s>>>(direction, img, pitch, g, descs, tabidx, payload, tabs, pool, max_src_px,
+                                              max_tmp_px, scratch, scratch_per_cta);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace pxz

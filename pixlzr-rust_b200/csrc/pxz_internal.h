@@ -1,0 +1,72 @@
+// pxz_internal.h — shared between the host side (abi.cpp, tables.cpp) and the kernels (kernels.cu).
+// Not part of the public ABI (that is include/pixlzr_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/pixlzr_b200.h"
+
+namespace pxz {
+
+constexpr int kMaxLevel = 16;              // level exponents 0..16 get their own resample table
+constexpr int kLevelsPerClass = kMaxLevel + 1;
+constexpr int kThresholds = 41;            // thr[k], k = 0..40: smallest f32 v with round(log2 v) >= -k
+constexpr uint32_t kLevelOnePixel = 0xFFu; // "level 0" / below every threshold: 1 px
+
+// One axis of a separable resample: n_in source samples -> n_out outputs.
+// Pool layout at `off` (32-bit words): left[n_out] | count[n_out] | weights[n_out * stride] (f32 bits).
+struct AxisTab {
+  uint32_t n_in, n_out, stride, off;
+};
+
+// Geometry of the block grid over a pitched image.
+struct Geom {
+  uint32_t W, H, bw, bh, cols, rows, C;
+  uint32_t trail_w, trail_h;  // W % bw, H % bh (0 = no trailing column / row)
+};
+
+// How raw metric values become (v0, v1): pixlzr.rs:162 (`x * factor * 10`), :199 (`x * factor`),
+// process/mod.rs:110 (identity); optional global normalisation first (extension).
+struct ValueMap {
+  float factor;
+  int mode;       // 0: MAD * factor * 10 | 1: MAD identity | 2: Sobel (hz,vr) * factor
+  int normalise;  // 0/1; minmax = {min_x, -max_x, min_y, -max_y} on device
+};
+
+struct LevelThresholds {
+  float thr[kThresholds];
+};
+
+// Guard band of the fast Oklab-MAD path (DESIGN.md "exactness"): a block is recomputed in
+// reference order when its fast value is within  rel * v + abs_raw * scale  of a threshold.
+struct GuardBand {
+  float rel;
+  float abs_raw;
+};
+
+// ---- kernel launchers (kernels.cu) ---------------------------------------------------------
+// All return cudaGetLastError() of the launch; *launches is incremented per kernel launched.
+cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, cudaStream_t s,
+                                    int sm_count, uint64_t* launches);
+cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
+                                     const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
+                                     const float* minmax, cudaStream_t s, int sm_count, uint64_t* launches);
+cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g, float* vx, float* vy, cudaStream_t s,
+                                 int sm_count, uint64_t* launches);
+cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* minmax4, cudaStream_t s,
+                          uint64_t* launches);
+cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
+                        const LevelThresholds& thr, pxz_block_desc* descs, uint32_t* tabidx, uint64_t* total_bytes,
+                        void* scan_state, cudaStream_t s, uint64_t* launches);
+size_t plan_scan_state_bytes(uint32_t nblocks);
+// direction 0: image tiles -> payload (shrink); 1: payload -> image tiles (expand)
+cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
+                            const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
+                            uint32_t max_src_px, uint32_t max_tmp_px, uint8_t* scratch, size_t scratch_per_cta,
+                            int grid_hint, cudaStream_t s, int sm_count, uint64_t* launches);
+size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
+int resample_grid(int sm_count, uint32_t nblocks);
+
+}  // namespace pxz

@@ -1,0 +1,139 @@
+// tables.cpp — host-side parameter setup for the kernels (O(block size) work, no pixel data):
+//   * per-axis resample tables (tap ranges + normalised f32 weights) for the `image`-crate
+//     semantics of PixlzrBlock::resize (src/data_types/block.rs:282-290 -> image 0.25.5
+//     imageops::sample::{vertical_sample, horizontal_sample});
+//   * the value -> level thresholds of reduce_image_section (src/operations.rs:147-148).
+// The kernels apply these tables in the reference's accumulation order, which is what makes the
+// resampled pixels bit-identical to the CPU result.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pxz_host.h"
+
+namespace pxz {
+
+namespace {
+
+const float kPi = 3.14159274101257324219f;  // f32::consts::PI
+
+// image 0.25.5 imageops/sample.rs kernels, evaluated in f32
+struct KernelFn {
+  float support;
+  float (*eval)(float);
+};
+
+float eval_box(float) { return 1.0f; }
+float eval_triangle(float x) {
+  const float a = fabsf(x);
+  return a < 1.0f ? 1.0f - a : 0.0f;
+}
+float eval_catmullrom(float x) {  // bc_cubic_spline(x, 0.0, 0.5)
+  const float a = fabsf(x);
+  float k = 0.0f;
+  if (a < 1.0f) {
+    const float a2 = a * a, a3 = a2 * a;
+    k = 9.0f * a3 + -15.0f * a2 + 6.0f;
+  } else if (a < 2.0f) {
+    const float a2 = a * a, a3 = a2 * a;
+    k = -3.0f * a3 + 15.0f * a2 + -24.0f * a + 12.0f;
+  }
+  return k / 6.0f;
+}
+float eval_gaussian(float x) {  // gaussian(x, 0.5)
+  const float r = 0.5f;
+  const float scale = 1.0f / (sqrtf(2.0f * kPi) * r);
+  return scale * expf(-(x * x) / (2.0f * (r * r)));
+}
+float sinc_f32(float t) {
+  const float a = t * kPi;
+  return t == 0.0f ? 1.0f : sinf(a) / a;
+}
+float eval_lanczos3(float x) { return fabsf(x) < 3.0f ? sinc_f32(x) * sinc_f32(x / 3.0f) : 0.0f; }
+
+bool kernel_of(int filter, KernelFn* k) {
+  switch (filter) {
+    case PXZ_NEAREST: *k = {0.0f, eval_box}; return true;
+    case PXZ_TRIANGLE: *k = {1.0f, eval_triangle}; return true;
+    case PXZ_CATMULLROM: *k = {2.0f, eval_catmullrom}; return true;
+    case PXZ_GAUSSIAN: *k = {3.0f, eval_gaussian}; return true;
+    case PXZ_LANCZOS3: *k = {3.0f, eval_lanczos3}; return true;
+  }
+  return false;
+}
+
+}  // namespace
+
+bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uint32_t>* pool, AxisTab* tab) {
+  KernelFn kf;
+  if (!kernel_of(filter, &kf) || n_in == 0 || n_out == 0) return false;
+  const float ratio = (float)n_in / (float)n_out;
+  const float sratio = ratio < 1.0f ? 1.0f : ratio;
+  const float reach = kf.support * sratio;
+
+  // first sweep: tap ranges, to size the weight rows
+  std::vector<uint32_t> lefts(n_out), counts(n_out);
+  uint32_t stride = 1;
+  for (uint32_t o = 0; o < n_out; ++o) {
+    const float centre = ((float)o + 0.5f) * ratio;
+    long long lo = (long long)floorf(centre - reach);
+    if (lo < 0) lo = 0;
+    if (lo > (long long)n_in - 1) lo = (long long)n_in - 1;
+    long long hi = (long long)ceilf(centre + reach);
+    if (hi < lo + 1) hi = lo + 1;
+    if (hi > (long long)n_in) hi = (long long)n_in;
+    lefts[o] = (uint32_t)lo;
+    counts[o] = (uint32_t)(hi - lo);
+    if (counts[o] > stride) stride = counts[o];
+  }
+  tab->n_in = n_in;
+  tab->n_out = n_out;
+  tab->stride = stride;
+  tab->off = (uint32_t)pool->size();
+  pool->insert(pool->end(), lefts.begin(), lefts.end());
+  pool->insert(pool->end(), counts.begin(), counts.end());
+  const size_t wbase = pool->size();
+  pool->resize(wbase + (size_t)n_out * stride, 0u);
+  // second sweep: weights, normalised by their sequential f32 sum
+  std::vector<float> row(stride);
+  for (uint32_t o = 0; o < n_out; ++o) {
+    const float centre = ((float)o + 0.5f) * ratio - 0.5f;
+    float total = 0.0f;
+    for (uint32_t i = 0; i < counts[o]; ++i) {
+      const float w = kf.eval(((float)(lefts[o] + i) - centre) / sratio);
+      row[i] = w;
+      total += w;
+    }
+    for (uint32_t i = 0; i < counts[o]; ++i) {
+      const float w = row[i] / total;
+      memcpy(&(*pool)[wbase + (size_t)o * stride + i], &w, sizeof(float));
+    }
+  }
+  return true;
+}
+
+// thr[k] = smallest positive f32 v with round(log2f(v)) >= -k  (round = half away from zero).
+// Built with the host libm exactly as the reference evaluates `value.log2().round()`, so the
+// device-side comparison `v >= thr[k]` reproduces the CPU decision for every f32 input.
+static inline int rounded_log2(float v) { return (int)roundf(log2f(v)); }
+
+void build_level_thresholds(LevelThresholds* out) {
+  for (int k = 0; k < kThresholds; ++k) {
+    // the switch happens between 2^(-k-1) (round(log2) = -k-1) and 2^-k (round(log2) = -k)
+    uint32_t lo, hi;
+    float flo = ldexpf(1.0f, -k - 1), fhi = ldexpf(1.0f, -k);
+    memcpy(&lo, &flo, 4);
+    memcpy(&hi, &fhi, 4);
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      float fm;
+      memcpy(&fm, &mid, 4);
+      if (rounded_log2(fm) >= -k) hi = mid; else lo = mid;
+    }
+    // (tests/test_host_logic.py checks +-4096 ulps around every threshold against log2f itself)
+    memcpy(&out->thr[k], &hi, 4);
+  }
+}
+
+}  // namespace pxz

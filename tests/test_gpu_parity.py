@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the
+reference's golden files.  Bars (BASELINE.json north star): block grid, levels / dims and chosen
+scales bit-exact; stored f32 values bit-exact in exact mode and within 1e-4 relative (+1e-6 abs) in
+the default fast mode; resampled pixels bit-exact with the oracle (the bar is +-1 LSB)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import pixlzr_b200 as P
+from conftest import GOLDEN, load_png
+
+pytestmark = pytest.mark.gpu
+N = P.native
+
+FILTERS = [0, 1, 2, 3, 4]
+# the five (down, up) pairs logged in the reference's strategies.txt
+STRATEGIES = [(0, 0), (1, 0), (2, 4), (4, 2), (4, 4)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return N.Context(0)
+
+
+def synth(w, h, c, seed, kind="mixed"):
+    """Seeded test image: smooth base + per-64x64-region noise of varying amplitude, so that block
+    values spread over many levels."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    base = np.stack([128 + 96 * np.sin(xx / 97.0 + seed), 128 + 96 * np.cos(yy / 131.0), 128 + 64 * np.sin((xx + yy) / 61.0)], -1)
+    if kind == "flat":
+        img = np.full((h, w, 3), 77.0, np.float32)
+    elif kind == "noise":
+        img = rng.integers(0, 256, (h, w, 3)).astype(np.float32)
+    else:
+        amp = rng.choice([0, 1, 2, 4, 8, 16, 32, 64, 128], size=((h + 31) // 32, (w + 31) // 32)).astype(np.float32)
+        amp = np.kron(amp, np.ones((32, 32), np.float32))[:h, :w]
+        img = base + (rng.random((h, w, 3), dtype=np.float32) - 0.5) * 2 * amp[..., None]
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    if c == 4:
+        a = np.full((h, w, 1), 255, np.uint8) if seed % 2 == 0 else rng.integers(0, 256, (h, w, 1), dtype=np.uint8)
+        img = np.concatenate([img, a], -1)
+    return np.ascontiguousarray(img)
+
+
+def rel_close(a, b, rel=1e-4, abs_=1e-6):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.all(np.abs(a - b) <= rel * np.abs(b) + abs_)
+
+
+def gpu_shrink(ctx, img, bw, bh, metric, factor, filt, flags=0):
+    d = ctx.image_upload(img)
+    pl = d.shrink(bw, bh, metric, factor, filt, flags)
+    descs, pixels = pl.download()
+    info = pl.info()
+    pl.free()
+    d.free()
+    return descs, pixels, info
+
+
+def assert_same_payload(descs, pixels, ref, exact_values):
+    assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"]), "dims"
+    assert np.array_equal(descs["offset"], ref.descs["offset"]), "offsets"
+    if exact_values:
+        assert np.array_equal(descs["value"].view("<u4"), ref.descs["value"].view("<u4")), "stored values bit-exact"
+    else:
+        assert rel_close(descs["value"], ref.descs["value"]), "stored values"
+    assert pixels.size == ref.payload.size
+    assert np.array_equal(pixels, ref.payload), "resampled pixels"
+
+
+# ---------------------------------------------------------------------------------------------
+# analysis
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,bs", [("Big-Ruscher.png", 16), ("Big-Ruscher.png", 32), ("Big-Ruscher.png", 64), ("base.png", 64)])
+def test_mad_values_fixture_images(ctx, name, bs):
+    img = load_png(name)
+    want, _ = O.analyze(img, bs, bs, O.METRIC_OKLAB_MAD, nthreads=8)
+    d = ctx.image_upload(img)
+    exact, _ = d.analyze(bs, bs, N.METRIC_OKLAB_MAD, N.FLAG_EXACT_VALUES)
+    fast, _ = d.analyze(bs, bs, N.METRIC_OKLAB_MAD, 0)
+    d.free()
+    assert np.array_equal(exact.view("<u4"), want.view("<u4")), "reference-order path must be bit-exact"
+    assert rel_close(fast, want, rel=2e-4, abs_=2e-6), float(np.max(np.abs(fast - want)))
+
+
+@pytest.mark.parametrize("w,h,c,bw,bh", [(257, 131, 3, 32, 32), (260, 132, 4, 64, 64), (259, 130, 4, 64, 64),
+                                         (100, 70, 4, 16, 8), (96, 96, 4, 128, 128), (300, 300, 3, 200, 100),
+                                         (64, 64, 4, 1, 1), (33, 9, 3, 64, 64), (1, 1, 4, 64, 64), (640, 64, 4, 20, 64)])
+def test_mad_values_ragged_shapes(ctx, w, h, c, bw, bh):
+    img = synth(w, h, c, seed=w * 7 + h)
+    want, _ = O.analyze(img, bw, bh, O.METRIC_OKLAB_MAD, nthreads=8)
+    d = ctx.image_upload(img)
+    exact, _ = d.analyze(bw, bh, N.METRIC_OKLAB_MAD, N.FLAG_EXACT_VALUES)
+    fast, _ = d.analyze(bw, bh, N.METRIC_OKLAB_MAD, 0)
+    d.free()
+    assert np.array_equal(exact.view("<u4"), want.view("<u4"))
+    assert rel_close(fast, want, rel=2e-4, abs_=2e-6), float(np.max(np.abs(fast - want)))
+
+
+@pytest.mark.parametrize("w,h,c,bw,bh", [(1920, 1080, 3, 32, 32), (257, 131, 3, 32, 32), (260, 132, 4, 64, 64), (99, 70, 4, 16, 8),
+                                         (300, 300, 3, 200, 100), (66, 66, 4, 64, 64)])
+def test_sobel_values_bit_exact(ctx, w, h, c, bw, bh):
+    img = load_png("Big-Ruscher.png") if (w, h) == (1920, 1080) else synth(w, h, c, seed=w + h)
+    hz, vr = O.analyze(img, bw, bh, O.METRIC_SOBEL_DIR, nthreads=8)
+    d = ctx.image_upload(img)
+    ghz, gvr = d.analyze(bw, bh, N.METRIC_SOBEL_DIR)
+    d.free()
+    assert np.array_equal(ghz.view("<u4"), hz.view("<u4")) and np.array_equal(gvr.view("<u4"), vr.view("<u4"))
+
+
+def test_sobel_rejects_blocks_thinner_than_two(ctx):
+    d = ctx.image_upload(synth(65, 64, 3, 1))  # trailing column of 1 px: the reference panics
+    with pytest.raises(N.PixlzrError):
+        d.analyze(64, 64, N.METRIC_SOBEL_DIR)
+    d.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# golden files of the reference, through the public API mirror
+# ---------------------------------------------------------------------------------------------
+def test_golden_big_ruscher_pix_exact_mode():
+    """Big-Ruscher.png --from_image(32,32).shrink_by(Lanczos3, 0.125)--> Big-Ruscher.pix, byte for byte."""
+    pix = P.Pixlzr.from_image(load_png("Big-Ruscher.png"), 32, 32)
+    pix.shrink_by(P.FilterType.Lanczos3, 0.125, exact_values=True)
+    assert pix.encode_to_vec() == open(os.path.join(GOLDEN, "Big-Ruscher.pix"), "rb").read()
+
+
+def test_golden_big_ruscher_pix_fast_mode():
+    gold = np.load(os.path.join(GOLDEN, "Big-Ruscher.pix.blocks.npy"))
+    pix = P.Pixlzr.from_image(load_png("Big-Ruscher.png"), 32, 32)
+    pix.shrink_by(P.FilterType.Lanczos3, 0.125)
+    blocks = pix.blocks
+    assert [b.width for b in blocks] == gold[:, 1].tolist() and [b.height for b in blocks] == gold[:, 2].tolist()
+    vals = np.array([b.block_value for b in blocks], np.float32)
+    assert rel_close(vals, gold[:, 0].astype("<u4").view("<f4"))
+    ref, _ = O.container_decode(open(os.path.join(GOLDEN, "Big-Ruscher.pix"), "rb").read())
+    assert np.array_equal(pix._pixels, ref.payload)
+
+
+def test_golden_big_ruscher_pix_png():
+    """Big-Ruscher.pix --to_image(Nearest)--> Big-Ruscher.pix.png"""
+    pix = P.Pixlzr.open(os.path.join(GOLDEN, "Big-Ruscher.pix"))
+    assert np.array_equal(pix.to_image(P.FilterType.Nearest), load_png("Big-Ruscher.pix.png"))
+
+
+@pytest.mark.parametrize("bs", [8, 64])
+def test_identity_roundtrip_image_png(bs, tmp_path):
+    """main.rs:299-356: image -> pix (file) -> image without shrinking is the identity."""
+    img = load_png("image.png")
+    pix = P.Pixlzr.from_image(img, bs, bs)
+    path = tmp_path / "image.pix"
+    pix.save(path)
+    back = P.Pixlzr.open(path)
+    assert np.array_equal(back.to_image(P.FilterType.Nearest), img)
+    assert np.array_equal(back.to_image(P.FilterType.Lanczos3), img)  # full-size blocks: resize is a clone
+
+
+def test_resize_constant_blocks():
+    """block.rs:401-435"""
+    for v in (0, 255):
+        b = P.PixlzrBlock(np.full((100, 100, 3), v, np.uint8))
+        r = b.resize(10, 10, P.FilterType.Lanczos3)
+        assert r.dimensions() == (10, 10) and r.block_value is None and (r.data == v).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# shrink / expand against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bs", [16, 32, 64])
+@pytest.mark.parametrize("down,up", STRATEGIES)
+def test_big_ruscher_all_strategies_mad(ctx, bs, down, up):
+    img = load_png("Big-Ruscher.png")
+    for factor in (1.0, 0.125):
+        ref = O.shrink(img, bs, bs, O.METRIC_OKLAB_MAD, factor, down, nthreads=8)
+        descs, pixels, info = gpu_shrink(ctx, img, bs, bs, N.METRIC_OKLAB_MAD, factor, down)
+        assert_same_payload(descs, pixels, ref, exact_values=False)
+        pl = ctx.payload_upload(1920, 1080, bs, bs, 3, descs, pixels)
+        out = pl.expand(up)
+        pl.free()
+        assert np.array_equal(out, O.expand(ref, up, nthreads=8))
+
+
+@pytest.mark.parametrize("bs", [16, 32, 64])
+@pytest.mark.parametrize("down,up", STRATEGIES)
+def test_big_ruscher_all_strategies_sobel(ctx, bs, down, up):
+    img = load_png("Big-Ruscher.png")
+    ref = O.shrink(img, bs, bs, O.METRIC_SOBEL_DIR, 8.0, down, nthreads=8)
+    descs, pixels, info = gpu_shrink(ctx, img, bs, bs, N.METRIC_SOBEL_DIR, 8.0, down)
+    assert_same_payload(descs, pixels, ref, exact_values=True)
+    pl = ctx.payload_upload(1920, 1080, bs, bs, 3, descs, pixels)
+    out = pl.expand(up)
+    pl.free()
+    assert np.array_equal(out, O.expand(ref, up, nthreads=8))
+
+
+@pytest.mark.parametrize("filt", FILTERS)
+def test_base_png_rgba_bench_parameters(ctx, filt):
+    """config C1: benches/base.png, 64x64 blocks, shrink_by(filter, 0.25 | 1.0) as benches/bench-00.rs:39,83."""
+    img = load_png("base.png")
+    for factor in (0.25, 1.0):
+        ref = O.shrink(img, 64, 64, O.METRIC_OKLAB_MAD, factor, filt, nthreads=8)
+        descs, pixels, info = gpu_shrink(ctx, img, 64, 64, N.METRIC_OKLAB_MAD, factor, filt)
+        assert_same_payload(descs, pixels, ref, exact_values=False)
+        assert info["bytes"] == ref.payload.size and (info["cols"], info["rows"]) == (17, 26)
+    d = ctx.image_upload(img)
+    pl = d.shrink(64, 64, N.METRIC_OKLAB_MAD, 1.0, filt, 0)
+    out = ctx.image_alloc(1080, 1617, 4)
+    pl.expand_to_image(filt, out)  # device-resident encode -> decode, no host round trip
+    got = out.download()
+    pl.free(); out.free(); d.free()
+    assert np.array_equal(got, O.expand(ref, filt, nthreads=8))
+
+
+@pytest.mark.parametrize("w,h,c,bw,bh", [(257, 131, 3, 32, 32), (260, 132, 4, 64, 64), (259, 130, 4, 64, 48),
+                                         (100, 70, 4, 16, 8), (300, 300, 3, 200, 100), (33, 9, 3, 64, 64),
+                                         (1, 1, 4, 64, 64), (130, 5, 4, 64, 64), (640, 128, 4, 20, 64)])
+@pytest.mark.parametrize("filt", [0, 2, 4])
+def test_ragged_shapes_shrink_expand(ctx, w, h, c, bw, bh, filt):
+    img = synth(w, h, c, seed=3 * w + h)
+    for factor, flags in ((2.0, 0), (0.3, N.FLAG_EXACT_VALUES), (-0.9, 0)):
+        ref = O.shrink(img, bw, bh, O.METRIC_OKLAB_MAD, factor, filt, nthreads=8)
+        descs, pixels, _ = gpu_shrink(ctx, img, bw, bh, N.METRIC_OKLAB_MAD, factor, filt, flags)
+        assert_same_payload(descs, pixels, ref, exact_values=bool(flags))
+        pl = ctx.payload_upload(w, h, bw, bh, c, descs, pixels)
+        out = pl.expand(filt)
+        pl.free()
+        assert np.array_equal(out, O.expand(ref, filt, nthreads=8))
+
+
+def test_expand_arbitrary_block_sizes(ctx):
+    """decode side with block sizes no shrink would produce (files written by other tools)."""
+    rng = np.random.default_rng(5)
+    w, h, bw, bh, c = 150, 100, 64, 64, 4
+    cols, rows = O.grid(w, h, bw, bh)
+    descs = np.zeros(cols * rows, O.DESC_DTYPE)
+    parts, off = [], 0
+    for i in range(cols * rows):
+        sw, sh = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        descs[i] = (off, 0.5, sw, sh)
+        parts.append(rng.integers(0, 256, sw * sh * c, dtype=np.uint8))
+        off += sw * sh * c
+    payload = np.concatenate(parts)
+    ref = O.Shrunk(w, h, bw, bh, c, descs, payload)
+    for filt in FILTERS:
+        pl = ctx.payload_upload(w, h, bw, bh, c, descs.astype(N.DESC_DTYPE), payload)
+        out = pl.expand(filt)
+        pl.free()
+        assert np.array_equal(out, O.expand(ref, filt, nthreads=8)), filt
+
+
+def test_process_old_api():
+    """process(image, block_size) (process/mod.rs:107-121): Lanczos3 down, Nearest up, RGBA canvas."""
+    img = load_png("Big-Ruscher.png")
+    out = P.process(img, 32)
+    ref = O.shrink(img, 32, 32, O.METRIC_OKLAB_MAD, 1.0, O.LANCZOS3, use_factor=False, nthreads=8)
+    want = O.expand(ref, O.NEAREST, nthreads=8)
+    assert out.shape == (1080, 1920, 4) and (out[..., 3] == 255).all()
+    assert np.array_equal(out[..., :3], want)
+
+
+def test_free_functions():
+    img = load_png("Big-Ruscher.png")
+    blk = np.ascontiguousarray(img[0:32, 0:32])
+    assert np.float32(P.get_block_variance(blk)) == np.float32(O.block_mad(blk))
+    hz, vr = P.get_block_variance_directionally(blk)
+    ohz, ovr = O.block_sobel(blk)
+    assert (np.float32(hz), np.float32(vr)) == (np.float32(ohz), np.float32(ovr))
+    blk2 = np.ascontiguousarray(img[320:352, 640:672])
+    r = P.reduce_image_section((0.2, 0.4), blk2, P.FilterType.CatmullRom)
+    ow, oh, st = O.reduce_dims(0.2, 0.4, 32, 32)
+    assert r.dimensions() == (ow, oh) and np.float32(r.block_value) == np.float32(st)
+    assert np.array_equal(r.data, O.resize(blk2, ow, oh, O.CATMULLROM))
+
+
+def test_normalise_global_extension(ctx):
+    img = synth(512, 384, 4, seed=11)
+    for metric, factor in ((O.METRIC_OKLAB_MAD, 0.05), (O.METRIC_SOBEL_DIR, 1.0)):
+        ref = O.shrink(img, 64, 64, metric, factor, O.TRIANGLE, normalise_global=True, nthreads=8)
+        descs, pixels, _ = gpu_shrink(ctx, img, 64, 64, metric, factor, O.TRIANGLE, N.FLAG_NORMALISE_GLOBAL)
+        assert_same_payload(descs, pixels, ref, exact_values=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size configuration (8K RGBA, 64x64 blocks): size-independent properties + sampled oracle check
+# ---------------------------------------------------------------------------------------------
+def test_8k_properties(ctx):
+    w, h = 7680, 4320
+    # white noise: every block keeps its size, so encode -> decode is the identity
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    d = ctx.image_upload(img)
+    pl = d.shrink(64, 64, N.METRIC_OKLAB_MAD, 1.0, O.LANCZOS3, 0)
+    info = pl.info()
+    assert (info["cols"], info["rows"]) == (120, 68) and info["bytes"] == w * h * 4
+    descs, pixels = pl.download()
+    assert (descs["w"] == 64).all() and set(descs["h"].tolist()) == {64, 32}
+    out = ctx.image_alloc(w, h, 4)
+    pl.expand_to_image(O.LANCZOS3, out)
+    assert np.array_equal(out.download(), img)
+    pl.free(); d.free()
+    # flat: every block collapses to one pixel of the flat colour
+    flat = np.empty((h, w, 4), np.uint8)
+    flat[...] = (10, 200, 90, 255)
+    d = ctx.image_upload(flat)
+    pl = d.shrink(64, 64, N.METRIC_OKLAB_MAD, 1.0, O.LANCZOS3, 0)
+    descs, pixels = pl.download()
+    assert (descs["w"] == 1).all() and (descs["h"] == 1).all() and pixels.size == 120 * 68 * 4
+    assert (pixels.reshape(-1, 4) == np.array([10, 200, 90, 255], np.uint8)).all()
+    pl.expand_to_image(O.NEAREST, out)
+    assert np.array_equal(out.download(), flat)
+    pl.free(); d.free(); out.free()
+
+
+def test_8k_mixed_sampled_against_oracle(ctx):
+    w, h = 7680, 4320
+    img = synth(w, h, 4, seed=2)
+    d = ctx.image_upload(img)
+    pl = d.shrink(64, 64, N.METRIC_OKLAB_MAD, 1.0, O.CATMULLROM, 0)
+    descs, pixels = pl.download()
+    out = ctx.image_alloc(w, h, 4)
+    pl.expand_to_image(O.CATMULLROM, out)
+    got = out.download()
+    pl.free(); out.free(); d.free()
+    # offsets are the exclusive scan of the sizes
+    sizes = descs["w"].astype(np.uint64) * descs["h"].astype(np.uint64) * 4
+    assert np.array_equal(descs["offset"], np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64))
+    assert pixels.size == int(sizes.sum())
+    assert len(set(descs["w"].tolist())) >= 5  # many levels are populated
+    # oracle on a band of block rows (rows 20..23) — same inputs, same block indices
+    y0, y1 = 20 * 64, 24 * 64
+    ref = O.shrink(np.ascontiguousarray(img[y0:y1]), 64, 64, O.METRIC_OKLAB_MAD, 1.0, O.CATMULLROM, nthreads=8)
+    sl = slice(20 * 120, 24 * 120)
+    assert np.array_equal(descs["w"][sl], ref.descs["w"]) and np.array_equal(descs["h"][sl], ref.descs["h"])
+    assert rel_close(descs["value"][sl], ref.descs["value"])
+    o0 = int(descs["offset"][20 * 120])
+    assert np.array_equal(pixels[o0:o0 + ref.payload.size], ref.payload)
+    assert np.array_equal(got[y0:y1], O.expand(ref, O.CATMULLROM, nthreads=8))

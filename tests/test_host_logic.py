@@ -1,0 +1,150 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, the host container stage reproduces the reference's files byte-for-byte, and the
+value -> level thresholds agree with the oracle.  No compute calls (no GPU here)."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as O
+import pixlzr_b200 as P
+from conftest import GOLDEN, ROOT, load_png
+
+N = P.native
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pixlzr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pxz_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = N.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert declared == set(N.SYMBOLS), declared ^ set(N.SYMBOLS)
+    assert lib.pxz_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    if N.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(N.PixlzrError):
+        N.Context(0)
+    with pytest.raises(N.PixlzrError):
+        P.Pixlzr.from_image(np.zeros((8, 8, 3), np.uint8), 4, 4).shrink_by(P.FilterType.Lanczos3, 1.0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pixlzr-rust_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pxz_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_srgb_lut_inc_matches_oracle(golden_meta):
+    txt = open(os.path.join(ROOT, "pixlzr-rust_b200", "csrc", "srgb_lut.inc")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    vals = [float.fromhex(t.rstrip("f")) for t in re.findall(r"-?0x[0-9a-f.]+p[+-]?\d+f", txt)]
+    arr = np.array(vals, dtype="<f4")
+    assert arr.shape == (256,)
+    assert hashlib.sha256(arr.tobytes()).hexdigest() == golden_meta["kat"]["srgb_lut_sha256_le_f32"]
+    assert np.array_equal(arr, O.srgb_lut())
+
+
+def test_grid_and_filter_enum():
+    assert N.grid(1080, 1617, 64, 64) == (17, 26)
+    assert N.grid(1920, 1080, 32, 32) == (60, 34)
+    assert N.grid(7680, 4320, 64, 64) == (120, 68)
+    assert N.grid(5, 5, 64, 64) == (1, 1)
+    assert [int(f) for f in P.FilterType] == [0, 1, 2, 3, 4]
+    assert P.FilterType.from_u8(200) == P.FilterType.Nearest and P.FilterType.from_u8(4) == P.FilterType.Lanczos3
+
+
+def test_parse_shrinking_factor(golden_meta):
+    """src/bin/main.rs:281-297"""
+    for s, want in golden_meta["kat"]["parse_shrinking_factor"].items():
+        assert P.parse_shrinking_factor(s) == want, s
+
+
+def test_level_thresholds_match_oracle(golden_meta):
+    for v, exp in golden_meta["kat"]["level_dims_64_56_17"].items():
+        got = [N.reduce_dims(float(v), float(v), n, n)[0] for n in (64, 56, 17)]
+        assert got == exp, v
+    # +-4096 ulps around every boundary 2^(k - 1/2), k = 0..-20, against log2f/round themselves
+    for k in range(0, 21):
+        centre = np.float32(2.0 ** (-k - 0.5))
+        bits = int(centre.view(np.uint32))
+        cand = np.arange(bits - 4096, bits + 4096, dtype=np.uint32).view(np.float32)
+        for v in cand[::37].tolist() + cand[4096 - 40:4096 + 40].tolist():
+            a = N.reduce_dims(v, v, 65535, 40000)
+            b = O.reduce_dims(v, v, 65535, 40000)
+            assert a[:2] == b[:2], (k, v)
+            assert np.float32(a[2]) == np.float32(b[2])
+    # specials
+    for v in [0.0, -0.0, -0.25, -1.0, -1.5, float("inf"), float("nan"), 1e-30, 3.0, -5.0]:
+        a, b = N.reduce_dims(v, 0.3, 64, 17), O.reduce_dims(v, 0.3, 64, 17)
+        assert a[:2] == b[:2], v
+        assert (np.isnan(a[2]) and np.isnan(b[2])) or a[2] == b[2], v
+
+
+def test_container_decode_encode_golden_files():
+    for name in ("Big-Ruscher.pix", "base.pixlzr"):
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        hdr, descs, pixels = N.container_decode(raw)
+        ref, filt = O.container_decode(raw)
+        assert (hdr["w"], hdr["h"], hdr["bw"], hdr["bh"], hdr["channels"], hdr["filter"]) == \
+               (ref.width, ref.height, ref.block_width, ref.block_height, ref.channels, filt)
+        assert np.array_equal(descs, ref.descs.astype(N.DESC_DTYPE))
+        assert np.array_equal(pixels, ref.payload)
+        again = N.container_encode(hdr["w"], hdr["h"], hdr["bw"], hdr["bh"], hdr["filter"], hdr["channels"], descs,
+                                   pixels, None, nthreads=4)
+        assert again == raw, name
+
+
+def test_from_image_encode_equals_base_pixlzr():
+    """benches/base.png --from_image(64,64)+save--> benches/base.pixlzr, byte for byte (host only)."""
+    img = load_png("base.png")
+    pix = P.Pixlzr.from_image(img, 64, 64)
+    assert pix.block_grid_dimensions() == (17, 26)
+    assert pix.block_grid_has_trailing() == (True, True)
+    blocks = pix.blocks
+    assert len(blocks) == 442 and all(b.block_value is None for b in blocks)
+    assert blocks[16].dimensions() == (56, 64) and blocks[-1].dimensions() == (56, 17)
+    assert pix.encode_to_vec() == open(os.path.join(GOLDEN, "base.pixlzr"), "rb").read()
+
+
+def test_decode_from_vec_mirrors_reference():
+    pix = P.Pixlzr.decode_from_vec(open(os.path.join(GOLDEN, "Big-Ruscher.pix"), "rb").read())
+    assert pix.dimensions() == (1920, 1080) and pix.block_dimensions() == (32, 32)
+    assert pix.filter == P.FilterType.Nearest and not pix.has_alpha()
+    blocks = pix.blocks
+    assert len(blocks) == 2040 and all(b.block_value is not None for b in blocks)
+    assert np.float32(blocks[0].block_value) == np.float32(float.fromhex("0x1.76b0acp-9"))
+    # already-valued blocks are skipped by shrink_by (pixlzr.rs:168-170): no GPU needed, no change
+    before = pix.encode_to_vec()
+    pix.shrink_by(P.FilterType.Lanczos3, 1.0)
+    assert pix.encode_to_vec() == before
+
+
+def test_container_rejects_garbage():
+    with pytest.raises(N.PixlzrError):
+        N.container_decode(b"NOTPIX" + bytes(40))
+    raw = open(os.path.join(GOLDEN, "Big-Ruscher.pix"), "rb").read()
+    with pytest.raises(N.PixlzrError):
+        N.container_decode(raw[:-5])
+    with pytest.raises(N.PixlzrError):
+        N.container_decode(raw + b"\0")
+
+
+def test_pixlzrblock_accessors():
+    """block.rs:346-399"""
+    b = P.PixlzrBlock(np.zeros((100, 100, 4), np.uint8))
+    assert b.width == 100 and b.height == 100 and b.has_alpha()
+    px = b.pixels()
+    assert px.shape == (10000, 4)
+    same = b.resize(100, 100, P.FilterType.Lanczos3)  # same size: clone, no GPU involved
+    assert same.data is not b.data and np.array_equal(same.data, b.data)
