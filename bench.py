@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py — encode+decode megapixels/s of the pixlzr hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], "C3"): synthetic 7680x4320 RGBA8 images, 64x64 blocks, metric
+Oklab-MAD with k = 1, Lanczos3 down / Lanczos3 up (the reference CLI's defaults, src/bin/main.rs:19,27-36).
+One step = encode (analyse -> plan -> shrink into the packed payload) + decode (expand + paste) of a batch
+of `--batch` distinct images per rank; images are independent, so ranks share nothing (weak scaling) and
+no collective sits on the data path.  `value` is timed with CUDA events on the launching stream with
+every input already resident in HBM; `e2e` runs the same work through the C ABI with pinned HOST
+buffers, host<->device copies inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "encode+decode megapixels/sec"
+UNIT = "MP/s"
+BS = 64
+FILTER_DOWN = 4  # Lanczos3
+FILTER_UP = 4
+FACTOR = 1.0
+IMG_W, IMG_H = 7680, 4320
+CPU_SAMPLE_ROWS = 1088  # 17 block rows of the 8K frame = 8.36 MP: the bounded CPU sample
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic input: slow colour ramps + per-64x64-tile uniform noise whose amplitude
+# is picked from {0,1,2,4,8,16,32,64} by a tile hash, so that every level 2^0 .. 2^-6 occurs
+# --------------------------------------------------------------------------------------------------
+def synth_image_np(seed: int, w: int, h: int) -> np.ndarray:
+    rng = np.random.default_rng(0x5049584C5A52 ^ seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    base = np.stack([128 + 96 * np.sin(xx / 9000.0 + seed), 128 + 96 * np.cos(yy / 7000.0 + 0.3 * seed),
+                     128 + 64 * np.sin((xx + yy) / 11000.0)], -1)
+    ty, tx = np.mgrid[0:(h + 63) // 64, 0:(w + 63) // 64].astype(np.uint64)
+    hsh = (tx * np.uint64(73856093)) ^ (ty * np.uint64(19349663)) ^ np.uint64((seed * 83492791) & 0xFFFFFFFF)
+    amp = np.array([0, 1, 2, 4, 8, 16, 32, 64], np.float32)[(hsh >> np.uint64(3)) % np.uint64(8)]
+    amp = np.kron(amp, np.ones((64, 64), np.float32))[:h, :w]
+    img = base + (rng.random((h, w, 3), dtype=np.float32) - 0.5) * 2 * amp[..., None]
+    img = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], -1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons of one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [ln for (t, ln) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [ln for _, ln in self.lines]
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (oracle = C++ port of the reference; the Rust reference itself cannot be built here)
+# --------------------------------------------------------------------------------------------------
+def cpu_encode_decode(O, sample: np.ndarray, threads: int) -> float:
+    t0 = time.perf_counter()
+    s = O.shrink(sample, BS, BS, O.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, nthreads=threads)
+    O.expand(s, FILTER_UP, nthreads=threads)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(sample: np.ndarray) -> dict:
+    import oracle as O
+
+    cores = os.cpu_count() or 1
+    mp = sample.shape[0] * sample.shape[1] / 1e6
+    cpu_encode_decode(O, sample, cores)  # warm-up (thread pool, page faults)
+    best_all = min(cpu_encode_decode(O, sample, cores) for _ in range(5))
+    best_one = min(cpu_encode_decode(O, sample, 1) for _ in range(2))
+    return {"value": mp / best_all, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"top {sample.shape[0]} rows ({mp:.2f} MP) of image 0 of the same workload, best of 5",
+            "one_thread_value": mp / best_one,
+            "note": "shrink* is a serial loop in the reference (pixlzr.rs:163-184); the all-core figure is charitable"}
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust crate cannot
+    be built in this image: no cargo/rustc) on the host cores, same config/metric."""
+    if rank != 0:
+        return
+    import oracle as O
+
+    cores = os.cpu_count() or 1
+    sample = synth_image_np(0, IMG_W, CPU_SAMPLE_ROWS)
+    mp = sample.shape[0] * sample.shape[1] / 1e6
+    for _ in range(args.warmup):
+        cpu_encode_decode(O, sample, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_encode_decode(O, sample, cores)
+    dt = time.perf_counter() - t0
+    val = mp * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1, sample_rows=CPU_SAMPLE_ROWS),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"each step = top {CPU_SAMPLE_ROWS} rows ({mp:.2f} MP) of one 8K frame of the workload"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch: int, sample_rows: int | None = None) -> dict:
+    cfg = {
+        "workload": "C3 synthetic 7680x4320 RGBA8 (alpha 255), 64x64 blocks, Oklab-MAD k=1, Lanczos3 down / Lanczos3 up, "
+                    "encode (analyse+plan+shrink) + decode (expand+paste)",
+        "width": IMG_W, "height": IMG_H, "channels": 4, "block": BS, "metric": "oklab_mad", "factor": FACTOR,
+        "filter_down": "Lanczos3", "filter_up": "Lanczos3", "images_per_step_per_gpu": batch,
+        "sharding": "independent images per rank, no data-path collective",
+        "cache": "inputs larger than L2 (batch x 132.7 MB per step)",
+        "resize_semantics": "image_rs (the branch pinned by the reference's fixtures)",
+    }
+    if sample_rows:
+        cfg["cpu_sample_rows"] = sample_rows
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    import pixlzr_b200 as P
+
+    N = P.native
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    batch = args.batch
+
+    with torch.cuda.stream(stream):
+        ctx = N.Context(local_rank, cuda_stream=stream.cuda_stream)
+        # inputs: host (pinned) for the e2e leg, device-resident copies for the kernel leg
+        host_imgs = []
+        for i in range(batch):
+            a = synth_image_np(rank * 1000 + i, IMG_W, IMG_H)
+            t = torch.from_numpy(a).pin_memory()
+            host_imgs.append(t)
+        dev_imgs = [t.to(dev, non_blocking=True) for t in host_imgs]
+        dev_out = torch.empty((IMG_H, IMG_W, 4), dtype=torch.uint8, device=dev)
+        stream.synchronize()
+        wrapped = [ctx.image_wrap(t.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for t in dev_imgs]
+        wrapped_out = ctx.image_wrap(dev_out.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4)
+
+        def step_device():
+            for im in wrapped:
+                pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+                pl.expand_to_image(FILTER_UP, wrapped_out)
+                pl.free()
+
+        # payload sizes (for the algorithmic-byte counts), untimed
+        payload_bytes, nblocks = [], 0
+        for im in wrapped:
+            pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+            info = pl.info()
+            payload_bytes.append(info["bytes"])
+            nblocks = info["cols"] * info["rows"]
+            pl.free()
+
+        for _ in range(args.warmup):
+            step_device()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                               int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+        sampler.start()
+        time.sleep(0.25)
+        launches0 = ctx.launch_count()
+        ctx.profile_enable(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+        if world > 1:
+            dist.barrier()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        launches = ctx.launch_count() - launches0
+        clocks = sampler.stop(t_wall0, t_wall1)
+
+        # ---- e2e: same work through the C ABI with pinned host buffers ---------------------------------
+        img_bytes = IMG_W * IMG_H * 4
+        pin_descs = torch.empty(nblocks * 16, dtype=torch.uint8).pin_memory()
+        pin_pixels = torch.empty(img_bytes, dtype=torch.uint8).pin_memory()
+        pin_out = torch.empty((IMG_H, IMG_W, 4), dtype=torch.uint8).pin_memory()
+        np_descs = pin_descs.numpy().view(N.DESC_DTYPE)
+        np_pixels, np_out = pin_pixels.numpy(), pin_out.numpy()
+        np_imgs = [t.numpy() for t in host_imgs]
+        h2d = d2h = 0
+
+        def step_e2e(count: bool):
+            nonlocal h2d, d2h
+            for a in np_imgs:
+                im = ctx.image_upload(a)                                   # H2D image
+                pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+                nbytes = pl.download_into(np_descs, np_pixels)             # D2H descs + payload (encode result)
+                pl.free()
+                im.free()
+                pl2 = ctx.payload_upload(IMG_W, IMG_H, BS, BS, 4, np_descs, np_pixels[:nbytes])  # H2D payload
+                pl2.expand_into(FILTER_UP, np_out)                         # D2H decoded image
+                pl2.free()
+                if count:
+                    h2d += img_bytes + nbytes + nblocks * 16
+                    d2h += nbytes + nblocks * 16 + img_bytes
+
+        e2e_steps = max(1, min(args.steps, 5))
+        step_e2e(False)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e(True)
+        stream.synchronize()
+        e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks: max time -------------------------------------------------------------------
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+    mp_per_step = world * batch * IMG_W * IMG_H / 1e6
+    value = mp_per_step * args.steps / (elapsed_ms / 1e3)
+    e2e_value = mp_per_step * e2e_steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        n_px = IMG_W * IMG_H
+        mean_payload = float(np.mean(payload_bytes))
+        # algorithmic bytes per launch of every kernel (DESIGN.md "algorithmic bytes")
+        algo = {
+            "analyze_mad_fast": 4 * n_px + 5 * nblocks,
+            "mad_exact": 4 * n_px + 4 * nblocks,
+            "plan": 4 * nblocks + 20 * nblocks,
+            "resample_down": 4 * n_px + mean_payload + 20 * nblocks,
+            "resample_up": mean_payload + 20 * nblocks + 4 * n_px,
+        }
+        kernels = {}
+        for name, (ms, n) in prof.items():
+            if n:
+                us = ms / n * 1e3
+                gbs = algo.get(name, 0) / (us * 1e-6) / 1e9
+                kernels[name] = {"us": round(us, 2), "launches": int(n), "algo_GBps": round(gbs, 1),
+                                 "frac": round(gbs / peak, 4), "share": round(ms / elapsed_ms, 4)}
+        dom = max(kernels, key=lambda k: kernels[k]["us"] * kernels[k]["launches"]) if kernels else None
+        roofline = None
+        if dom:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["algo_GBps"], "peak": peak,
+                        "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": int(algo[dom]), "avg_launch_us": kernels[dom]["us"]}
+        # whole encode+decode stage against the roofline (image read once + payload written, payload read + image written)
+        stage_bytes = (4 * n_px + mean_payload + 16 * nblocks) + (mean_payload + 16 * nblocks + 4 * n_px)
+        per_image_s = elapsed_ms / 1e3 / (args.steps * batch)
+        stage = {"algorithmic_bytes_per_image": int(stage_bytes), "GBps": round(stage_bytes / per_image_s / 1e9, 1),
+                 "frac_of_hbm_peak": round(stage_bytes / per_image_s / 1e9 / peak, 4),
+                 "payload_fraction": round(mean_payload / (4 * n_px), 4)}
+        cpu = cpu_baseline(np.ascontiguousarray(np_imgs[0][:CPU_SAMPLE_ROWS])) if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, batch),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // e2e_steps),
+                    "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps,
+                    "path": "pxz_image_upload -> pxz_shrink -> pxz_payload_download -> pxz_payload_upload -> pxz_expand, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "kernels": kernels,
+            "encode_decode_stage": stage,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="8K images per rank per step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun when started plainly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,13 @@ const char* pxz_last_error(const pxz_ctx* ctx);
 pxz_status pxz_synchronize(pxz_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t pxz_launch_count(const pxz_ctx* ctx);
+/* Per-kernel device timing (CUDA events recorded on the context's stream around every kernel
+ * launch while enabled).  pxz_profile_read synchronises the stream, returns the accumulated
+ * duration and launch count of kernel `kernel_id` since profiling was enabled.  Kernel ids are
+ * 0 .. n-1 where pxz_profile_kernel_name(n) == NULL. */
+pxz_status pxz_profile_enable(pxz_ctx* ctx, int on);
+const char* pxz_profile_kernel_name(int kernel_id);
+pxz_status pxz_profile_read(pxz_ctx* ctx, int kernel_id, double* total_ms, uint64_t* launches);
 /* pinned host memory for fast H2D / D2H */
 pxz_status pxz_host_alloc(size_t bytes, void** out);
 void pxz_host_free(void* p);

@@ -35,6 +35,9 @@ SYMBOLS = {
     "pxz_last_error": (C.c_char_p, [_vp]),
     "pxz_synchronize": (_i, [_vp]),
     "pxz_launch_count": (_u64, [_vp]),
+    "pxz_profile_enable": (_i, [_vp, _i]),
+    "pxz_profile_kernel_name": (C.c_char_p, [_i]),
+    "pxz_profile_read": (_i, [_vp, _i, _P(C.c_double), _P(_u64)]),
     "pxz_host_alloc": (_i, [_sz, _P(_vp)]),
     "pxz_host_free": (None, [_vp]),
     "pxz_image_upload": (_i, [_vp, _vp, _u32, _u32, _u32, _sz, _P(_vp)]),
@@ -128,6 +131,22 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().pxz_launch_count(self._h))
+
+    def profile_enable(self, on: bool = True):
+        self.check(lib().pxz_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total ms, launches)} since profiling was enabled (synchronises)."""
+        out, i = {}, 0
+        while True:
+            name = lib().pxz_profile_kernel_name(i)
+            if name is None:
+                break
+            ms, n = C.c_double(), C.c_uint64()
+            self.check(lib().pxz_profile_read(self._h, i, C.byref(ms), C.byref(n)))
+            out[name.decode()] = (ms.value, n.value)
+            i += 1
+        return out
 
     def close(self):
         if self._h:
@@ -235,6 +254,16 @@ class Payload:
         pixels = np.empty(max(1, i["bytes"]), np.uint8)
         self.ctx.check(lib().pxz_payload_download(self.ctx.handle, self._h, ptr(descs), ptr(pixels)))
         return descs, pixels[:i["bytes"]]
+
+    def download_into(self, descs: np.ndarray, pixels: np.ndarray) -> int:
+        """Like download(), into caller-provided (e.g. pinned) buffers; returns the payload byte count."""
+        i = self.info()
+        assert descs.dtype == DESC_DTYPE and descs.size >= i["cols"] * i["rows"] and pixels.size >= i["bytes"]
+        self.ctx.check(lib().pxz_payload_download(self.ctx.handle, self._h, ptr(descs), ptr(pixels)))
+        return i["bytes"]
+
+    def expand_into(self, filter_up: int, out: np.ndarray):
+        self.ctx.check(lib().pxz_expand(self.ctx.handle, self._h, int(filter_up), ptr(out), out.strides[0]))
 
     def expand(self, filter_up: int) -> np.ndarray:
         i = self.info()

@@ -41,6 +41,14 @@ struct TabSet {  // device copy of the axis tables of one (spec, filter, directi
 
 using TabKey = std::tuple<std::vector<uint32_t>, std::vector<uint32_t>, int, int>;
 
+enum KernelId { K_MAD_FAST = 0, K_MAD_EXACT, K_SOBEL, K_MINMAX, K_PLAN, K_RESAMPLE_DOWN, K_RESAMPLE_UP, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"analyze_mad_fast", "mad_exact",     "analyze_sobel", "minmax",
+                                           "plan",             "resample_down", "resample_up"};
+struct ProfRec {
+  int id;
+  cudaEvent_t a, b;
+};
+
 }  // namespace
 
 struct pxz_ctx {
@@ -56,6 +64,7 @@ struct pxz_ctx {
   // scratch, grown on demand
   float* d_vx = nullptr;
   float* d_vy = nullptr;
+  uint8_t* d_opaque = nullptr;
   size_t values_cap = 0;
   float* d_minmax = nullptr;
   void* d_scan = nullptr;
@@ -65,6 +74,12 @@ struct pxz_ctx {
   uint64_t* h_total = nullptr;  // pinned
   std::map<TabKey, TabSet> tabs;
   void* comm = nullptr;
+  // per-kernel timing
+  bool profiling = false;
+  std::vector<ProfRec> prof_open;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[K_COUNT] = {0};
+  uint64_t prof_n[K_COUNT] = {0};
 };
 
 struct pxz_image {
@@ -108,6 +123,34 @@ pxz_status fail(pxz_ctx* ctx, pxz_status st, const std::string& msg) {
     }                                                                                                   \
   } while (0)
 
+// records an event pair around one kernel launch while profiling is on
+struct ProfScope {
+  pxz_ctx* ctx;
+  ProfRec rec;
+  bool live = false;
+  ProfScope(pxz_ctx* c, int id) : ctx(c) {
+    if (!c->profiling) return;
+    auto take = [&](cudaEvent_t* e) {
+      if (!c->prof_pool.empty()) {
+        *e = c->prof_pool.back();
+        c->prof_pool.pop_back();
+        return true;
+      }
+      return cudaEventCreate(e) == cudaSuccess;
+    };
+    rec.id = id;
+    if (!take(&rec.a)) return;
+    if (!take(&rec.b)) { c->prof_pool.push_back(rec.a); return; }
+    cudaEventRecord(rec.a, c->stream);
+    live = true;
+  }
+  ~ProfScope() {
+    if (!live) return;
+    cudaEventRecord(rec.b, ctx->stream);
+    ctx->prof_open.push_back(rec);
+  }
+};
+
 inline uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a + b - 1) / b); }
 
 pxz_status make_geom(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t c, uint32_t bw, uint32_t bh, Geom* g) {
@@ -137,11 +180,14 @@ pxz_status ensure_scratch(pxz_ctx* ctx, uint32_t nblocks) {
   if (ctx->values_cap < nblocks) {
     dev_free(ctx, ctx->d_vx);
     dev_free(ctx, ctx->d_vy);
+    dev_free(ctx, ctx->d_opaque);
     ctx->d_vx = ctx->d_vy = nullptr;
+    ctx->d_opaque = nullptr;
     ctx->values_cap = 0;
     pxz_status st;
     if ((st = dev_alloc(ctx, (void**)&ctx->d_vx, (size_t)nblocks * 4)) != PXZ_OK) return st;
     if ((st = dev_alloc(ctx, (void**)&ctx->d_vy, (size_t)nblocks * 4)) != PXZ_OK) return st;
+    if ((st = dev_alloc(ctx, (void**)&ctx->d_opaque, (size_t)nblocks)) != PXZ_OK) return st;
     ctx->values_cap = nblocks;
   }
   const size_t need = plan_scan_state_bytes(nblocks);
@@ -229,6 +275,7 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
     }
     scratch = ctx->d_scratch;
   }
+  ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
                                 max_src_px, max_tmp_px, scratch, per_cta, grid, ctx->stream, ctx->sm_count, &ctx->launches));
   return PXZ_OK;
@@ -279,8 +326,8 @@ pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx*
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
   }
   build_level_thresholds(&ctx->thr);
-  ctx->band.rel = 1.0e-3f;
-  ctx->band.abs_raw = 5.0e-5f;
+  ctx->band.rel = 2.0e-5f;     // fast arithmetic, relative
+  ctx->band.abs_raw = 8.0e-6f; // fast arithmetic, absolute (SFU cube roots; measured <= 4e-6)
   if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
   if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
   if (cudaMalloc((void**)&ctx->d_minmax, 4 * sizeof(float)) != cudaSuccess ||
@@ -328,9 +375,12 @@ void pxz_ctx_destroy(pxz_ctx* ctx) {
   }
   dev_free(ctx, ctx->d_vx);
   dev_free(ctx, ctx->d_vy);
+  dev_free(ctx, ctx->d_opaque);
   dev_free(ctx, ctx->d_scan);
   dev_free(ctx, ctx->d_scratch);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->prof_open) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
   cudaFree(ctx->d_minmax);
   cudaFreeHost(ctx->h_total);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -346,6 +396,46 @@ pxz_status pxz_synchronize(pxz_ctx* ctx) {
 }
 
 uint64_t pxz_launch_count(const pxz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static pxz_status prof_drain(pxz_ctx* ctx) {
+  if (ctx->prof_open.empty()) return PXZ_OK;
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof_open) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ctx->prof_ms[r.id] += ms;
+      ctx->prof_n[r.id] += 1;
+    }
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof_open.clear();
+  return PXZ_OK;
+}
+
+pxz_status pxz_profile_enable(pxz_ctx* ctx, int on) {
+  if (!ctx) return PXZ_E_ARG;
+  pxz_status st = prof_drain(ctx);
+  if (st != PXZ_OK) return st;
+  if (on) {
+    for (int i = 0; i < K_COUNT; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+  }
+  ctx->profiling = on != 0;
+  return PXZ_OK;
+}
+
+const char* pxz_profile_kernel_name(int kernel_id) {
+  return (kernel_id >= 0 && kernel_id < K_COUNT) ? kKernelNames[kernel_id] : nullptr;
+}
+
+pxz_status pxz_profile_read(pxz_ctx* ctx, int kernel_id, double* total_ms, uint64_t* launches) {
+  if (!ctx || kernel_id < 0 || kernel_id >= K_COUNT) return PXZ_E_ARG;
+  pxz_status st = prof_drain(ctx);
+  if (st != PXZ_OK) return st;
+  if (total_ms) *total_ms = ctx->prof_ms[kernel_id];
+  if (launches) *launches = ctx->prof_n[kernel_id];
+  return PXZ_OK;
+}
 
 pxz_status pxz_host_alloc(size_t bytes, void** out) {
   if (!out) return PXZ_E_ARG;
@@ -445,13 +535,18 @@ static pxz_status run_analysis(pxz_ctx* ctx, const pxz_image* img, const Geom& g
   if (st != PXZ_OK) return st;
   if (metric == PXZ_METRIC_OKLAB_MAD) {
     if (exact_all) {
-      PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, nullptr, nullptr, nullptr, nullptr, nullptr,
+      ProfScope prof(ctx, K_MAD_EXACT);
+      PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                              ctx->stream, ctx->sm_count, &ctx->launches));
     } else {
-      PXZ_CUDA(ctx, launch_analyze_mad_fast(img->d, img->pitch, g, ctx->d_vx, ctx->stream, ctx->sm_count, &ctx->launches));
+      {
+        ProfScope prof(ctx, K_MAD_FAST);
+        PXZ_CUDA(ctx, launch_analyze_mad_fast(img->d, img->pitch, g, ctx->d_vx, ctx->d_opaque, ctx->stream, ctx->sm_count, &ctx->launches));
+      }
       if (vm_for_band) {
         // recompute, in reference order, the tiles whose level could differ from the CPU result
-        PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, ctx->d_vx, vm_for_band, &ctx->thr,
+        ProfScope prof(ctx, K_MAD_EXACT);
+        PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, ctx->d_vx, ctx->d_opaque, vm_for_band, &ctx->thr,
                                                &ctx->band, ctx->d_minmax, ctx->stream, ctx->sm_count, &ctx->launches));
       }
     }
@@ -461,6 +556,7 @@ static pxz_status run_analysis(pxz_ctx* ctx, const pxz_image* img, const Geom& g
     const uint32_t min_h = g.trail_h ? std::min(g.bh, g.trail_h) : std::min(g.bh, g.H);
     if (min_w < 2 || min_h < 2)
       return fail(ctx, PXZ_E_ARG, "directional metric needs every block to be at least 2x2 (the reference panics)");
+    ProfScope prof(ctx, K_SOBEL);
     PXZ_CUDA(ctx, launch_analyze_sobel(img->d, img->pitch, g, ctx->d_vx, ctx->d_vy, ctx->stream, ctx->sm_count, &ctx->launches));
   } else {
     return fail(ctx, PXZ_E_ARG, "unknown metric");
@@ -531,6 +627,7 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   if (st != PXZ_OK) return st;
 
   if (normalise) {
+    ProfScope prof(ctx, K_MINMAX);
     PXZ_CUDA(ctx, launch_minmax(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, nblocks, ctx->d_minmax,
                                 ctx->stream, &ctx->launches));
     if (ctx->comm) {
@@ -558,8 +655,12 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
       p->max_tmp_up = th_max * tw_max;
     }
   }
-  cudaError_t e = launch_plan(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, g, vm, ctx->d_minmax, ctx->thr,
-                              p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, ctx->stream, &ctx->launches);
+  cudaError_t e;
+  {
+    ProfScope prof(ctx, K_PLAN);
+    e = launch_plan(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, g, vm, ctx->d_minmax, ctx->thr, p->d_descs,
+                    p->d_tabidx, p->d_total, ctx->d_scan, ctx->stream, &ctx->launches);
+  }
   if (e != cudaSuccess) {
     payload_release(p);
     return fail(ctx, PXZ_E_CUDA, std::string("plan: ") + cudaGetErrorString(e));

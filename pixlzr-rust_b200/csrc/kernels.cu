@@ -128,7 +128,7 @@ __device__ __forceinline__ OklabFast lms_fast(uint32_t px, const float* lut_lane
 
 template <int G, int QPT>
 __global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
-                                                               float* __restrict__ vx) {
+                                                               float* __restrict__ vx, uint8_t* __restrict__ opaque) {
   constexpr int TPC = kThreads / G;  // tiles per CTA iteration
   constexpr int WPG = G / 32;        // warps per group
   extern __shared__ float s_lut[];   // [256][32]
@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __
     }
     const float count = (float)(t.tw * t.th);
     const float inv = valid ? 1.0f / count : 0.f;
+    // alpha 255 is exactly 1.0f and tiles here have <= 4096 px, so the tree sum of an opaque tile is the exact
+    // integer `count`, while a single non-opaque pixel lowers it by >= 1/255 (far above one ulp)
+    const bool is_opaque = (sa == count);
     sl *= inv; sm *= inv; ss *= inv; sa *= inv;
     // the Lab transform is linear: mean(Lab) = M2 * mean(l', m', s')
     const float nL = -(M2_00 * sl + M2_01 * sm + M2_02 * ss);
@@ -242,7 +245,10 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __
 #pragma unroll
       for (int w = 0; w < WPG; ++w) d += s_r2[buf][gwarp0 + w];
     }
-    if (valid && gt == 0) vx[tile] = d * inv;
+    if (valid && gt == 0) {
+      vx[tile] = d * inv;
+      opaque[tile] = (uint8_t)(is_opaque ? 1 : 0);
+    }
 #pragma unroll
     for (int j = 0; j < QPT; ++j) cur[j] = nxt[j];
   }
@@ -253,10 +259,11 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __
 // 16 * 256 pixels recomputes the rest in pass 2.
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_analyze_mad_any(const uint8_t* __restrict__ img, size_t pitch, Geom g,
-                                                              float* __restrict__ vx) {
+                                                              float* __restrict__ vx, uint8_t* __restrict__ opaque) {
   extern __shared__ float s_lut[];
   __shared__ float s_r1[kThreads / 32][4];
   __shared__ float s_r2[kThreads / 32];
+  __shared__ int s_opq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 256 * 32; i += kThreads) s_lut[i] = c_srgb_lut[i >> 5];
   __syncthreads();
@@ -267,11 +274,18 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_any(const uint8_t* __r
     const Tile t = tile_of(g, tile);
     const uint32_t npx = t.tw * t.th;
     const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
+    if (tid == 0) s_opq = 1;
+    bool all255 = true;
     auto fetch = [&](uint32_t idx, float& a) -> OklabFast {
       uint32_t y = idx / t.tw, x = idx - y * t.tw;
       const uint8_t* p = base + (size_t)y * pitch + (size_t)x * C;
       uint32_t px = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-      a = (C == 4) ? (float)p[3] * kInv255 : 0.f;
+      if (C == 4) {
+        a = (float)p[3] * kInv255;
+        all255 = all255 && (p[3] == 255);
+      } else {
+        a = 0.f;
+      }
       return lms_fast(px, lut_lane);
     };
     OklabFast c[KEEP];
@@ -292,6 +306,7 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_any(const uint8_t* __r
     }
     sl = warp_sum(sl); sm = warp_sum(sm); ss = warp_sum(ss); sa = warp_sum(sa);
     if (lane == 0) { s_r1[warp][0] = sl; s_r1[warp][1] = sm; s_r1[warp][2] = ss; s_r1[warp][3] = sa; }
+    if (C == 4 && !all255) s_opq = 0;  // benign race: everyone writes the same value
     __syncthreads();
     sl = sm = ss = sa = 0.f;
 #pragma unroll
@@ -328,6 +343,7 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_any(const uint8_t* __r
 #pragma unroll
       for (int w = 0; w < kThreads / 32; ++w) tot += s_r2[w];
       vx[tile] = tot * inv;
+      opaque[tile] = (uint8_t)((C == 3 || s_opq) ? 1 : 0);
     }
     __syncthreads();  // s_r1 / s_r2 reuse
   }
@@ -495,31 +511,42 @@ __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, c
   return result;  // valid in warp 0
 }
 
-// tiles whose fast value could round to a different level than the reference-order value
-__device__ __forceinline__ bool in_guard_band(float raw, const Tile& t, const ValueMap& vm, const LevelThresholds& thr,
-                                              const GuardBand& band, const float* minmax) {
+// Could the reference-order value of this tile land on the other side of a level threshold?
+// Bound of |v_ref - v_fast| in raw-metric units for a tile of n pixels (DESIGN.md "guard band"):
+//   sequential f32 mean of channel c : |delta_c| <= 0.375 * n * 2^-24 * max|x_c|   (0.375 = 3/4 * 1/2: partial
+//                                      sums grow at most linearly, ulp(s) <= 3/4 * 2^-23 s on average over the ramp)
+//   with max L <= 1, max|a| <= 0.276, max|b| <= 0.312 over the sRGB gamut, max alpha <= 1 (0 if the tile is opaque:
+//   its alpha sum is exact);  shifting a mean by delta moves that channel's MAD by at most |delta|;
+//   sequential f32 sum of the deviations: relative n * 2^-24;  fast arithmetic (SFU cube roots, tree sums): band.abs_raw.
+__device__ __forceinline__ bool in_guard_band(float raw, bool opaque, int C, const Tile& t, const ValueMap& vm,
+                                              const LevelThresholds& thr, const GuardBand& band, const float* minmax) {
   float v0, v1;
   map_values(vm, minmax, raw, raw, v0, v1);
   const float pv = parse_value_dev(v0);
   if (pv != pv) return true;
+  const float n = (float)(t.tw * t.th);
+  const float nu = n * 5.9604645e-8f;  // n * 2^-24
+  const float gamut = (C == 4 && !opaque) ? 2.588f : 1.588f;
+  const float tol_raw = 0.375f * nu * gamut + (nu + band.rel) * fabsf(raw) + band.abs_raw;
   const float scale = (vm.mode == 0) ? fabsf(vm.factor) * 10.0f : 1.0f;
-  const float tol = band.rel * fabsf(pv) + band.abs_raw * scale;
+  const float tol = tol_raw * scale * 1.0001f + 1e-30f;
   // only thresholds that change the size of this tile matter
-  uint32_t n = max(t.tw, t.th);
+  uint32_t nmax = max(t.tw, t.th);
   int kmax = 0;
-  while ((1u << kmax) < n) ++kmax;  // dims are 1 for every k >= ceil(log2 n)
+  while ((1u << kmax) < nmax) ++kmax;  // dims are 1 for every k >= ceil(log2 n)
   if (kmax > kThresholds - 1) kmax = kThresholds - 1;
   for (int k = 0; k < kmax; ++k) {  // thr[k] separates level k+1 (below) from k (at or above)
     if (fabsf(pv - thr.thr[k]) <= tol) return true;
   }
-  // the kink of parse_value at v = -1 (1 + v = 0) maps to 1 px on both sides; v = -0 is exact
+  // the kink of parse_value at v = -1 (1 + v = 0) maps to 1 px on both sides
   return false;
 }
 
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_mad_exact(const uint8_t* __restrict__ img, size_t pitch, Geom g, float* vx,
-                                                        const float* vx_fast, ValueMap vm, LevelThresholds thr,
-                                                        GuardBand band, const float* minmax) {
+                                                        const float* vx_fast, const uint8_t* __restrict__ opaque,
+                                                        ValueMap vm, LevelThresholds thr, GuardBand band,
+                                                        const float* minmax) {
   extern __shared__ float s_dyn[];
   float* s_val = s_dyn;  // 4 * kExactStride
   __shared__ float s_lut256[256];
@@ -530,7 +557,7 @@ __global__ void __launch_bounds__(kThreads) k_mad_exact(const uint8_t* __restric
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const Tile t = tile_of(g, tile);
     if (vx_fast != nullptr) {
-      if (!in_guard_band(vx_fast[tile], t, vm, thr, band, minmax)) continue;  // CTA-uniform
+      if (!in_guard_band(vx_fast[tile], opaque[tile] != 0, C, t, vm, thr, band, minmax)) continue;  // CTA-uniform
     }
     const float v = mad_exact_tile<C>(img, pitch, t, s_val, s_lut256, s_avg);
     if (threadIdx.x == 0) vx[tile] = v;
@@ -901,8 +928,8 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaSuccess;
 }
 
-cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, cudaStream_t s,
-                                    int sm_count, uint64_t* launches) {
+cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, uint8_t* opaque,
+                                    cudaStream_t s, int sm_count, uint64_t* launches) {
   const uint32_t ntiles = g.cols * g.rows;
   const size_t smem = 256 * 32 * sizeof(float);
   const bool aligned = g.C == 4 && (g.bw % 4 == 0) && (g.W % 4 == 0) && (pitch % 16 == 0) &&
@@ -915,34 +942,34 @@ cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom
     if (quads > 512) {
       e = set_smem(k_analyze_mad_rgba<256, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     } else if (quads > 256) {
       e = set_smem(k_analyze_mad_rgba<128, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     } else if (quads > 128) {
       e = set_smem(k_analyze_mad_rgba<64, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     } else {
       e = set_smem(k_analyze_mad_rgba<32, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     }
   } else if (g.C == 4) {
     e = set_smem(k_analyze_mad_any<4>, smem);
     if (e != cudaSuccess) return e;
-    k_analyze_mad_any<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+    k_analyze_mad_any<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
   } else {
     e = set_smem(k_analyze_mad_any<3>, smem);
     if (e != cudaSuccess) return e;
-    k_analyze_mad_any<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx);
+    k_analyze_mad_any<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
-                                     const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
+                                     const uint8_t* opaque, const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
                                      const float* minmax, cudaStream_t s, int sm_count, uint64_t* launches) {
   const uint32_t ntiles = g.cols * g.rows;
   const size_t smem = (size_t)4 * kExactStride * sizeof(float);
@@ -957,11 +984,11 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
   if (g.C == 4) {
     e = set_smem(k_mad_exact<4>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, v, t, b, minmax);
+    k_mad_exact<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, opaque, v, t, b, minmax);
   } else {
     e = set_smem(k_mad_exact<3>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, v, t, b, minmax);
+    k_mad_exact<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, opaque, v, t, b, minmax);
   }
   return cudaGetLastError();
 }

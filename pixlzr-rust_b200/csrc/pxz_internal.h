@@ -39,8 +39,9 @@ struct LevelThresholds {
   float thr[kThresholds];
 };
 
-// Guard band of the fast Oklab-MAD path (DESIGN.md "exactness"): a block is recomputed in
-// reference order when its fast value is within  rel * v + abs_raw * scale  of a threshold.
+// Guard band of the fast Oklab-MAD path (DESIGN.md "guard band"): a block is recomputed in reference
+// order when its fast value is within the bound of |v_ref - v_fast| of a level threshold.  The bound's
+// sequential-summation terms are derived in kernels.cu; `abs_raw` / `rel` cover the fast arithmetic itself.
 struct GuardBand {
   float rel;
   float abs_raw;
@@ -48,10 +49,10 @@ struct GuardBand {
 
 // ---- kernel launchers (kernels.cu) ---------------------------------------------------------
 // All return cudaGetLastError() of the launch; *launches is incremented per kernel launched.
-cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, cudaStream_t s,
-                                    int sm_count, uint64_t* launches);
+cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, uint8_t* opaque,
+                                    cudaStream_t s, int sm_count, uint64_t* launches);
 cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
-                                     const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
+                                     const uint8_t* opaque, const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
                                      const float* minmax, cudaStream_t s, int sm_count, uint64_t* launches);
 cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g, float* vx, float* vy, cudaStream_t s,
                                  int sm_count, uint64_t* launches);
