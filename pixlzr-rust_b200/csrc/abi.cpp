@@ -37,6 +37,7 @@ struct TabSpec {
 struct TabSet {  // device copy of the axis tables of one (spec, filter, direction)
   AxisTab* d_tabs = nullptr;
   uint32_t* d_pool = nullptr;
+  uint32_t max_words = 0;  // largest single table (left | count | weights), in 32-bit words
 };
 
 using TabKey = std::tuple<std::vector<uint32_t>, std::vector<uint32_t>, int, int>;
@@ -241,6 +242,7 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
     seen[{n_in, n_out}] = tabs[i];
   }
   TabSet ts;
+  for (const AxisTab& t : tabs) ts.max_words = std::max(ts.max_words, 2 * t.n_out + t.n_out * t.stride);
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_tabs, tabs.size() * sizeof(AxisTab))) != PXZ_OK) return st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_pool, pool.size() * 4)) != PXZ_OK) return st;
@@ -277,7 +279,8 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   }
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
-                                max_src_px, max_tmp_px, scratch, per_cta, grid, ctx->stream, ctx->sm_count, &ctx->launches));
+                                max_src_px, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->stream, ctx->sm_count,
+                                &ctx->launches));
   return PXZ_OK;
 }
 

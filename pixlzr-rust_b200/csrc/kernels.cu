@@ -918,6 +918,247 @@ __global__ void __launch_bounds__(kThreads) k_resample(int direction, uint8_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// RGBA fast paths of the resample: tiles of at most 64x64 (4096 px, 1024 16-byte quads), 16-byte
+// aligned tile rows.  Same arithmetic and accumulation order as k_resample (so the pixels stay
+// bit-identical), but
+//   * the next block's source is prefetched into registers while the current one is resampled
+//     (persistent CTAs, grid-stride), so global-load latency is off the critical path;
+//   * the source block is converted u8 -> f32 once, into shared memory;
+//   * the tap tables of the block's two axes are staged in shared memory;
+//   * no integer division in the inner loops.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastMaxPx = 4096;
+constexpr int kFastMaxTabWords = 1024;  // left | count | weights of one axis (checked on the host: max_tab_words)
+
+struct FastSmem {
+  float4* src;     // [4096]
+  float4* tmp;     // [max_tmp_px]
+  uint32_t* taby;  // [kFastMaxTabWords]
+  uint32_t* tabx;
+};
+
+__device__ __forceinline__ FastSmem carve_fast_smem(float* base, uint32_t max_tmp_px) {
+  FastSmem s;
+  s.src = reinterpret_cast<float4*>(base);
+  s.tmp = s.src + kFastMaxPx;
+  s.taby = reinterpret_cast<uint32_t*>(s.tmp + max_tmp_px);
+  s.tabx = s.taby + kFastMaxTabWords;
+  return s;
+}
+
+__device__ __forceinline__ void stage_table(const AxisTab& t, const uint32_t* __restrict__ pool, uint32_t* dst) {
+  const uint32_t words = 2 * t.n_out + t.n_out * t.stride;
+  for (uint32_t i = threadIdx.x; i < words; i += kThreads) dst[i] = __ldg(pool + t.off + i);
+}
+
+__device__ __forceinline__ float4 px_to_f4(uint32_t w) {
+  return make_float4(byte_to_float<0>(w), byte_to_float<1>(w), byte_to_float<2>(w), byte_to_float<3>(w));
+}
+__device__ __forceinline__ uint32_t f4_to_px(const float4& a) {
+  return to_u8(a.x) | (to_u8(a.y) << 8) | (to_u8(a.z) << 16) | (to_u8(a.w) << 24);
+}
+// acc += p * w, sequential f32, no contraction (image 0.25.5 sample loops)
+__device__ __forceinline__ void mac4(float4& acc, const float4& p, float w) {
+  acc.x = __fadd_rn(acc.x, __fmul_rn(p.x, w));
+  acc.y = __fadd_rn(acc.y, __fmul_rn(p.y, w));
+  acc.z = __fadd_rn(acc.z, __fmul_rn(p.z, w));
+  acc.w = __fadd_rn(acc.w, __fmul_rn(p.w, w));
+}
+
+// vertical_sample: src [sh][sw] -> tmp [dh][sw].  Lanes per row = next power of two >= sw.
+__device__ __forceinline__ void fast_vertical(const float4* src, float4* tmp, uint32_t sw, uint32_t dh, const uint32_t* taby,
+                                              uint32_t stride) {
+  const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);
+  const uint32_t x = threadIdx.x & ((1u << lshift) - 1), g = threadIdx.x >> lshift, ng = kThreads >> lshift;
+  if (x >= sw) return;
+  const uint32_t* left = taby;
+  const uint32_t* cnt = taby + dh;
+  const float* w = reinterpret_cast<const float*>(taby + 2 * dh);
+  for (uint32_t oy = g; oy < dh; oy += ng) {
+    const uint32_t n = cnt[oy];
+    const float* wr = w + oy * stride;
+    const float4* sp = src + left[oy] * sw + x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t k = 0;
+    for (; k + 4 <= n; k += 4) {  // loads first, then the dependent chain
+      const float4 p0 = sp[0], p1 = sp[sw], p2 = sp[2 * sw], p3 = sp[3 * sw];
+      const float w0 = wr[k], w1 = wr[k + 1], w2 = wr[k + 2], w3 = wr[k + 3];
+      mac4(acc, p0, w0); mac4(acc, p1, w1); mac4(acc, p2, w2); mac4(acc, p3, w3);
+      sp += 4 * sw;
+    }
+    for (; k < n; ++k) {
+      mac4(acc, sp[0], wr[k]);
+      sp += sw;
+    }
+    tmp[oy * sw + x] = acc;
+  }
+}
+
+// horizontal_sample of one output pixel: tmp row (stride sw) -> clamp/round -> packed RGBA
+__device__ __forceinline__ uint32_t fast_horizontal_px(const float4* tmp_row, uint32_t ox, uint32_t dw, const uint32_t* tabx,
+                                                       uint32_t stride) {
+  const uint32_t n = tabx[dw + ox];
+  const float* wr = reinterpret_cast<const float*>(tabx + 2 * dw) + ox * stride;
+  const float4* sp = tmp_row + tabx[ox];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t k = 0;
+  for (; k + 4 <= n; k += 4) {
+    const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];
+    const float w0 = wr[k], w1 = wr[k + 1], w2 = wr[k + 2], w3 = wr[k + 3];
+    mac4(acc, p0, w0); mac4(acc, p1, w1); mac4(acc, p2, w2); mac4(acc, p3, w3);
+    sp += 4;
+  }
+  for (; k < n; ++k) mac4(acc, *sp++, wr[k]);
+  return f4_to_px(acc);
+}
+
+// ---- encode side: 64x64-or-smaller tiles of the pitched image -> packed payload -----------------------------
+__global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                             const pxz_block_desc* __restrict__ descs,
+                                                             const uint32_t* __restrict__ tabidx, uint8_t* __restrict__ payload,
+                                                             const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool,
+                                                             uint32_t max_tmp_px) {
+  extern __shared__ float s_dyn[];
+  const FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nblocks = g.cols * g.rows;
+  const uint32_t qpr = g.bw >> 2;  // 16-byte quads per full tile row
+
+  uint4 cur[4];
+  auto prefetch = [&](uint32_t b, uint4(&v)[4]) {
+    if (b >= nblocks) return;
+    const Tile t = tile_of(g, b);
+    const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t q = tid + j * kThreads, row = q / qpr, c4 = q - row * qpr;
+      v[j] = (row < t.th && c4 * 4 < t.tw) ? ldg_nc_v4(base + (size_t)row * pitch + (size_t)c4 * 16) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  uint32_t b = blockIdx.x;
+  prefetch(b, cur);
+  for (; b < nblocks; b += gridDim.x) {
+    const Tile t = tile_of(g, b);
+    const pxz_block_desc d = descs[b];
+    const uint32_t ti = tabidx[b];
+    uint4 nxt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nxt[j] = make_uint4(0, 0, 0, 0);
+    prefetch(b + gridDim.x, nxt);
+    uint8_t* dst = payload + d.offset;
+    const uint32_t sw = t.tw, sh = t.th, dw = d.w, dh = d.h;
+    if (sw == dw && sh == dh) {
+      // block.rs:279-281: clone.  The tile is contiguous in the payload (4-byte aligned only).
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t q = tid + j * kThreads, row = q / qpr, c4 = q - row * qpr;
+        if (row < sh && c4 * 4 < sw) {
+          uint32_t* o = reinterpret_cast<uint32_t*>(dst) + (size_t)row * sw + c4 * 4;
+          o[0] = cur[j].x; o[1] = cur[j].y; o[2] = cur[j].z; o[3] = cur[j].w;
+        }
+      }
+    } else {
+      const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
+      stage_table(ty, pool, sm.taby);
+      stage_table(tx, pool, sm.tabx);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t q = tid + j * kThreads, row = q / qpr, c4 = q - row * qpr;
+        if (row < sh && c4 * 4 < sw) {
+          float4* o = sm.src + row * sw + c4 * 4;
+          o[0] = px_to_f4(cur[j].x); o[1] = px_to_f4(cur[j].y); o[2] = px_to_f4(cur[j].z); o[3] = px_to_f4(cur[j].w);
+        }
+      }
+      __syncthreads();
+      fast_vertical(sm.src, sm.tmp, sw, dh, sm.taby, ty.stride);
+      __syncthreads();
+      uint32_t* out = reinterpret_cast<uint32_t*>(dst);
+      for (uint32_t i = tid; i < dw * dh; i += kThreads) {
+        const uint32_t oy = i / dw, ox = i - oy * dw;
+        out[i] = fast_horizontal_px(sm.tmp + oy * sw, ox, dw, sm.tabx, tx.stride);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+  }
+}
+
+// ---- decode side: packed payload blocks -> 64x64-or-smaller tiles of the pitched image (expand + paste) ------
+__global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                             const pxz_block_desc* __restrict__ descs,
+                                                             const uint32_t* __restrict__ tabidx,
+                                                             const uint8_t* __restrict__ payload,
+                                                             const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool,
+                                                             uint32_t max_tmp_px) {
+  extern __shared__ float s_dyn[];
+  const FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nblocks = g.cols * g.rows;
+
+  uint32_t cur[16];
+  pxz_block_desc dcur;
+  auto prefetch = [&](uint32_t b, uint32_t(&v)[16], pxz_block_desc& d) {
+    if (b >= nblocks) { d.w = 0; d.h = 0; d.offset = 0; return; }
+    d = descs[b];
+    const uint32_t n = (uint32_t)d.w * d.h;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(payload + d.offset);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t i = tid + j * kThreads;
+      v[j] = i < n ? __ldg(p + i) : 0u;
+    }
+  };
+  uint32_t b = blockIdx.x;
+  prefetch(b, cur, dcur);
+  for (; b < nblocks; b += gridDim.x) {
+    const Tile t = tile_of(g, b);
+    const pxz_block_desc d = dcur;
+    const uint32_t ti = tabidx[b];
+    uint32_t nxt[16];
+    pxz_block_desc dnxt;
+    prefetch(b + gridDim.x, nxt, dnxt);
+    uint8_t* dst = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
+    const uint32_t sw = d.w, sh = d.h, dw = t.tw, dh = t.th;
+    if (sw == dw && sh == dh) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t i = tid + j * kThreads;
+        if (i < sw * sh) {
+          const uint32_t y = i / sw, x = i - y * sw;
+          *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + (size_t)x * 4) = cur[j];
+        }
+      }
+    } else {
+      const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
+      stage_table(ty, pool, sm.taby);
+      stage_table(tx, pool, sm.tabx);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t i = tid + j * kThreads;
+        if (i < sw * sh) sm.src[i] = px_to_f4(cur[j]);
+      }
+      __syncthreads();
+      fast_vertical(sm.src, sm.tmp, sw, dh, sm.taby, ty.stride);
+      __syncthreads();
+      // one output pixel per thread and row; lanes per row = next power of two >= dw
+      const uint32_t lshift = dw <= 1 ? 0 : 32 - __clz(dw - 1);
+      const uint32_t ox = tid & ((1u << lshift) - 1), g0 = tid >> lshift, ng = kThreads >> lshift;
+      if (ox < dw) {
+        for (uint32_t oy = g0; oy < dh; oy += ng) {
+          *reinterpret_cast<uint32_t*>(dst + (size_t)oy * pitch + (size_t)ox * 4) =
+              fast_horizontal_px(sm.tmp + oy * sw, ox, dw, sm.tabx, tx.stride);
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+    dcur = dnxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static inline int clamp_grid(long long want, long long cap) { return (int)(want < 1 ? 1 : (want > cap ? cap : want)); }
@@ -1037,12 +1278,29 @@ int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (
 
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
-                            uint32_t max_src_px, uint32_t max_tmp_px, uint8_t* scratch, size_t scratch_per_cta,
-                            int grid, cudaStream_t s, int sm_count, uint64_t* launches) {
-  (void)sm_count;
-  const size_t smem = scratch ? 0 : resample_smem_bytes(max_src_px, max_tmp_px, g.C);
+                            uint32_t max_src_px, uint32_t max_tmp_px, uint32_t max_tab_words, uint8_t* scratch,
+                            size_t scratch_per_cta, int grid, cudaStream_t s, int sm_count, uint64_t* launches) {
   cudaError_t e;
   ++*launches;
+  // RGBA fast paths: tiles <= 64x64 with 16-byte aligned rows
+  const bool fast = g.C == 4 && g.bw <= 64 && g.bh <= 64 && (g.bw % 4 == 0) && (g.W % 4 == 0) && (pitch % 16 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && max_src_px <= (uint32_t)kFastMaxPx &&
+                    max_tmp_px <= (uint32_t)kFastMaxPx && max_tab_words <= (uint32_t)kFastMaxTabWords && scratch == nullptr;
+  if (fast) {
+    const size_t smem = (size_t)(kFastMaxPx + max_tmp_px) * sizeof(float4) + 2 * (size_t)kFastMaxTabWords * sizeof(uint32_t);
+    const int fgrid = clamp_grid((long long)g.cols * g.rows, (long long)sm_count * 2);
+    if (direction == 0) {
+      e = set_smem(k_shrink_rgba, smem);
+      if (e != cudaSuccess) return e;
+      k_shrink_rgba<<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+    } else {
+      e = set_smem(k_expand_rgba, smem);
+      if (e != cudaSuccess) return e;
+      k_expand_rgba<<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+    }
+    return cudaGetLastError();
+  }
+  const size_t smem = scratch ? 0 : resample_smem_bytes(max_src_px, max_tmp_px, g.C);
   if (g.C == 4) {
     e = set_smem(k_resample<4>, smem);
     if (e != cudaSuccess) return e;
