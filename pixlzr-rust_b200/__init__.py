@@ -19,3 +19,4 @@ from .api import (  # noqa: F401
     reduce_image_section,
 )
 from . import _native as native  # noqa: F401
+from . import sharding  # noqa: F401

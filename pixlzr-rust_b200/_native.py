@@ -148,6 +148,12 @@ class Context:
             i += 1
         return out
 
+    def comm_init(self, nranks: int, rank: int, comm_id: bytes):
+        """Joins the NCCL communicator used by PXZ_FLAG_NORMALISE_GLOBAL (all ranks must call this)."""
+        assert len(comm_id) == COMM_ID_BYTES
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self.check(lib().pxz_comm_init(self._h, nranks, rank, buf))
+
     def close(self):
         if self._h:
             lib().pxz_ctx_destroy(self._h)
@@ -300,6 +306,14 @@ def reduce_dims(v0: float, v1: float, w: int, h: int):
     if rc != OK:
         raise PixlzrError(rc, "pxz_reduce_dims")
     return ow.value, oh.value, st.value
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    st = lib().pxz_comm_unique_id(buf)
+    if st != OK:
+        raise PixlzrError(st, "pxz_comm_unique_id (is libnccl.so.2 loadable?)")
+    return bytes(buf)
 
 
 def device_count() -> int:
