@@ -103,6 +103,7 @@ struct pxz_payload {
   uint64_t bytes = 0;
   std::shared_ptr<TabSpec> spec;
   uint32_t max_small_px = 0;  // largest reduced block (pixels)
+  uint32_t max_small_dim = 0; // largest reduced block side
   uint32_t max_tmp_down = 0;  // largest vertical-pass intermediate when shrinking / expanding (pixels)
   uint32_t max_tmp_up = 0;
 };
@@ -242,7 +243,7 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
     seen[{n_in, n_out}] = tabs[i];
   }
   TabSet ts;
-  for (const AxisTab& t : tabs) ts.max_words = std::max(ts.max_words, 2 * t.n_out + t.n_out * t.stride);
+  for (const AxisTab& t : tabs) ts.max_words = std::max(ts.max_words, std::max(2 * t.n_out + t.n_out * t.stride, t.bwords));
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_tabs, tabs.size() * sizeof(AxisTab))) != PXZ_OK) return st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_pool, pool.size() * 4)) != PXZ_OK) return st;
@@ -256,7 +257,7 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
 }
 
 pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch, const pxz_payload* p, const TabSet& ts,
-                        uint32_t max_src_px, uint32_t max_tmp_px) {
+                        uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px) {
   const Geom& g = p->g;
   const uint32_t nblocks = g.cols * g.rows;
   size_t smem = resample_smem_bytes(max_src_px, max_tmp_px, g.C);
@@ -279,7 +280,7 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   }
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
-                                max_src_px, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->stream, ctx->sm_count,
+                                max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->stream, ctx->sm_count,
                                 &ctx->launches));
   return PXZ_OK;
 }
@@ -647,15 +648,16 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
     // shared-memory bounds of the two resample directions for this geometry
     const bool coupled = metric == PXZ_METRIC_OKLAB_MAD;  // both axes share the level
     const uint32_t tw_max = g.bw, th_max = g.bh;
+    auto pad8 = [](uint32_t v) { return (v + 7u) & ~7u; };  // intermediate rows are padded to 8 columns
     p->max_small_px = tw_max * th_max;
+    p->max_small_dim = std::max(tw_max, th_max);
     if (coupled) {
-      p->max_tmp_down = ((th_max + 1) / 2) * tw_max;  // dh <= ceil(th/2), sw = tw
-      p->max_tmp_up = th_max * ((tw_max + 1) / 2);    // dh = th, sw <= ceil(tw/2)
-      p->max_small_px = ((th_max + 1) / 2) * ((tw_max + 1) / 2);
+      p->max_tmp_down = ((th_max + 1) / 2) * pad8(tw_max);  // dh <= ceil(th/2), sw = tw
+      p->max_tmp_up = th_max * pad8((tw_max + 1) / 2);      // dh = th, sw <= ceil(tw/2)
       // a 1-px-wide/-high trailing tile keeps that axis while the other shrinks: still within the bounds
     } else {
-      p->max_tmp_down = th_max * tw_max;
-      p->max_tmp_up = th_max * tw_max;
+      p->max_tmp_down = th_max * pad8(tw_max);
+      p->max_tmp_up = th_max * pad8(tw_max);
     }
   }
   cudaError_t e;
@@ -670,7 +672,7 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   }
   TabSet ts;
   st = get_tabset(ctx, *p->spec, (int)filter_down, 0, &ts);
-  if (st == PXZ_OK) st = run_resample(ctx, 0, img->d, img->pitch, p, ts, g.bw * g.bh, p->max_tmp_down);
+  if (st == PXZ_OK) st = run_resample(ctx, 0, img->d, img->pitch, p, ts, g.bw * g.bh, std::max(g.bw, g.bh), p->max_tmp_down);
   if (st != PXZ_OK) {
     payload_release(p);
     return st;
@@ -766,7 +768,8 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
   auto spec = std::make_shared<TabSpec>();
   std::map<std::pair<uint32_t, uint32_t>, uint32_t> index;
   std::vector<uint32_t> tabidx(nblocks);
-  uint32_t max_small = 1, max_tmp_up = 1, max_tmp_down = 1;
+  uint32_t max_small = 1, max_tmp_up = 1, max_tmp_down = 1, max_dim = 1;
+  auto pad8 = [](uint32_t v) { return (v + 7u) & ~7u; };
   auto idx_of = [&](uint32_t small, uint32_t tile) -> uint32_t {
     auto it = index.find({small, tile});
     if (it != index.end()) return it->second;
@@ -790,14 +793,16 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
     if (ix > 0xFFFFu || iy > 0xFFFFu) return fail(ctx, PXZ_E_UNSUPPORTED, "more than 65536 distinct block sizes");
     tabidx[b] = ix | (iy << 16);
     max_small = std::max(max_small, (uint32_t)d.w * d.h);
-    max_tmp_up = std::max(max_tmp_up, th * (uint32_t)d.w);
-    max_tmp_down = std::max(max_tmp_down, (uint32_t)d.h * tw);
+    max_dim = std::max(max_dim, (uint32_t)std::max(d.w, d.h));
+    max_tmp_up = std::max(max_tmp_up, th * pad8(d.w));
+    max_tmp_down = std::max(max_tmp_down, (uint32_t)d.h * pad8(tw));
   }
   pxz_payload* p = nullptr;
   st = payload_new(ctx, g, bytes, &p);
   if (st != PXZ_OK) return st;
   p->spec = spec;
   p->max_small_px = max_small;
+  p->max_small_dim = max_dim;
   p->max_tmp_up = max_tmp_up;
   p->max_tmp_down = max_tmp_down;
   p->bytes = bytes;
@@ -827,7 +832,7 @@ pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter fi
   TabSet ts;
   pxz_status st = get_tabset(ctx, *p->spec, (int)filter_up, 1, &ts);
   if (st != PXZ_OK) return st;
-  return run_resample(ctx, 1, out->d, out->pitch, p, ts, p->max_small_px, p->max_tmp_up);
+  return run_resample(ctx, 1, out->d, out->pitch, p, ts, p->max_small_px, p->max_small_dim, p->max_tmp_up);
 }
 
 pxz_status pxz_expand(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, uint8_t* host_out, size_t host_pitch) {

@@ -918,21 +918,24 @@ __global__ void __launch_bounds__(kThreads) k_resample(int direction, uint8_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// RGBA fast paths of the resample: tiles of at most 64x64 (4096 px, 1024 16-byte quads), 16-byte
-// aligned tile rows.  Same arithmetic and accumulation order as k_resample (so the pixels stay
-// bit-identical), but
+// RGBA fast paths of the resample: blocks of at most 64x64 (4096 px), 16-byte aligned tile rows.
+// Same arithmetic and accumulation order as k_resample (so the pixels stay bit-identical), but
 //   * the next block's source is prefetched into registers while the current one is resampled
 //     (persistent CTAs, grid-stride), so global-load latency is off the critical path;
-//   * the source block is converted u8 -> f32 once, into shared memory;
-//   * the tap tables of the block's two axes are staged in shared memory;
-//   * no integer division in the inner loops.
+//   * the source block is converted u8 -> f32 once, into shared memory (row stride 64, XOR swizzle);
+//   * outputs are produced in groups of 4 that share one walk over the source samples (blocked tap
+//     tables, AxisTab::boff): one 16-byte source load + one broadcast 16-byte weight load feed 16
+//     multiply-adds, so the kernel is bound by the FP32 pipe and not by shared-memory bandwidth;
+//   * when every alpha of the block is 255 the alpha channel is not computed (it resamples to 255);
+//   * rounding to u8 avoids the conversion pipe.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastMaxPx = 4096;
-constexpr int kFastMaxTabWords = 1024;  // left | count | weights of one axis (checked on the host: max_tab_words)
+constexpr int kFastMaxTabWords = 1024;  // one staged table section (checked on the host: max_tab_words)
+constexpr int kSrcStride = 64;          // float4 per source row in shared memory
 
 struct FastSmem {
-  float4* src;     // [4096]
-  float4* tmp;     // [max_tmp_px]
+  float4* src;     // [64][64], column index swizzled by swz_src()
+  float4* tmp;     // [dh][ts], ts = sw rounded up to 8, column index XORed with (row & 7)
   uint32_t* taby;  // [kFastMaxTabWords]
   uint32_t* tabx;
 };
@@ -946,70 +949,185 @@ __device__ __forceinline__ FastSmem carve_fast_smem(float* base, uint32_t max_tm
   return s;
 }
 
-__device__ __forceinline__ void stage_table(const AxisTab& t, const uint32_t* __restrict__ pool, uint32_t* dst) {
-  const uint32_t words = 2 * t.n_out + t.n_out * t.stride;
-  for (uint32_t i = threadIdx.x; i < words; i += kThreads) dst[i] = __ldg(pool + t.off + i);
+// quad-mapped stores (lane l writes pixels 4l+i) and column-mapped loads are both conflict free
+__device__ __forceinline__ uint32_t swz_src(uint32_t x) { return x ^ ((x >> 3) & 7u); }
+
+__device__ __forceinline__ void stage_words(const uint32_t* __restrict__ src, uint32_t words, uint32_t* dst) {
+  for (uint32_t i = threadIdx.x; i < words; i += kThreads) dst[i] = __ldg(src + i);
 }
 
 __device__ __forceinline__ float4 px_to_f4(uint32_t w) {
   return make_float4(byte_to_float<0>(w), byte_to_float<1>(w), byte_to_float<2>(w), byte_to_float<3>(w));
 }
-__device__ __forceinline__ uint32_t f4_to_px(const float4& a) {
-  return to_u8(a.x) | (to_u8(a.y) << 8) | (to_u8(a.z) << 16) | (to_u8(a.w) << 24);
+
+// NumCast::from(FloatNearest(clamp(t, 0, 255))): round half away from zero, without F2I/I2F.
+// u = t + 2^23 rounds to nearest-even into the low mantissa bits; an exact .5 tie that went down is bumped.
+__device__ __forceinline__ uint32_t to_u8_fast(float t) {
+  t = fminf(fmaxf(t, 0.0f), 255.0f);
+  const float u = __fadd_rn(t, 8388608.0f);
+  const float r = __fadd_rn(u, -8388608.0f);
+  uint32_t q = __float_as_uint(u) & 0xFFu;
+  if (__fadd_rn(t, -r) == 0.5f) q += 1;
+  return q;
 }
-// acc += p * w, sequential f32, no contraction (image 0.25.5 sample loops)
-__device__ __forceinline__ void mac4(float4& acc, const float4& p, float w) {
+
+template <bool ALPHA>
+__device__ __forceinline__ void mac(float4& acc, const float4& p, float w) {
   acc.x = __fadd_rn(acc.x, __fmul_rn(p.x, w));
   acc.y = __fadd_rn(acc.y, __fmul_rn(p.y, w));
   acc.z = __fadd_rn(acc.z, __fmul_rn(p.z, w));
-  acc.w = __fadd_rn(acc.w, __fmul_rn(p.w, w));
+  if (ALPHA) acc.w = __fadd_rn(acc.w, __fmul_rn(p.w, w));
+}
+template <bool ALPHA>
+__device__ __forceinline__ uint32_t pack_px(const float4& a) {
+  return to_u8_fast(a.x) | (to_u8_fast(a.y) << 8) | (to_u8_fast(a.z) << 16) | (ALPHA ? (to_u8_fast(a.w) << 24) : 0xFF000000u);
 }
 
-// vertical_sample: src [sh][sw] -> tmp [dh][sw].  Lanes per row = next power of two >= sw.
-__device__ __forceinline__ void fast_vertical(const float4* src, float4* tmp, uint32_t sw, uint32_t dh, const uint32_t* taby,
-                                              uint32_t stride) {
-  const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);
-  const uint32_t x = threadIdx.x & ((1u << lshift) - 1), g = threadIdx.x >> lshift, ng = kThreads >> lshift;
+// One staged axis table: either the blocked form (outputs in groups of 4) or the per-output form.
+struct StagedTab {
+  bool blocked;
+  uint32_t n_out, stride, nb;
+  const uint32_t* base;  // shared memory
+  // blocked: w4 at base, then lo | rows | first
+  __device__ __forceinline__ const float4* w4() const { return reinterpret_cast<const float4*>(base); }
+  __device__ __forceinline__ const uint32_t* blo(uint32_t rows_total) const { return base + 4 * rows_total; }
+};
+
+// ---- vertical_sample: src [sh][64] -> tmp [dh][ts] ---------------------------------------------------------------
+template <bool ALPHA>
+__device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
+                                                 const AxisTab& ty, const uint32_t* taby) {
+  const uint32_t x = threadIdx.x & 63u, grp = threadIdx.x >> 6;
+  if (x >= sw) return;
+  const float4* w4 = reinterpret_cast<const float4*>(taby);
+  const uint32_t* lo = taby + 4 * ty.brows_total;
+  const uint32_t* rows = lo + ty.nb;
+  const uint32_t* first = rows + ty.nb;
+  const uint32_t xs = swz_src(x);
+  for (uint32_t ob = grp; ob < ty.nb; ob += kThreads / 64) {
+    const uint32_t n = rows[ob];
+    const float4* wp = w4 + first[ob];
+    const float4* sp = src + lo[ob] * kSrcStride + xs;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    uint32_t r = 0;
+    for (; r + 2 <= n; r += 2) {
+      const float4 p0 = sp[0], p1 = sp[kSrcStride];
+      const float4 w0 = wp[r], w1 = wp[r + 1];
+      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
+      mac<ALPHA>(a0, p1, w1.x); mac<ALPHA>(a1, p1, w1.y); mac<ALPHA>(a2, p1, w1.z); mac<ALPHA>(a3, p1, w1.w);
+      sp += 2 * kSrcStride;
+    }
+    if (r < n) {
+      const float4 p0 = sp[0];
+      const float4 w0 = wp[r];
+      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
+    }
+    const uint32_t oy = ob * 4;
+    tmp[(oy + 0) * ts + (x ^ ((oy + 0) & 7u))] = a0;
+    if (oy + 1 < dh) tmp[(oy + 1) * ts + (x ^ ((oy + 1) & 7u))] = a1;
+    if (oy + 2 < dh) tmp[(oy + 2) * ts + (x ^ ((oy + 2) & 7u))] = a2;
+    if (oy + 3 < dh) tmp[(oy + 3) * ts + (x ^ ((oy + 3) & 7u))] = a3;
+  }
+}
+
+template <bool ALPHA>
+__device__ __forceinline__ void vertical_plain(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
+                                               const AxisTab& ty, const uint32_t* taby) {
+  const uint32_t x = threadIdx.x & 63u, grp = threadIdx.x >> 6;
   if (x >= sw) return;
   const uint32_t* left = taby;
   const uint32_t* cnt = taby + dh;
   const float* w = reinterpret_cast<const float*>(taby + 2 * dh);
-  for (uint32_t oy = g; oy < dh; oy += ng) {
+  const uint32_t xs = swz_src(x);
+  for (uint32_t oy = grp; oy < dh; oy += kThreads / 64) {
     const uint32_t n = cnt[oy];
-    const float* wr = w + oy * stride;
-    const float4* sp = src + left[oy] * sw + x;
+    const float* wr = w + oy * ty.stride;
+    const float4* sp = src + left[oy] * kSrcStride + xs;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t k = 0;
-    for (; k + 4 <= n; k += 4) {  // loads first, then the dependent chain
-      const float4 p0 = sp[0], p1 = sp[sw], p2 = sp[2 * sw], p3 = sp[3 * sw];
+    for (; k + 4 <= n; k += 4) {
+      const float4 p0 = sp[0], p1 = sp[kSrcStride], p2 = sp[2 * kSrcStride], p3 = sp[3 * kSrcStride];
       const float w0 = wr[k], w1 = wr[k + 1], w2 = wr[k + 2], w3 = wr[k + 3];
-      mac4(acc, p0, w0); mac4(acc, p1, w1); mac4(acc, p2, w2); mac4(acc, p3, w3);
-      sp += 4 * sw;
+      mac<ALPHA>(acc, p0, w0); mac<ALPHA>(acc, p1, w1); mac<ALPHA>(acc, p2, w2); mac<ALPHA>(acc, p3, w3);
+      sp += 4 * kSrcStride;
     }
     for (; k < n; ++k) {
-      mac4(acc, sp[0], wr[k]);
-      sp += sw;
+      mac<ALPHA>(acc, sp[0], wr[k]);
+      sp += kSrcStride;
     }
-    tmp[oy * sw + x] = acc;
+    tmp[oy * ts + (x ^ (oy & 7u))] = acc;
   }
 }
 
-// horizontal_sample of one output pixel: tmp row (stride sw) -> clamp/round -> packed RGBA
-__device__ __forceinline__ uint32_t fast_horizontal_px(const float4* tmp_row, uint32_t ox, uint32_t dw, const uint32_t* tabx,
-                                                       uint32_t stride) {
-  const uint32_t n = tabx[dw + ox];
-  const float* wr = reinterpret_cast<const float*>(tabx + 2 * dw) + ox * stride;
-  const float4* sp = tmp_row + tabx[ox];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t k = 0;
-  for (; k + 4 <= n; k += 4) {
-    const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];
-    const float w0 = wr[k], w1 = wr[k + 1], w2 = wr[k + 2], w3 = wr[k + 3];
-    mac4(acc, p0, w0); mac4(acc, p1, w1); mac4(acc, p2, w2); mac4(acc, p3, w3);
-    sp += 4;
+// ---- horizontal_sample: tmp [dh][ts] -> packed RGBA pixels, written through `put(oy, ox, n, px[4])` ------------------
+template <bool ALPHA, typename Put>
+__device__ __forceinline__ void horizontal_blocked(const float4* tmp, uint32_t ts, uint32_t dw, uint32_t dh, const AxisTab& tx,
+                                                   const uint32_t* tabx, Put put) {
+  const float4* w4 = reinterpret_cast<const float4*>(tabx);
+  const uint32_t* lo = tabx + 4 * tx.brows_total;
+  const uint32_t* rows = lo + tx.nb;
+  const uint32_t* first = rows + tx.nb;
+  const uint32_t hshift = dh <= 1 ? 0 : 32 - __clz(dh - 1);  // lanes = consecutive output rows
+  const uint32_t items = tx.nb << hshift;
+  for (uint32_t i = threadIdx.x; i < items; i += kThreads) {
+    const uint32_t oy = i & ((1u << hshift) - 1), ob = i >> hshift;
+    if (oy >= dh) continue;
+    const uint32_t n = rows[ob], c0 = lo[ob], s7 = oy & 7u;
+    const float4* wp = w4 + first[ob];
+    const float4* trow = tmp + oy * ts;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    uint32_t c = 0;
+    for (; c + 2 <= n; c += 2) {
+      const float4 p0 = trow[(c0 + c) ^ s7], p1 = trow[(c0 + c + 1) ^ s7];
+      const float4 w0 = wp[c], w1 = wp[c + 1];
+      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
+      mac<ALPHA>(a0, p1, w1.x); mac<ALPHA>(a1, p1, w1.y); mac<ALPHA>(a2, p1, w1.z); mac<ALPHA>(a3, p1, w1.w);
+    }
+    if (c < n) {
+      const float4 p0 = trow[(c0 + c) ^ s7];
+      const float4 w0 = wp[c];
+      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
+    }
+    const uint32_t ox = ob * 4;
+    const uint32_t nvalid = min(4u, dw - ox);
+    uint32_t px[4] = {pack_px<ALPHA>(a0), pack_px<ALPHA>(a1), pack_px<ALPHA>(a2), pack_px<ALPHA>(a3)};
+    put(oy, ox, nvalid, px);
   }
-  for (; k < n; ++k) mac4(acc, *sp++, wr[k]);
-  return f4_to_px(acc);
+}
+
+template <bool ALPHA, typename Put>
+__device__ __forceinline__ void horizontal_plain(const float4* tmp, uint32_t ts, uint32_t dw, uint32_t dh, const AxisTab& tx,
+                                                 const uint32_t* tabx, Put put) {
+  const uint32_t* left = tabx;
+  const uint32_t* cnt = tabx + dw;
+  const float* w = reinterpret_cast<const float*>(tabx + 2 * dw);
+  for (uint32_t i = threadIdx.x; i < dw * dh; i += kThreads) {
+    const uint32_t oy = i / dw, ox = i - oy * dw, s7 = oy & 7u;
+    const uint32_t n = cnt[ox], c0 = left[ox];
+    const float* wr = w + ox * tx.stride;
+    const float4* trow = tmp + oy * ts;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t k = 0; k < n; ++k) mac<ALPHA>(acc, trow[(c0 + k) ^ s7], wr[k]);
+    uint32_t px[4] = {pack_px<ALPHA>(acc), 0, 0, 0};
+    put(oy, ox, 1u, px);
+  }
+}
+
+// the two passes for one staged block; `put` writes up to 4 horizontally adjacent output pixels
+template <bool ALPHA, typename Put>
+__device__ __forceinline__ void resample_staged(const FastSmem& sm, uint32_t sw, uint32_t dw, uint32_t dh, const AxisTab& tx,
+                                                const AxisTab& ty, bool yblocked, bool xblocked, Put put) {
+  const uint32_t ts = (sw + 7u) & ~7u;
+  if (yblocked) vertical_blocked<ALPHA>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
+  else vertical_plain<ALPHA>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
+  __syncthreads();
+  if (xblocked) horizontal_blocked<ALPHA>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
+  else horizontal_plain<ALPHA>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
+}
+
+__device__ __forceinline__ void stage_axis(const AxisTab& t, bool blocked, const uint32_t* __restrict__ pool, uint32_t* dst) {
+  if (blocked) stage_words(pool + t.boff, t.bwords, dst);
+  else stage_words(pool + t.off, 2 * t.n_out + t.n_out * t.stride, dst);
 }
 
 // ---- encode side: 64x64-or-smaller tiles of the pitched image -> packed payload -----------------------------
@@ -1023,6 +1141,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
   const uint32_t tid = threadIdx.x;
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t qpr = g.bw >> 2;  // 16-byte quads per full tile row
+  uint32_t qrow[4], qcol[4];       // this thread's four quads: fixed for the whole launch
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t q = tid + j * kThreads;
+    qrow[j] = q / qpr;
+    qcol[j] = (q - qrow[j] * qpr) * 4;
+  }
 
   uint4 cur[4];
   auto prefetch = [&](uint32_t b, uint4(&v)[4]) {
@@ -1030,10 +1155,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
     const Tile t = tile_of(g, b);
     const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t q = tid + j * kThreads, row = q / qpr, c4 = q - row * qpr;
-      v[j] = (row < t.th && c4 * 4 < t.tw) ? ldg_nc_v4(base + (size_t)row * pitch + (size_t)c4 * 16) : make_uint4(0, 0, 0, 0);
-    }
+    for (int j = 0; j < 4; ++j)
+      v[j] = (qrow[j] < t.th && qcol[j] < t.tw) ? ldg_nc_v4(base + (size_t)qrow[j] * pitch + (size_t)qcol[j] * 4)
+                                                 : make_uint4(0xFF000000u, 0xFF000000u, 0xFF000000u, 0xFF000000u);
   };
   uint32_t b = blockIdx.x;
   prefetch(b, cur);
@@ -1045,38 +1169,44 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) nxt[j] = make_uint4(0, 0, 0, 0);
     prefetch(b + gridDim.x, nxt);
-    uint8_t* dst = payload + d.offset;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset);
     const uint32_t sw = t.tw, sh = t.th, dw = d.w, dh = d.h;
     if (sw == dw && sh == dh) {
       // block.rs:279-281: clone.  The tile is contiguous in the payload (4-byte aligned only).
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t q = tid + j * kThreads, row = q / qpr, c4 = q - row * qpr;
-        if (row < sh && c4 * 4 < sw) {
-          uint32_t* o = reinterpret_cast<uint32_t*>(dst) + (size_t)row * sw + c4 * 4;
+        if (qrow[j] < sh && qcol[j] < sw) {
+          uint32_t* o = dst + (size_t)qrow[j] * sw + qcol[j];
           o[0] = cur[j].x; o[1] = cur[j].y; o[2] = cur[j].z; o[3] = cur[j].w;
         }
       }
     } else {
       const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
-      stage_table(ty, pool, sm.taby);
-      stage_table(tx, pool, sm.tabx);
+      const bool yb = dh >= 8, xb = dw >= 8 && dh >= 8;
+      stage_axis(ty, yb, pool, sm.taby);
+      stage_axis(tx, xb, pool, sm.tabx);
+      uint32_t aand = 0xFF000000u;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t q = tid + j * kThreads, row = q / qpr, c4 = q - row * qpr;
-        if (row < sh && c4 * 4 < sw) {
-          float4* o = sm.src + row * sw + c4 * 4;
-          o[0] = px_to_f4(cur[j].x); o[1] = px_to_f4(cur[j].y); o[2] = px_to_f4(cur[j].z); o[3] = px_to_f4(cur[j].w);
+        aand &= (cur[j].x & cur[j].y) & (cur[j].z & cur[j].w);  // out-of-tile quads were filled with alpha 255
+        if (qrow[j] < sh && qcol[j] < sw) {
+          float4* o = sm.src + qrow[j] * kSrcStride;
+          o[swz_src(qcol[j] + 0)] = px_to_f4(cur[j].x);
+          o[swz_src(qcol[j] + 1)] = px_to_f4(cur[j].y);
+          o[swz_src(qcol[j] + 2)] = px_to_f4(cur[j].z);
+          o[swz_src(qcol[j] + 3)] = px_to_f4(cur[j].w);
         }
       }
-      __syncthreads();
-      fast_vertical(sm.src, sm.tmp, sw, dh, sm.taby, ty.stride);
-      __syncthreads();
-      uint32_t* out = reinterpret_cast<uint32_t*>(dst);
-      for (uint32_t i = tid; i < dw * dh; i += kThreads) {
-        const uint32_t oy = i / dw, ox = i - oy * dw;
-        out[i] = fast_horizontal_px(sm.tmp + oy * sw, ox, dw, sm.tabx, tx.stride);
-      }
+      const bool opaque = __syncthreads_and(aand == 0xFF000000u) != 0;  // also the barrier after staging
+      auto put = [&](uint32_t oy, uint32_t ox, uint32_t n, const uint32_t(&px)[4]) {
+        uint32_t* o = dst + (size_t)oy * dw + ox;
+        o[0] = px[0];
+        if (n > 1) o[1] = px[1];
+        if (n > 2) o[2] = px[2];
+        if (n > 3) o[3] = px[3];
+      };
+      if (opaque) resample_staged<false>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      else resample_staged<true>(sm, sw, dw, dh, tx, ty, yb, xb, put);
       __syncthreads();
     }
 #pragma unroll
@@ -1106,7 +1236,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const uint32_t i = tid + j * kThreads;
-      v[j] = i < n ? __ldg(p + i) : 0u;
+      v[j] = i < n ? __ldg(p + i) : 0xFF000000u;
     }
   };
   uint32_t b = blockIdx.x;
@@ -1120,36 +1250,45 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
     prefetch(b + gridDim.x, nxt, dnxt);
     uint8_t* dst = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
     const uint32_t sw = d.w, sh = d.h, dw = t.tw, dh = t.th;
+    const bool pow2 = (sw & (sw - 1)) == 0;
+    const uint32_t sshift = 31 - __clz(sw);
     if (sw == dw && sh == dh) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const uint32_t i = tid + j * kThreads;
         if (i < sw * sh) {
-          const uint32_t y = i / sw, x = i - y * sw;
+          const uint32_t y = pow2 ? (i >> sshift) : (i / sw), x = i - y * sw;
           *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + (size_t)x * 4) = cur[j];
         }
       }
     } else {
       const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
-      stage_table(ty, pool, sm.taby);
-      stage_table(tx, pool, sm.tabx);
+      const bool yb = dh >= 8, xb = dw >= 8 && dh >= 8;
+      stage_axis(ty, yb, pool, sm.taby);
+      stage_axis(tx, xb, pool, sm.tabx);
+      uint32_t aand = 0xFF000000u;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const uint32_t i = tid + j * kThreads;
-        if (i < sw * sh) sm.src[i] = px_to_f4(cur[j]);
-      }
-      __syncthreads();
-      fast_vertical(sm.src, sm.tmp, sw, dh, sm.taby, ty.stride);
-      __syncthreads();
-      // one output pixel per thread and row; lanes per row = next power of two >= dw
-      const uint32_t lshift = dw <= 1 ? 0 : 32 - __clz(dw - 1);
-      const uint32_t ox = tid & ((1u << lshift) - 1), g0 = tid >> lshift, ng = kThreads >> lshift;
-      if (ox < dw) {
-        for (uint32_t oy = g0; oy < dh; oy += ng) {
-          *reinterpret_cast<uint32_t*>(dst + (size_t)oy * pitch + (size_t)ox * 4) =
-              fast_horizontal_px(sm.tmp + oy * sw, ox, dw, sm.tabx, tx.stride);
+        aand &= cur[j];
+        if (i < sw * sh) {
+          const uint32_t y = pow2 ? (i >> sshift) : (i / sw), x = i - y * sw;
+          sm.src[y * kSrcStride + swz_src(x)] = px_to_f4(cur[j]);
         }
       }
+      const bool opaque = __syncthreads_and((aand & 0xFF000000u) == 0xFF000000u) != 0;
+      auto put = [&](uint32_t oy, uint32_t ox, uint32_t n, const uint32_t(&px)[4]) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(dst + (size_t)oy * pitch) + ox;
+        if (n == 4) {
+          *reinterpret_cast<uint4*>(o) = make_uint4(px[0], px[1], px[2], px[3]);  // tile rows are 16-byte aligned
+        } else {
+          o[0] = px[0];
+          if (n > 1) o[1] = px[1];
+          if (n > 2) o[2] = px[2];
+        }
+      };
+      if (opaque) resample_staged<false>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      else resample_staged<true>(sm, sw, dw, dh, tx, ty, yb, xb, put);
       __syncthreads();
     }
 #pragma unroll
@@ -1278,13 +1417,13 @@ int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (
 
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
-                            uint32_t max_src_px, uint32_t max_tmp_px, uint32_t max_tab_words, uint8_t* scratch,
+                            uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words, uint8_t* scratch,
                             size_t scratch_per_cta, int grid, cudaStream_t s, int sm_count, uint64_t* launches) {
   cudaError_t e;
   ++*launches;
   // RGBA fast paths: tiles <= 64x64 with 16-byte aligned rows
   const bool fast = g.C == 4 && g.bw <= 64 && g.bh <= 64 && (g.bw % 4 == 0) && (g.W % 4 == 0) && (pitch % 16 == 0) &&
-                    ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && max_src_px <= (uint32_t)kFastMaxPx &&
+                    ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && max_src_px <= (uint32_t)kFastMaxPx && max_src_dim <= 64u &&
                     max_tmp_px <= (uint32_t)kFastMaxPx && max_tab_words <= (uint32_t)kFastMaxTabWords && scratch == nullptr;
   if (fast) {
     const size_t smem = (size_t)(kFastMaxPx + max_tmp_px) * sizeof(float4) + 2 * (size_t)kFastMaxTabWords * sizeof(uint32_t);

@@ -17,8 +17,14 @@ constexpr uint32_t kLevelOnePixel = 0xFFu; // "level 0" / below every threshold:
 
 // One axis of a separable resample: n_in source samples -> n_out outputs.
 // Pool layout at `off` (32-bit words): left[n_out] | count[n_out] | weights[n_out * stride] (f32 bits).
+// Blocked form at `boff` (outputs in groups of 4, nb = ceil(n_out / 4) groups; pool offset is a multiple of 4 words):
+//   w4[rows_total] (float4: the weights of the group's 4 outputs for one source sample, 0 outside an output's
+//   window) | lo[nb] | rows[nb] | first[nb] (index of the group's first float4)
+// A kernel walks source samples lo .. lo+rows once per group and feeds 4 accumulators, so each accumulator still
+// receives its taps in ascending order (adding p * 0 is exact).
 struct AxisTab {
   uint32_t n_in, n_out, stride, off;
+  uint32_t boff, nb, brows_total, bwords;
 };
 
 // Geometry of the block grid over a pitched image.
@@ -65,7 +71,7 @@ size_t plan_scan_state_bytes(uint32_t nblocks);
 // direction 0: image tiles -> payload (shrink); 1: payload -> image tiles (expand)
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
-                            uint32_t max_src_px, uint32_t max_tmp_px, uint32_t max_tab_words, uint8_t* scratch,
+                            uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words, uint8_t* scratch,
                             size_t scratch_per_cta, int grid_hint, cudaStream_t s, int sm_count, uint64_t* launches);
 size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
 int resample_grid(int sm_count, uint32_t nblocks);

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "pxz_host.h"
@@ -110,6 +111,40 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
       memcpy(&(*pool)[wbase + (size_t)o * stride + i], &w, sizeof(float));
     }
   }
+  // blocked form: groups of 4 consecutive outputs share one walk over the source samples
+  while (pool->size() % 4) pool->push_back(0u);
+  const uint32_t nb = (n_out + 3) / 4;
+  std::vector<uint32_t> lo(nb), rows(nb), first(nb);
+  uint32_t total_rows = 0;
+  for (uint32_t b = 0; b < nb; ++b) {
+    uint32_t l = lefts[4 * b], h = 0;
+    for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
+      l = std::min(l, lefts[4 * b + j]);
+      h = std::max(h, lefts[4 * b + j] + counts[4 * b + j]);
+    }
+    lo[b] = l;
+    rows[b] = h - l;
+    first[b] = total_rows;
+    total_rows += rows[b];
+  }
+  tab->boff = (uint32_t)pool->size();
+  tab->nb = nb;
+  tab->brows_total = total_rows;
+  const size_t w4base = pool->size();
+  pool->resize(w4base + (size_t)total_rows * 4, 0u);  // +0.0f everywhere
+  for (uint32_t b = 0; b < nb; ++b) {
+    for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
+      const uint32_t o = 4 * b + j;
+      for (uint32_t i = 0; i < counts[o]; ++i) {
+        const uint32_t r = lefts[o] + i - lo[b];
+        (*pool)[w4base + ((size_t)first[b] + r) * 4 + j] = (*pool)[wbase + (size_t)o * stride + i];
+      }
+    }
+  }
+  pool->insert(pool->end(), lo.begin(), lo.end());
+  pool->insert(pool->end(), rows.begin(), rows.end());
+  pool->insert(pool->end(), first.begin(), first.end());
+  tab->bwords = (uint32_t)(pool->size() - w4base);
   return true;
 }
 
