@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpixlzr_b200.so")
+LIB_PATH = os.environ.get("PXZ_LIB", os.path.join(HERE, "libpixlzr_b200.so"))
 
 OK, E_ARG, E_CUDA, E_OOM, E_NCCL, E_UNSUPPORTED, E_FORMAT = 0, -1, -2, -3, -4, -5, -6
 STATUS_NAMES = {0: "PXZ_OK", -1: "PXZ_E_ARG", -2: "PXZ_E_CUDA", -3: "PXZ_E_OOM", -4: "PXZ_E_NCCL",

@@ -66,6 +66,7 @@ struct pxz_ctx {
   float* d_vx = nullptr;
   float* d_vy = nullptr;
   uint8_t* d_opaque = nullptr;
+  uint32_t* d_list = nullptr;  // [values_cap + 1]: banded tile indices, last word = count
   size_t values_cap = 0;
   float* d_minmax = nullptr;
   void* d_scan = nullptr;
@@ -183,13 +184,16 @@ pxz_status ensure_scratch(pxz_ctx* ctx, uint32_t nblocks) {
     dev_free(ctx, ctx->d_vx);
     dev_free(ctx, ctx->d_vy);
     dev_free(ctx, ctx->d_opaque);
+    dev_free(ctx, ctx->d_list);
     ctx->d_vx = ctx->d_vy = nullptr;
     ctx->d_opaque = nullptr;
+    ctx->d_list = nullptr;
     ctx->values_cap = 0;
     pxz_status st;
     if ((st = dev_alloc(ctx, (void**)&ctx->d_vx, (size_t)nblocks * 4)) != PXZ_OK) return st;
     if ((st = dev_alloc(ctx, (void**)&ctx->d_vy, (size_t)nblocks * 4)) != PXZ_OK) return st;
     if ((st = dev_alloc(ctx, (void**)&ctx->d_opaque, (size_t)nblocks)) != PXZ_OK) return st;
+    if ((st = dev_alloc(ctx, (void**)&ctx->d_list, ((size_t)nblocks + 1) * 4)) != PXZ_OK) return st;
     ctx->values_cap = nblocks;
   }
   const size_t need = plan_scan_state_bytes(nblocks);
@@ -380,6 +384,7 @@ void pxz_ctx_destroy(pxz_ctx* ctx) {
   dev_free(ctx, ctx->d_vx);
   dev_free(ctx, ctx->d_vy);
   dev_free(ctx, ctx->d_opaque);
+  dev_free(ctx, ctx->d_list);
   dev_free(ctx, ctx->d_scan);
   dev_free(ctx, ctx->d_scratch);
   cudaStreamSynchronize(ctx->stream);
@@ -541,7 +546,7 @@ static pxz_status run_analysis(pxz_ctx* ctx, const pxz_image* img, const Geom& g
     if (exact_all) {
       ProfScope prof(ctx, K_MAD_EXACT);
       PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                             ctx->stream, ctx->sm_count, &ctx->launches));
+                                             ctx->d_list, ctx->d_list + nblocks, ctx->stream, ctx->sm_count, &ctx->launches));
     } else {
       {
         ProfScope prof(ctx, K_MAD_FAST);
@@ -551,7 +556,8 @@ static pxz_status run_analysis(pxz_ctx* ctx, const pxz_image* img, const Geom& g
         // recompute, in reference order, the tiles whose level could differ from the CPU result
         ProfScope prof(ctx, K_MAD_EXACT);
         PXZ_CUDA(ctx, launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, ctx->d_vx, ctx->d_opaque, vm_for_band, &ctx->thr,
-                                               &ctx->band, ctx->d_minmax, ctx->stream, ctx->sm_count, &ctx->launches));
+                                               &ctx->band, ctx->d_minmax, ctx->d_list, ctx->d_list + nblocks, ctx->stream,
+                                               ctx->sm_count, &ctx->launches));
       }
     }
   } else if (metric == PXZ_METRIC_SOBEL_DIR) {

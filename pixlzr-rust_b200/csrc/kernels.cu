@@ -17,6 +17,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "pxz_internal.h"
 
 namespace pxz {
@@ -126,9 +128,30 @@ __device__ __forceinline__ OklabFast lms_fast(uint32_t px, const float* lut_lane
   return o;
 }
 
+// cube-rooted LMS of one packed RGBA pixel.  lut_lane_addr = shared-space byte address of s_lut[lane];
+// entry v lives at +v*128 bytes, so the bank is always the lane: no conflicts for arbitrary pixel data.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float r;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ OklabFast lms_fast_addr(uint32_t px, uint32_t lut_lane_addr) {
+  const float r = lds_f32(lut_lane_addr + (__byte_perm(px, 0, 0x4440) << 7));
+  const float g = lds_f32(lut_lane_addr + (__byte_perm(px, 0, 0x4441) << 7));
+  const float b = lds_f32(lut_lane_addr + (__byte_perm(px, 0, 0x4442) << 7));
+  OklabFast o;
+  o.l = cbrt_fast(fmaf(M1_02, b, fmaf(M1_01, g, M1_00 * r)));
+  o.m = cbrt_fast(fmaf(M1_12, b, fmaf(M1_11, g, M1_10 * r)));
+  o.s = cbrt_fast(fmaf(M1_22, b, fmaf(M1_21, g, M1_20 * r)));
+  return o;
+}
+
+#ifndef PXZ_MAD_MINBLOCKS
+#define PXZ_MAD_MINBLOCKS 3
+#endif
 template <int G, int QPT>
-__global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
-                                                               float* __restrict__ vx, uint8_t* __restrict__ opaque) {
+__global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                                  float* __restrict__ vx, uint8_t* __restrict__ opaque) {
   constexpr int TPC = kThreads / G;  // tiles per CTA iteration
   constexpr int WPG = G / 32;        // warps per group
   extern __shared__ float s_lut[];   // [256][32]
@@ -139,66 +162,63 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __
   const int grp = tid / G, gt = tid % G, gwarp0 = grp * WPG;
   for (int i = tid; i < 256 * 32; i += kThreads) s_lut[i] = c_srgb_lut[i >> 5];
   __syncthreads();
-  const float* lut_lane = s_lut + lane;
+  const uint32_t lut_lane_addr = (uint32_t)__cvta_generic_to_shared(s_lut + lane);
 
   const uint32_t ntiles = g.cols * g.rows;
   const uint32_t qpr = g.bw >> 2;  // quads (4 px = 16 B) per full tile row
-  uint32_t it = 0;
+  // this thread's quads: the (row, column) mapping does not depend on the tile
+  uint32_t qrc[QPT];   // row << 16 | first column
+  uint32_t qoff[QPT];  // byte offset inside the tile (tile rows * pitch < 2^32, checked by the launcher)
+  bool all_in = true;  // every quad of this thread lies inside a FULL tile
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const uint32_t q = gt + j * G;
+    const uint32_t row = q / qpr, col = (q - row * qpr) * 4;
+    qrc[j] = (row << 16) | col;
+    qoff[j] = (uint32_t)((size_t)row * pitch + (size_t)col * 4);
+    all_in = all_in && (row < g.bh);
+  }
+#define QROW(j) (qrc[j] >> 16)
+#define QCOL(j) (qrc[j] & 0xFFFFu)
+  const bool cta_all_in = __syncthreads_and(all_in) != 0;
 
-  uint4 cur[QPT];
-  // ---- load helper (as a lambda to keep cur/next symmetric) ----
   auto load_tile = [&](uint32_t tile, uint4(&v)[QPT]) {
     if (tile < ntiles) {
-      Tile t = tile_of(g, tile);
+      const Tile t = tile_of(g, tile);
       const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
 #pragma unroll
-      for (int j = 0; j < QPT; ++j) {
-        uint32_t q = gt + j * G;
-        uint32_t row = q / qpr, c4 = q - row * qpr;
-        if (row < t.th && c4 * 4 < t.tw) {
-          v[j] = ldg_nc_v4(base + (size_t)row * pitch + (size_t)c4 * 16);
-        } else {
-          v[j] = make_uint4(0, 0, 0, 0);
-        }
-      }
+      for (int j = 0; j < QPT; ++j)
+        v[j] = (QROW(j) < t.th && QCOL(j) < t.tw) ? ldg_nc_v4(base + qoff[j]) : make_uint4(0, 0, 0, 0);
     }
   };
 
-  uint32_t base_tile = blockIdx.x * TPC;
-  load_tile(base_tile + grp, cur);
-  for (; base_tile < ntiles; base_tile += gridDim.x * TPC, ++it) {
-    const uint32_t tile = base_tile + grp;
-    const bool valid = tile < ntiles;
-    Tile t = valid ? tile_of(g, tile) : Tile{0, 0, 0, 0};
-    // prefetch the next tile of this group while this one is being chewed on
-    uint4 nxt[QPT];
-#pragma unroll
-    for (int j = 0; j < QPT; ++j) nxt[j] = make_uint4(0, 0, 0, 0);
-    load_tile(tile + gridDim.x * TPC, nxt);
-
+  // one tile; MASK = false when every pixel of every thread is inside the tile (interior tiles)
+  auto process = [&](auto mask_tag, const Tile& t, bool valid, uint4(&cur)[QPT], uint4(&nxt)[QPT], uint32_t next_tile,
+                     uint32_t tile, int buf) {
+    constexpr bool MASK = decltype(mask_tag)::value;
     OklabFast c[QPT * 4];
-    float al[QPT * 4];
-    float sl = 0.f, sm = 0.f, ss = 0.f, sa = 0.f;
+    float sl = 0.f, sm = 0.f, ss = 0.f;
+    uint32_t asum = 0;  // integer sum of the alpha bytes (exact)
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
-      uint32_t q = gt + j * G;
-      uint32_t row = q / qpr, c4 = q - row * qpr;
-      const bool inq = valid && row < t.th && c4 * 4 < t.tw;
+      const bool inq = !MASK || (valid && QROW(j) < t.th && QCOL(j) < t.tw);
       const uint32_t w4[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        OklabFast o = lms_fast(w4[k], lut_lane);
-        float a = byte_to_float<3>(w4[k]) * kInv255;
-        const bool in = inq && (c4 * 4 + k) < t.tw;
-        if (!in) { o.l = 0.f; o.m = 0.f; o.s = 0.f; a = 0.f; }
+        OklabFast o = lms_fast_addr(w4[k], lut_lane_addr);
+        if (MASK && !inq) { o.l = 0.f; o.m = 0.f; o.s = 0.f; }
         c[j * 4 + k] = o;
-        al[j * 4 + k] = a;
-        sl += o.l; sm += o.m; ss += o.s; sa += a;
+        sl += o.l; sm += o.m; ss += o.s;
+        asum = __dp4a(w4[k], 0x01000000u, asum);  // out-of-tile quads were loaded as zeros
       }
     }
-    // ---- group reduction 1: sums of l', m', s', alpha ----
+    // the source quads are dead now: fetch the next tile while pass 2 and the reductions run
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) nxt[j] = make_uint4(0, 0, 0, 0);
+    load_tile(next_tile, nxt);
+    // ---- group reduction 1 ----
+    float sa = (float)asum;
     sl = warp_sum(sl); sm = warp_sum(sm); ss = warp_sum(ss); sa = warp_sum(sa);
-    const int buf = it & 1;
     if (WPG > 1) {
       if (lane == 0) { s_r1[buf][warp][0] = sl; s_r1[buf][warp][1] = sm; s_r1[buf][warp][2] = ss; s_r1[buf][warp][3] = sa; }
       __syncthreads();
@@ -211,30 +231,43 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __
     }
     const float count = (float)(t.tw * t.th);
     const float inv = valid ? 1.0f / count : 0.f;
-    // alpha 255 is exactly 1.0f and tiles here have <= 4096 px, so the tree sum of an opaque tile is the exact
-    // integer `count`, while a single non-opaque pixel lowers it by >= 1/255 (far above one ulp)
-    const bool is_opaque = (sa == count);
-    sl *= inv; sm *= inv; ss *= inv; sa *= inv;
+    // byte sums of <= 4096 pixels are exact in f32: the tile is opaque iff the sum is 255 * count
+    const bool is_opaque = (sa == 255.0f * count);
+    sl *= inv; sm *= inv; ss *= inv;
+    const float mean_alpha = sa * inv * kInv255;
     // the Lab transform is linear: mean(Lab) = M2 * mean(l', m', s')
     const float nL = -(M2_00 * sl + M2_01 * sm + M2_02 * ss);
     const float nA = -(M2_10 * sl + M2_11 * sm + M2_12 * ss);
     const float nB = -(M2_20 * sl + M2_21 * sm + M2_22 * ss);
     float d = 0.f;
+    float dp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < QPT; ++j) {
-      uint32_t q = gt + j * G;
-      uint32_t row = q / qpr, c4 = q - row * qpr;
-      const bool inq = valid && row < t.th && c4 * 4 < t.tw;
+    for (int i = 0; i < QPT * 4; ++i) {
+      const OklabFast o = c[i];
+      const float dL = fmaf(M2_02, o.s, fmaf(M2_01, o.m, fmaf(M2_00, o.l, nL)));
+      const float dA = fmaf(M2_12, o.s, fmaf(M2_11, o.m, fmaf(M2_10, o.l, nA)));
+      const float dB = fmaf(M2_22, o.s, fmaf(M2_21, o.m, fmaf(M2_20, o.l, nB)));
+      if (MASK) {
+        const int j = i >> 2, k = i & 3;
+        const bool in = valid && QROW(j) < t.th && (QCOL(j) + k) < t.tw;
+        d += in ? (fabsf(dA) + fabsf(dB)) + fabsf(dL) : 0.f;
+      } else {
+        dp[i & 3] += (fabsf(dA) + fabsf(dB)) + fabsf(dL);
+      }
+    }
+    if (!MASK) d = (dp[0] + dp[1]) + (dp[2] + dp[3]);
+    if (!is_opaque) {
+      // rare: per-pixel alpha deviations; the quads are re-read (L1/L2 hot) instead of being kept in registers
+      if (valid) {
+        const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const OklabFast o = c[j * 4 + k];
-        const float dL = fmaf(M2_02, o.s, fmaf(M2_01, o.m, fmaf(M2_00, o.l, nL)));
-        const float dA = fmaf(M2_12, o.s, fmaf(M2_11, o.m, fmaf(M2_10, o.l, nA)));
-        const float dB = fmaf(M2_22, o.s, fmaf(M2_21, o.m, fmaf(M2_20, o.l, nB)));
-        const float dAl = al[j * 4 + k] - sa;
-        const bool in = inq && (c4 * 4 + k) < t.tw;
-        const float e = (fabsf(dA) + fabsf(dB)) + (fabsf(dL) + fabsf(dAl));
-        d += in ? e : 0.f;
+        for (int j = 0; j < QPT; ++j) {
+          if (QROW(j) < t.th && QCOL(j) < t.tw) {
+            const uint4 q = ldg_nc_v4(base + qoff[j]);
+            d += fabsf(byte_to_float<3>(q.x) * kInv255 - mean_alpha) + fabsf(byte_to_float<3>(q.y) * kInv255 - mean_alpha);
+            d += fabsf(byte_to_float<3>(q.z) * kInv255 - mean_alpha) + fabsf(byte_to_float<3>(q.w) * kInv255 - mean_alpha);
+          }
+        }
       }
     }
     d = warp_sum(d);
@@ -249,10 +282,30 @@ __global__ void __launch_bounds__(kThreads) k_analyze_mad_rgba(const uint8_t* __
       vx[tile] = d * inv;
       opaque[tile] = (uint8_t)(is_opaque ? 1 : 0);
     }
+  };
+
+  uint4 cur[QPT], nxt[QPT];
+  uint32_t base_tile = blockIdx.x * TPC;
+  uint32_t it = 0;
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) cur[j] = make_uint4(0, 0, 0, 0);
+  load_tile(base_tile + grp, cur);
+  for (; base_tile < ntiles; base_tile += gridDim.x * TPC, ++it) {
+    const uint32_t tile = base_tile + grp;
+    const bool valid = tile < ntiles;
+    const Tile t = valid ? tile_of(g, tile) : Tile{0, 0, 0, 0};
+    const uint32_t next_tile = tile + gridDim.x * TPC;
+    // interior tiles of a fully populated CTA skip every bounds predicate (CTA-uniform choice when TPC == 1)
+    const bool full = cta_all_in && valid && t.tw == g.bw && t.th == g.bh;
+    const bool full_all = (TPC == 1) ? full : (__syncthreads_and(full) != 0);
+    if (full_all) process(std::false_type{}, t, valid, cur, nxt, next_tile, tile, it & 1);
+    else process(std::true_type{}, t, valid, cur, nxt, next_tile, tile, it & 1);
 #pragma unroll
     for (int j = 0; j < QPT; ++j) cur[j] = nxt[j];
   }
 }
+#undef QROW
+#undef QCOL
 
 // Any channel count / alignment / tile size: one CTA per tile (grid-stride), byte loads, same fast
 // arithmetic.  The first 16 pixels of every thread stay in registers; a tile with more than
@@ -443,7 +496,7 @@ __device__ __forceinline__ void oklab_ref(const float* lut, uint32_t r8, uint32_
 }
 
 constexpr int kExactChunk = 4096;             // pixels staged per pass
-constexpr int kExactStride = kExactChunk + 1; // +1: the 4 channel lanes hit different banks
+constexpr int kExactStride = kExactChunk + 4; // +4 floats: 16-byte aligned rows, and the 4 channel lanes hit different banks
 
 template <int C>
 __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, const Tile& t, float* s_val /*[4][stride]*/,
@@ -480,16 +533,27 @@ __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, c
         __syncthreads();
       }
       if (warp == 0 && lane < C) {
-        const float* p = s_val + lane * kExactStride;
+        // the sequential f32 sum of the reference; loads run one batch of 16 ahead of the dependent adds
+        const float4* p4 = reinterpret_cast<const float4*>(s_val + lane * kExactStride);
         float s = run;
-        uint32_t i = 0;
-        for (; i + 8 <= n; i += 8) {
-          const float a0 = p[i], a1 = p[i + 1], a2 = p[i + 2], a3 = p[i + 3];
-          const float a4 = p[i + 4], a5 = p[i + 5], a6 = p[i + 6], a7 = p[i + 7];
-          s = __fadd_rn(s, a0); s = __fadd_rn(s, a1); s = __fadd_rn(s, a2); s = __fadd_rn(s, a3);
-          s = __fadd_rn(s, a4); s = __fadd_rn(s, a5); s = __fadd_rn(s, a6); s = __fadd_rn(s, a7);
+        const uint32_t nb = n >> 4;
+#define PXZ_ADD16(q0, q1, q2, q3)                                                                       \
+  s = __fadd_rn(s, q0.x); s = __fadd_rn(s, q0.y); s = __fadd_rn(s, q0.z); s = __fadd_rn(s, q0.w);        \
+  s = __fadd_rn(s, q1.x); s = __fadd_rn(s, q1.y); s = __fadd_rn(s, q1.z); s = __fadd_rn(s, q1.w);        \
+  s = __fadd_rn(s, q2.x); s = __fadd_rn(s, q2.y); s = __fadd_rn(s, q2.z); s = __fadd_rn(s, q2.w);        \
+  s = __fadd_rn(s, q3.x); s = __fadd_rn(s, q3.y); s = __fadd_rn(s, q3.z); s = __fadd_rn(s, q3.w);
+        if (nb) {
+          float4 a0 = p4[0], a1 = p4[1], a2 = p4[2], a3 = p4[3];
+          for (uint32_t bi = 1; bi < nb; ++bi) {
+            const float4 c0 = p4[4 * bi], c1 = p4[4 * bi + 1], c2 = p4[4 * bi + 2], c3 = p4[4 * bi + 3];
+            PXZ_ADD16(a0, a1, a2, a3)
+            a0 = c0; a1 = c1; a2 = c2; a3 = c3;
+          }
+          PXZ_ADD16(a0, a1, a2, a3)
         }
-        for (; i < n; ++i) s = __fadd_rn(s, p[i]);
+#undef PXZ_ADD16
+        const float* p = s_val + lane * kExactStride;
+        for (uint32_t i = nb << 4; i < n; ++i) s = __fadd_rn(s, p[i]);
         run = s;
       }
       __syncthreads();
@@ -542,23 +606,33 @@ __device__ __forceinline__ bool in_guard_band(float raw, bool opaque, int C, con
   return false;
 }
 
+// compact list of the tiles inside the guard band (order is irrelevant)
+__global__ void __launch_bounds__(kThreads) k_band_list(const float* __restrict__ vx_fast, const uint8_t* __restrict__ opaque,
+                                                        Geom g, int C, ValueMap vm, LevelThresholds thr, GuardBand band,
+                                                        const float* minmax, uint32_t* __restrict__ list,
+                                                        uint32_t* __restrict__ count) {
+  const uint32_t ntiles = g.cols * g.rows;
+  const uint32_t tile = blockIdx.x * kThreads + threadIdx.x;
+  if (tile >= ntiles) return;
+  const Tile t = tile_of(g, tile);
+  if (in_guard_band(vx_fast[tile], opaque[tile] != 0, C, t, vm, thr, band, minmax)) list[atomicAdd(count, 1u)] = tile;
+}
+
+// list == nullptr: every tile (PXZ_FLAG_EXACT_VALUES); else the *count tiles of the list, one per CTA round-robin
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_mad_exact(const uint8_t* __restrict__ img, size_t pitch, Geom g, float* vx,
-                                                        const float* vx_fast, const uint8_t* __restrict__ opaque,
-                                                        ValueMap vm, LevelThresholds thr, GuardBand band,
-                                                        const float* minmax) {
+                                                        const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
   extern __shared__ float s_dyn[];
   float* s_val = s_dyn;  // 4 * kExactStride
   __shared__ float s_lut256[256];
   __shared__ float s_avg[4];
+  const uint32_t n = list ? *count : g.cols * g.rows;
+  if (blockIdx.x >= n) return;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut256[i] = c_srgb_lut[i];
   __syncthreads();
-  const uint32_t ntiles = g.cols * g.rows;
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t tile = list ? list[i] : i;
     const Tile t = tile_of(g, tile);
-    if (vx_fast != nullptr) {
-      if (!in_guard_band(vx_fast[tile], opaque[tile] != 0, C, t, vm, thr, band, minmax)) continue;  // CTA-uniform
-    }
     const float v = mad_exact_tile<C>(img, pitch, t, s_val, s_lut256, s_avg);
     if (threadIdx.x == 0) vx[tile] = v;
     __syncthreads();
@@ -1350,25 +1424,31 @@ cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom
 
 cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
                                      const uint8_t* opaque, const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
-                                     const float* minmax, cudaStream_t s, int sm_count, uint64_t* launches) {
+                                     const float* minmax, uint32_t* list, uint32_t* count, cudaStream_t s, int sm_count,
+                                     uint64_t* launches) {
   const uint32_t ntiles = g.cols * g.rows;
   const size_t smem = (size_t)4 * kExactStride * sizeof(float);
-  ValueMap v{1.0f, 1, 0};
-  LevelThresholds t{};
-  GuardBand b{0.f, 0.f};
-  if (vm) v = *vm;
-  if (thr) t = *thr;
-  if (band) b = *band;
   cudaError_t e;
+  const bool banded = vx_fast != nullptr;
+  if (banded) {
+    e = cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    k_band_list<<<(ntiles + kThreads - 1) / kThreads, kThreads, 0, s>>>(vx_fast, opaque, g, (int)g.C, *vm, *thr, *band, minmax,
+                                                                       list, count);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   ++*launches;
+  const int grid = clamp_grid(ntiles, (long long)sm_count * 3);
   if (g.C == 4) {
     e = set_smem(k_mad_exact<4>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, opaque, v, t, b, minmax);
+    k_mad_exact<4><<<grid, kThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
   } else {
     e = set_smem(k_mad_exact<3>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, vx_fast, opaque, v, t, b, minmax);
+    k_mad_exact<3><<<grid, kThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
   }
   return cudaGetLastError();
 }

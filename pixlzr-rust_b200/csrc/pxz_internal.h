@@ -59,7 +59,8 @@ cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom
                                     cudaStream_t s, int sm_count, uint64_t* launches);
 cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
                                      const uint8_t* opaque, const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
-                                     const float* minmax, cudaStream_t s, int sm_count, uint64_t* launches);
+                                     const float* minmax, uint32_t* list, uint32_t* count, cudaStream_t s, int sm_count,
+                                     uint64_t* launches);
 cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g, float* vx, float* vy, cudaStream_t s,
                                  int sm_count, uint64_t* launches);
 cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* minmax4, cudaStream_t s,
