@@ -266,9 +266,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 self.descs = self.pin[0].numpy().view(N.DESC_DTYPE)
                 self.pixels, self.out = self.pin[1].numpy(), self.pin[2].numpy()
                 self.h2d = self.d2h = 0
+                self.busy_s = 0.0
 
             def encode_decode(self, a):
                 c = self.ctx
+                t_in = time.perf_counter()
                 im = c.image_upload(a)                                                  # H2D image
                 pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
                 nbytes = pl.download_into(self.descs, self.pixels)                      # D2H descs + payload (encode result)
@@ -279,6 +281,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 pl2.free()
                 self.h2d += img_bytes + nbytes + nblocks * 16
                 self.d2h += nbytes + nblocks * 16 + img_bytes
+                self.busy_s += time.perf_counter() - t_in
 
         workers = [Worker() for _ in range(n_workers)]
 
@@ -294,10 +297,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             for t in th:
                 t.join()
 
-        e2e_steps = max(1, min(args.steps, 5))
-        run_steps(1)
+        e2e_steps = max(2, min(args.steps, 8))
+        run_steps(2)
         for wk in workers:
             wk.h2d = wk.d2h = 0
+            wk.busy_s = 0.0
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -305,6 +309,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         e2e_s = time.perf_counter() - t0
         h2d = sum(wk.h2d for wk in workers)
         d2h = sum(wk.d2h for wk in workers)
+        if os.environ.get("PXZ_BENCH_DEBUG"):
+            sys.stderr.write(f"[rank {rank}] e2e {e2e_s * 1e3:.1f} ms for {e2e_steps * batch} images; per-worker busy "
+                             f"{[round(wk.busy_s * 1e3, 1) for wk in workers]} ms\n")
 
     # ---- reduce over ranks: max time -------------------------------------------------------------------
     times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
