@@ -83,6 +83,10 @@ const char* pxz_last_error(const pxz_ctx* ctx);
 pxz_status pxz_synchronize(pxz_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t pxz_launch_count(const pxz_ctx* ctx);
+/* Resample arithmetic of this context.  0 (default): the reference's order — separate multiply and add, no
+ * contraction — resampled pixels are bit-identical to the CPU result.  1: fused multiply-add on the RGBA fast paths;
+ * faster, dims / offsets / values unchanged, pixels within +-1 LSB of the reference (the bar BASELINE.json states). */
+pxz_status pxz_ctx_set_fast_resample(pxz_ctx* ctx, int on);
 /* Per-kernel device timing (CUDA events recorded on the context's stream around every kernel
  * launch while enabled).  pxz_profile_read synchronises the stream, returns the accumulated
  * duration and launch count of kernel `kernel_id` since profiling was enabled.  Kernel ids are

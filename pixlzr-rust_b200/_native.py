@@ -35,6 +35,7 @@ SYMBOLS = {
     "pxz_last_error": (C.c_char_p, [_vp]),
     "pxz_synchronize": (_i, [_vp]),
     "pxz_launch_count": (_u64, [_vp]),
+    "pxz_ctx_set_fast_resample": (_i, [_vp, _i]),
     "pxz_profile_enable": (_i, [_vp, _i]),
     "pxz_profile_kernel_name": (C.c_char_p, [_i]),
     "pxz_profile_read": (_i, [_vp, _i, _P(C.c_double), _P(_u64)]),
@@ -131,6 +132,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().pxz_launch_count(self._h))
+
+    def set_fast_resample(self, on: bool = True):
+        """Fused multiply-add in the RGBA resample kernels: pixels within +-1 LSB instead of bit-exact."""
+        self.check(lib().pxz_ctx_set_fast_resample(self._h, int(on)))
 
     def profile_enable(self, on: bool = True):
         self.check(lib().pxz_profile_enable(self._h, int(on)))

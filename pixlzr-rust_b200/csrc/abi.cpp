@@ -76,6 +76,7 @@ struct pxz_ctx {
   uint64_t* h_total = nullptr;  // pinned
   std::map<TabKey, TabSet> tabs;
   void* comm = nullptr;
+  bool fast_resample = false;
   // per-kernel timing
   bool profiling = false;
   std::vector<ProfRec> prof_open;
@@ -284,7 +285,7 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   }
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
-                                max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->stream, ctx->sm_count,
+                                max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, ctx->stream, ctx->sm_count,
                                 &ctx->launches));
   return PXZ_OK;
 }
@@ -405,6 +406,12 @@ pxz_status pxz_synchronize(pxz_ctx* ctx) {
 }
 
 uint64_t pxz_launch_count(const pxz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+pxz_status pxz_ctx_set_fast_resample(pxz_ctx* ctx, int on) {
+  if (!ctx) return PXZ_E_ARG;
+  ctx->fast_resample = on != 0;
+  return PXZ_OK;
+}
 
 static pxz_status prof_drain(pxz_ctx* ctx) {
   if (ctx->prof_open.empty()) return PXZ_OK;

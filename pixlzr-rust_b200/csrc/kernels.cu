@@ -709,6 +709,83 @@ __global__ void __launch_bounds__(kThreads) k_analyze_sobel(const uint8_t* __res
   }
 }
 
+// Tiles up to 64x64: the tile is staged once in shared memory as one u32 per pixel; thread (column, row band)
+// walks its band keeping the separable partial sums of the two previous rows in registers:
+//   h(y) = v(x,y) + 2 v(x+1,y) + v(x+2,y)   ->  hz = h(y+2) - h(y)
+//   g(y) = v(x+2,y) - v(x,y)                ->  vr = g(y) + 2 g(y+1) + g(y+2)
+// |.| + accumulate is one VABSDIFF each.  Integer arithmetic throughout: bit-exact by construction.
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_analyze_sobel_tile64(const uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                                   float* __restrict__ vx, float* __restrict__ vy) {
+  __shared__ uint32_t s_px[64 * 64];
+  __shared__ unsigned long long s_red[kThreads / 32][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ntiles = g.cols * g.rows;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const Tile t = tile_of(g, tile);
+    const uint8_t* base = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
+    const uint32_t npx = t.tw * t.th;
+    for (uint32_t i = tid; i < npx; i += kThreads) {
+      const uint32_t y = i / t.tw, x = i - y * t.tw;
+      const uint8_t* p = base + (size_t)y * pitch + (size_t)x * C;
+      s_px[y * 64 + x] = (C == 4) ? *reinterpret_cast<const uint32_t*>(p)
+                                  : ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16));
+    }
+    __syncthreads();
+    uint32_t ahz = 0, avr = 0;
+    if (t.tw >= 3 && t.th >= 3) {
+      const uint32_t ww = t.tw - 2, wh = t.th - 2;
+      const uint32_t x = tid & 63u, band = tid >> 6;  // 4 bands of window rows
+      const uint32_t rows_per = (wh + 3) >> 2;
+      const uint32_t y_lo = band * rows_per, y_hi = min(wh, y_lo + rows_per);
+      if (x < ww && y_lo < y_hi) {
+        int h0[3], h1[3], g0[3], g1[3];
+        auto row_terms = [&](uint32_t y, int(&h)[3], int(&gd)[3]) {
+          const uint32_t* r = s_px + y * 64 + x;
+          const uint32_t p0 = r[0], p1 = r[1], p2 = r[2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int a = (int)((p0 >> (8 * c)) & 0xFFu), b = (int)((p1 >> (8 * c)) & 0xFFu), d = (int)((p2 >> (8 * c)) & 0xFFu);
+            h[c] = a + 2 * b + d;
+            gd[c] = d - a;
+          }
+        };
+        row_terms(y_lo, h0, g0);
+        row_terms(y_lo + 1, h1, g1);
+#pragma unroll 2
+        for (uint32_t y = y_lo; y < y_hi; ++y) {
+          int h2[3], g2[3];
+          row_terms(y + 2, h2, g2);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            ahz = __sad(h2[c], h0[c], ahz);                  // |hz|, operations.rs:240-241,247
+            avr = __sad(g0[c] + 2 * g1[c] + g2[c], 0, avr);  // |vr|, operations.rs:244-245,248
+            h0[c] = h1[c]; h1[c] = h2[c];
+            g0[c] = g1[c]; g1[c] = g2[c];
+          }
+        }
+      }
+    }
+    unsigned long long shz = warp_sum_u64(ahz), svr = warp_sum_u64(avr);  // per thread <= 16 rows * 3 * 1020 each
+    if (lane == 0) { s_red[warp][0] = shz; s_red[warp][1] = svr; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long a = 0, b = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) { a += s_red[w][0]; b += s_red[w][1]; }
+      const unsigned long long f = (unsigned long long)(t.tw - 2) * (unsigned long long)(t.th - 2) * 4096ull;  // :158,:253-254
+      if (t.tw < 3 || t.th < 3 || f == 0) {
+        vx[tile] = __uint_as_float(0xFFC00000u);  // 0/0 in the reference (x86: negative quiet NaN)
+        vy[tile] = __uint_as_float(0xFFC00000u);
+      } else {
+        vx[tile] = __double2float_rn(__ddiv_rn((double)a, (double)f));
+        vy[tile] = __double2float_rn(__ddiv_rn((double)b, (double)f));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // min / -max of the raw values (normalise extension).  out = {min_x, -max_x, min_y, -max_y}, so a
 // single ncclMin all-reduce of 4 floats finishes the job across ranks.  NaNs are ignored.
@@ -741,7 +818,7 @@ __global__ void __launch_bounds__(1024) k_minmax(const float* __restrict__ vx, c
 // plan: reduce_image_section minus the resize (operations.rs:140-156) + exclusive scan of the
 // payload sizes (single pass, decoupled look-back), producing the descriptor table.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPlanItems = 4;
+constexpr int kPlanItems = 1;
 constexpr int kPlanTile = kThreads * kPlanItems;
 
 struct ScanState {
@@ -1045,16 +1122,25 @@ __device__ __forceinline__ uint32_t to_u8_fast(float t) {
   return q;
 }
 
-template <bool ALPHA>
+// MODE bit 0: the alpha channel is computed; bit 1: fused multiply-add (PXZ "fast resample": not bit-exact,
+// pixels stay within +-1 LSB of the reference order)
+template <int MODE>
 __device__ __forceinline__ void mac(float4& acc, const float4& p, float w) {
-  acc.x = __fadd_rn(acc.x, __fmul_rn(p.x, w));
-  acc.y = __fadd_rn(acc.y, __fmul_rn(p.y, w));
-  acc.z = __fadd_rn(acc.z, __fmul_rn(p.z, w));
-  if (ALPHA) acc.w = __fadd_rn(acc.w, __fmul_rn(p.w, w));
+  if (MODE & 2) {
+    acc.x = fmaf(p.x, w, acc.x);
+    acc.y = fmaf(p.y, w, acc.y);
+    acc.z = fmaf(p.z, w, acc.z);
+    if (MODE & 1) acc.w = fmaf(p.w, w, acc.w);
+  } else {
+    acc.x = __fadd_rn(acc.x, __fmul_rn(p.x, w));
+    acc.y = __fadd_rn(acc.y, __fmul_rn(p.y, w));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(p.z, w));
+    if (MODE & 1) acc.w = __fadd_rn(acc.w, __fmul_rn(p.w, w));
+  }
 }
-template <bool ALPHA>
+template <int MODE>
 __device__ __forceinline__ uint32_t pack_px(const float4& a) {
-  return to_u8_fast(a.x) | (to_u8_fast(a.y) << 8) | (to_u8_fast(a.z) << 16) | (ALPHA ? (to_u8_fast(a.w) << 24) : 0xFF000000u);
+  return to_u8_fast(a.x) | (to_u8_fast(a.y) << 8) | (to_u8_fast(a.z) << 16) | ((MODE & 1) ? (to_u8_fast(a.w) << 24) : 0xFF000000u);
 }
 
 // One staged axis table: either the blocked form (outputs in groups of 4) or the per-output form.
@@ -1068,7 +1154,7 @@ struct StagedTab {
 };
 
 // ---- vertical_sample: src [sh][64] -> tmp [dh][ts] ---------------------------------------------------------------
-template <bool ALPHA>
+template <int MODE>
 __device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
                                                  const AxisTab& ty, const uint32_t* taby) {
   const uint32_t x = threadIdx.x & 63u, grp = threadIdx.x >> 6;
@@ -1087,14 +1173,14 @@ __device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp,
     for (; r + 2 <= n; r += 2) {
       const float4 p0 = sp[0], p1 = sp[kSrcStride];
       const float4 w0 = wp[r], w1 = wp[r + 1];
-      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
-      mac<ALPHA>(a0, p1, w1.x); mac<ALPHA>(a1, p1, w1.y); mac<ALPHA>(a2, p1, w1.z); mac<ALPHA>(a3, p1, w1.w);
+      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
+      mac<MODE>(a0, p1, w1.x); mac<MODE>(a1, p1, w1.y); mac<MODE>(a2, p1, w1.z); mac<MODE>(a3, p1, w1.w);
       sp += 2 * kSrcStride;
     }
     if (r < n) {
       const float4 p0 = sp[0];
       const float4 w0 = wp[r];
-      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
+      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
     }
     const uint32_t oy = ob * 4;
     tmp[(oy + 0) * ts + (x ^ ((oy + 0) & 7u))] = a0;
@@ -1104,7 +1190,7 @@ __device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp,
   }
 }
 
-template <bool ALPHA>
+template <int MODE>
 __device__ __forceinline__ void vertical_plain(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
                                                const AxisTab& ty, const uint32_t* taby) {
   const uint32_t x = threadIdx.x & 63u, grp = threadIdx.x >> 6;
@@ -1122,11 +1208,11 @@ __device__ __forceinline__ void vertical_plain(const float4* src, float4* tmp, u
     for (; k + 4 <= n; k += 4) {
       const float4 p0 = sp[0], p1 = sp[kSrcStride], p2 = sp[2 * kSrcStride], p3 = sp[3 * kSrcStride];
       const float w0 = wr[k], w1 = wr[k + 1], w2 = wr[k + 2], w3 = wr[k + 3];
-      mac<ALPHA>(acc, p0, w0); mac<ALPHA>(acc, p1, w1); mac<ALPHA>(acc, p2, w2); mac<ALPHA>(acc, p3, w3);
+      mac<MODE>(acc, p0, w0); mac<MODE>(acc, p1, w1); mac<MODE>(acc, p2, w2); mac<MODE>(acc, p3, w3);
       sp += 4 * kSrcStride;
     }
     for (; k < n; ++k) {
-      mac<ALPHA>(acc, sp[0], wr[k]);
+      mac<MODE>(acc, sp[0], wr[k]);
       sp += kSrcStride;
     }
     tmp[oy * ts + (x ^ (oy & 7u))] = acc;
@@ -1134,7 +1220,7 @@ __device__ __forceinline__ void vertical_plain(const float4* src, float4* tmp, u
 }
 
 // ---- horizontal_sample: tmp [dh][ts] -> packed RGBA pixels, written through `put(oy, ox, n, px[4])` ------------------
-template <bool ALPHA, typename Put>
+template <int MODE, typename Put>
 __device__ __forceinline__ void horizontal_blocked(const float4* tmp, uint32_t ts, uint32_t dw, uint32_t dh, const AxisTab& tx,
                                                    const uint32_t* tabx, Put put) {
   const float4* w4 = reinterpret_cast<const float4*>(tabx);
@@ -1154,22 +1240,22 @@ __device__ __forceinline__ void horizontal_blocked(const float4* tmp, uint32_t t
     for (; c + 2 <= n; c += 2) {
       const float4 p0 = trow[(c0 + c) ^ s7], p1 = trow[(c0 + c + 1) ^ s7];
       const float4 w0 = wp[c], w1 = wp[c + 1];
-      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
-      mac<ALPHA>(a0, p1, w1.x); mac<ALPHA>(a1, p1, w1.y); mac<ALPHA>(a2, p1, w1.z); mac<ALPHA>(a3, p1, w1.w);
+      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
+      mac<MODE>(a0, p1, w1.x); mac<MODE>(a1, p1, w1.y); mac<MODE>(a2, p1, w1.z); mac<MODE>(a3, p1, w1.w);
     }
     if (c < n) {
       const float4 p0 = trow[(c0 + c) ^ s7];
       const float4 w0 = wp[c];
-      mac<ALPHA>(a0, p0, w0.x); mac<ALPHA>(a1, p0, w0.y); mac<ALPHA>(a2, p0, w0.z); mac<ALPHA>(a3, p0, w0.w);
+      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
     }
     const uint32_t ox = ob * 4;
     const uint32_t nvalid = min(4u, dw - ox);
-    uint32_t px[4] = {pack_px<ALPHA>(a0), pack_px<ALPHA>(a1), pack_px<ALPHA>(a2), pack_px<ALPHA>(a3)};
+    uint32_t px[4] = {pack_px<MODE>(a0), pack_px<MODE>(a1), pack_px<MODE>(a2), pack_px<MODE>(a3)};
     put(oy, ox, nvalid, px);
   }
 }
 
-template <bool ALPHA, typename Put>
+template <int MODE, typename Put>
 __device__ __forceinline__ void horizontal_plain(const float4* tmp, uint32_t ts, uint32_t dw, uint32_t dh, const AxisTab& tx,
                                                  const uint32_t* tabx, Put put) {
   const uint32_t* left = tabx;
@@ -1181,22 +1267,22 @@ __device__ __forceinline__ void horizontal_plain(const float4* tmp, uint32_t ts,
     const float* wr = w + ox * tx.stride;
     const float4* trow = tmp + oy * ts;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t k = 0; k < n; ++k) mac<ALPHA>(acc, trow[(c0 + k) ^ s7], wr[k]);
-    uint32_t px[4] = {pack_px<ALPHA>(acc), 0, 0, 0};
+    for (uint32_t k = 0; k < n; ++k) mac<MODE>(acc, trow[(c0 + k) ^ s7], wr[k]);
+    uint32_t px[4] = {pack_px<MODE>(acc), 0, 0, 0};
     put(oy, ox, 1u, px);
   }
 }
 
 // the two passes for one staged block; `put` writes up to 4 horizontally adjacent output pixels
-template <bool ALPHA, typename Put>
+template <int MODE, typename Put>
 __device__ __forceinline__ void resample_staged(const FastSmem& sm, uint32_t sw, uint32_t dw, uint32_t dh, const AxisTab& tx,
                                                 const AxisTab& ty, bool yblocked, bool xblocked, Put put) {
   const uint32_t ts = (sw + 7u) & ~7u;
-  if (yblocked) vertical_blocked<ALPHA>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
-  else vertical_plain<ALPHA>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
+  if (yblocked) vertical_blocked<MODE>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
+  else vertical_plain<MODE>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
   __syncthreads();
-  if (xblocked) horizontal_blocked<ALPHA>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
-  else horizontal_plain<ALPHA>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
+  if (xblocked) horizontal_blocked<MODE>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
+  else horizontal_plain<MODE>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
 }
 
 __device__ __forceinline__ void stage_axis(const AxisTab& t, bool blocked, const uint32_t* __restrict__ pool, uint32_t* dst) {
@@ -1205,6 +1291,7 @@ __device__ __forceinline__ void stage_axis(const AxisTab& t, bool blocked, const
 }
 
 // ---- encode side: 64x64-or-smaller tiles of the pitched image -> packed payload -----------------------------
+template <bool FUSED>
 __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
                                                              const pxz_block_desc* __restrict__ descs,
                                                              const uint32_t* __restrict__ tabidx, uint8_t* __restrict__ payload,
@@ -1279,8 +1366,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
         if (n > 2) o[2] = px[2];
         if (n > 3) o[3] = px[3];
       };
-      if (opaque) resample_staged<false>(sm, sw, dw, dh, tx, ty, yb, xb, put);
-      else resample_staged<true>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      if (opaque) resample_staged<(FUSED ? 2 : 0)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      else resample_staged<(FUSED ? 3 : 1)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
       __syncthreads();
     }
 #pragma unroll
@@ -1289,6 +1376,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
 }
 
 // ---- decode side: packed payload blocks -> 64x64-or-smaller tiles of the pitched image (expand + paste) ------
+template <bool FUSED>
 __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict__ img, size_t pitch, Geom g,
                                                              const pxz_block_desc* __restrict__ descs,
                                                              const uint32_t* __restrict__ tabidx,
@@ -1361,8 +1449,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
           if (n > 2) o[2] = px[2];
         }
       };
-      if (opaque) resample_staged<false>(sm, sw, dw, dh, tx, ty, yb, xb, put);
-      else resample_staged<true>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      if (opaque) resample_staged<(FUSED ? 2 : 0)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      else resample_staged<(FUSED ? 3 : 1)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
       __syncthreads();
     }
 #pragma unroll
@@ -1457,10 +1545,17 @@ cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g
                                  int sm_count, uint64_t* launches) {
   const uint32_t ntiles = g.cols * g.rows;
   ++*launches;
-  if (g.C == 4)
+  const bool small = g.bw <= 64 && g.bh <= 64 && (g.C == 3 || ((pitch & 3u) == 0 && (reinterpret_cast<uintptr_t>(img) & 3u) == 0));
+  if (small) {
+    if (g.C == 4)
+      k_analyze_sobel_tile64<4><<<clamp_grid(ntiles, sm_count * 8), kThreads, 0, s>>>(img, pitch, g, vx, vy);
+    else
+      k_analyze_sobel_tile64<3><<<clamp_grid(ntiles, sm_count * 8), kThreads, 0, s>>>(img, pitch, g, vx, vy);
+  } else if (g.C == 4) {
     k_analyze_sobel<4><<<clamp_grid(ntiles, sm_count * 8), kThreads, 0, s>>>(img, pitch, g, vx, vy);
-  else
+  } else {
     k_analyze_sobel<3><<<clamp_grid(ntiles, sm_count * 8), kThreads, 0, s>>>(img, pitch, g, vx, vy);
+  }
   return cudaGetLastError();
 }
 
@@ -1498,7 +1593,7 @@ int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words, uint8_t* scratch,
-                            size_t scratch_per_cta, int grid, cudaStream_t s, int sm_count, uint64_t* launches) {
+                            size_t scratch_per_cta, int grid, bool fused, cudaStream_t s, int sm_count, uint64_t* launches) {
   cudaError_t e;
   ++*launches;
   // RGBA fast paths: tiles <= 64x64 with 16-byte aligned rows
@@ -1508,14 +1603,22 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
   if (fast) {
     const size_t smem = (size_t)(kFastMaxPx + max_tmp_px) * sizeof(float4) + 2 * (size_t)kFastMaxTabWords * sizeof(uint32_t);
     const int fgrid = clamp_grid((long long)g.cols * g.rows, (long long)sm_count * 2);
-    if (direction == 0) {
-      e = set_smem(k_shrink_rgba, smem);
+    if (direction == 0 && !fused) {
+      e = set_smem(k_shrink_rgba<false>, smem);
       if (e != cudaSuccess) return e;
-      k_shrink_rgba<<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+      k_shrink_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+    } else if (direction == 0) {
+      e = set_smem(k_shrink_rgba<true>, smem);
+      if (e != cudaSuccess) return e;
+      k_shrink_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+    } else if (!fused) {
+      e = set_smem(k_expand_rgba<false>, smem);
+      if (e != cudaSuccess) return e;
+      k_expand_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
     } else {
-      e = set_smem(k_expand_rgba, smem);
+      e = set_smem(k_expand_rgba<true>, smem);
       if (e != cudaSuccess) return e;
-      k_expand_rgba<<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+      k_expand_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
     }
     return cudaGetLastError();
   }

@@ -351,3 +351,35 @@ def test_8k_mixed_sampled_against_oracle(ctx):
     o0 = int(descs["offset"][20 * 120])
     assert np.array_equal(pixels[o0:o0 + ref.payload.size], ref.payload)
     assert np.array_equal(got[y0:y1], O.expand(ref, O.CATMULLROM, nthreads=8))
+
+
+# ---------------------------------------------------------------------------------------------
+# opt-in fused-multiply-add resample: dims / offsets / values unchanged, pixels within +-1 LSB
+# ---------------------------------------------------------------------------------------------
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+@pytest.mark.parametrize("filt", [1, 2, 3, 4])
+def test_fast_resample_within_one_lsb(filt):
+    ctx = N.Context(0)
+    ctx.set_fast_resample(True)
+    for img in (load_png("base.png"), synth(1024, 768, 4, seed=9), synth(1000, 600, 4, seed=8)):
+        h, w = img.shape[:2]
+        ref = O.shrink(img, 64, 64, O.METRIC_OKLAB_MAD, 1.0, filt, nthreads=8)
+        descs, pixels, _ = gpu_shrink(ctx, img, 64, 64, N.METRIC_OKLAB_MAD, 1.0, filt)
+        assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+        assert np.array_equal(descs["offset"], ref.descs["offset"])
+        d = np.abs(pixels.astype(np.int16) - ref.payload.astype(np.int16))
+        assert d.max() <= 1, "shrunk pixels must stay within +-1 LSB"
+        pl = ctx.payload_upload(w, h, 64, 64, 4, ref.descs.astype(N.DESC_DTYPE), ref.payload)
+        out = pl.expand(filt)
+        pl.free()
+        want = O.expand(ref, filt, nthreads=8)
+        d2 = np.abs(out.astype(np.int16) - want.astype(np.int16))
+        assert d2.max() <= 1, "expanded pixels must stay within +-1 LSB"
+        assert psnr(out, want) > 70.0
+        print(f"filter {filt}: shrink differing px {float((d > 0).mean()):.2e}, expand differing px {float((d2 > 0).mean()):.2e}, "
+              f"PSNR vs reference decode {psnr(out, want):.1f} dB")
+    ctx.close()

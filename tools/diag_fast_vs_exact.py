@@ -64,6 +64,16 @@ for filt in (4, 2, 0):
     for k, (ms, n) in prof.items():
         if n:
             print(f"   {k:18s} {ms / n * 1000:9.1f} us x{n}")
+# fused multiply-add resample (opt-in)
+ctx.set_fast_resample(True)
+for it in range(2):
+    pl = d.shrink(64, 64, N.METRIC_OKLAB_MAD, 1.0, 4, 0); pl.expand_to_image(4, out); pl.free()
+ctx.profile_enable(True)
+for it in range(10):
+    pl = d.shrink(64, 64, N.METRIC_OKLAB_MAD, 1.0, 4, 0); pl.expand_to_image(4, out); pl.free()
+print("fma resample:", {k: round(ms / n * 1000, 1) for k, (ms, n) in ctx.profile_read().items() if n})
+ctx.profile_enable(False)
+ctx.set_fast_resample(False)
 # exact-all timing
 ctx.profile_enable(True)
 for it in range(3):
