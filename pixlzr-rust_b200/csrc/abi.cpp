@@ -38,6 +38,7 @@ struct TabSet {  // device copy of the axis tables of one (spec, filter, directi
   AxisTab* d_tabs = nullptr;
   uint32_t* d_pool = nullptr;
   uint32_t max_words = 0;  // largest single table (left | count | weights), in 32-bit words
+  uint32_t ntabs = 0;
 };
 
 using TabKey = std::tuple<std::vector<uint32_t>, std::vector<uint32_t>, int, int>;
@@ -248,6 +249,7 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
     seen[{n_in, n_out}] = tabs[i];
   }
   TabSet ts;
+  ts.ntabs = (uint32_t)tabs.size();
   for (const AxisTab& t : tabs) ts.max_words = std::max(ts.max_words, std::max(2 * t.n_out + t.n_out * t.stride, t.bwords));
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_tabs, tabs.size() * sizeof(AxisTab))) != PXZ_OK) return st;
@@ -285,7 +287,7 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   }
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
-                                max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, ctx->stream, ctx->sm_count,
+                                ts.ntabs, max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, ctx->stream, ctx->sm_count,
                                 &ctx->launches));
   return PXZ_OK;
 }

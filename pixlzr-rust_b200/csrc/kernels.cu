@@ -1078,49 +1078,70 @@ __global__ void __launch_bounds__(kThreads) k_resample(int direction, uint8_t* _
 //     tables, AxisTab::boff): one 16-byte source load + one broadcast 16-byte weight load feed 16
 //     multiply-adds, so the kernel is bound by the FP32 pipe and not by shared-memory bandwidth;
 //   * when every alpha of the block is 255 the alpha channel is not computed (it resamples to 255);
-//   * rounding to u8 avoids the conversion pipe.
+//   * rounding to u8 avoids the conversion pipe;
+//   * descriptors, table indices and the tap tables themselves run one block ahead (cp.async into a second
+//     shared-memory table buffer), so no dependent global load sits between two blocks.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastMaxPx = 4096;
-constexpr int kFastMaxTabWords = 1024;  // one staged table section (checked on the host: max_tab_words)
+constexpr int kFastMaxTabWords = 768;   // one staged table section (checked on the host: max_tab_words)
+constexpr int kFastMaxTabs = 128;       // AxisTab entries cached in shared memory (checked on the host)
 constexpr int kSrcStride = 64;          // float4 per source row in shared memory
 
 struct FastSmem {
-  float4* src;     // [64][64], column index swizzled by swz_src()
-  float4* tmp;     // [dh][ts], ts = sw rounded up to 8, column index XORed with (row & 7)
-  uint32_t* taby;  // [kFastMaxTabWords]
+  float4* src;        // [64][64], column index swizzled by swz_src()
+  float4* tmp;        // [dh][ts], ts = sw rounded up to 8, column index XORed with (row & 7)
+  uint32_t* tab;      // [2 buffers][2 axes (y, x)][kFastMaxTabWords]
+  AxisTab* atab;      // [kFastMaxTabs]
+  uint32_t* taby;     // current buffer, set per block
   uint32_t* tabx;
 };
+
+__host__ __device__ constexpr size_t fast_smem_bytes(uint32_t max_tmp_px) {
+  return (size_t)(kFastMaxPx + max_tmp_px) * 16 + 4 * (size_t)kFastMaxTabWords * 4 + (size_t)kFastMaxTabs * sizeof(AxisTab);
+}
 
 __device__ __forceinline__ FastSmem carve_fast_smem(float* base, uint32_t max_tmp_px) {
   FastSmem s;
   s.src = reinterpret_cast<float4*>(base);
   s.tmp = s.src + kFastMaxPx;
-  s.taby = reinterpret_cast<uint32_t*>(s.tmp + max_tmp_px);
-  s.tabx = s.taby + kFastMaxTabWords;
+  s.tab = reinterpret_cast<uint32_t*>(s.tmp + max_tmp_px);
+  s.atab = reinterpret_cast<AxisTab*>(s.tab + 4 * kFastMaxTabWords);
+  s.taby = s.tab;
+  s.tabx = s.tab + kFastMaxTabWords;
   return s;
 }
 
+__device__ __forceinline__ void cp_async_4(uint32_t* smem_dst, const uint32_t* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_keep1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// asynchronous staging of one axis table (blocked or per-output form) into a shared-memory table buffer
+__device__ __forceinline__ void stage_axis_async(const AxisTab& t, bool blocked, const uint32_t* __restrict__ pool, uint32_t* dst) {
+  const uint32_t* src = pool + (blocked ? t.boff : t.off);
+  const uint32_t words = blocked ? t.bwords : 2 * t.n_out + t.n_out * t.stride;
+  for (uint32_t i = threadIdx.x; i < words; i += kThreads) cp_async_4(dst + i, src + i);
+}
+// which table forms a (sw x sh) -> (dw x dh) block uses
+__device__ __forceinline__ bool y_blocked(uint32_t dh) { return dh >= 8; }
+__device__ __forceinline__ bool x_blocked(uint32_t dw, uint32_t dh) { return dw >= 8 && dh >= 8; }
+
 // quad-mapped stores (lane l writes pixels 4l+i) and column-mapped loads are both conflict free
 __device__ __forceinline__ uint32_t swz_src(uint32_t x) { return x ^ ((x >> 3) & 7u); }
-
-__device__ __forceinline__ void stage_words(const uint32_t* __restrict__ src, uint32_t words, uint32_t* dst) {
-  for (uint32_t i = threadIdx.x; i < words; i += kThreads) dst[i] = __ldg(src + i);
-}
 
 __device__ __forceinline__ float4 px_to_f4(uint32_t w) {
   return make_float4(byte_to_float<0>(w), byte_to_float<1>(w), byte_to_float<2>(w), byte_to_float<3>(w));
 }
 
-// NumCast::from(FloatNearest(clamp(t, 0, 255))): round half away from zero, without F2I/I2F.
-// u = t + 2^23 rounds to nearest-even into the low mantissa bits; an exact .5 tie that went down is bumped.
-__device__ __forceinline__ uint32_t to_u8_fast(float t) {
+// NumCast::from(FloatNearest(clamp(t, 0, 255))): round half away from zero, without F2I/I2F.  For t >= 0 that is
+// floor(t + 0.5): both additions round toward zero, so t + 0.5 never crosses an integer upwards and adding 2^23
+// drops the fraction; the integer sits in the low mantissa bits.  Returns the float whose low byte is the result.
+__device__ __forceinline__ uint32_t to_u8_bits(float t) {
   t = fminf(fmaxf(t, 0.0f), 255.0f);
-  const float u = __fadd_rn(t, 8388608.0f);
-  const float r = __fadd_rn(u, -8388608.0f);
-  uint32_t q = __float_as_uint(u) & 0xFFu;
-  if (__fadd_rn(t, -r) == 0.5f) q += 1;
-  return q;
+  return __float_as_uint(__fadd_rz(__fadd_rz(t, 0.5f), 8388608.0f));
 }
+__device__ __forceinline__ uint32_t to_u8_fast(float t) { return to_u8_bits(t) & 0xFFu; }
 
 // MODE bit 0: the alpha channel is computed; bit 1: fused multiply-add (PXZ "fast resample": not bit-exact,
 // pixels stay within +-1 LSB of the reference order)
@@ -1140,7 +1161,10 @@ __device__ __forceinline__ void mac(float4& acc, const float4& p, float w) {
 }
 template <int MODE>
 __device__ __forceinline__ uint32_t pack_px(const float4& a) {
-  return to_u8_fast(a.x) | (to_u8_fast(a.y) << 8) | (to_u8_fast(a.z) << 16) | ((MODE & 1) ? (to_u8_fast(a.w) << 24) : 0xFF000000u);
+  // byte 0 of each rounded channel, gathered with two byte permutes
+  const uint32_t rg = __byte_perm(to_u8_bits(a.x), to_u8_bits(a.y), 0x0040);                              // {r, g, r, r}
+  const uint32_t ba = __byte_perm(to_u8_bits(a.z), (MODE & 1) ? to_u8_bits(a.w) : 0x000000FFu, 0x0040);  // {b, a, b, b}
+  return __byte_perm(rg, ba, 0x5410);                                                                    // {r, g, b, a}
 }
 
 // One staged axis table: either the blocked form (outputs in groups of 4) or the per-output form.
@@ -1157,14 +1181,15 @@ struct StagedTab {
 template <int MODE>
 __device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
                                                  const AxisTab& ty, const uint32_t* taby) {
-  const uint32_t x = threadIdx.x & 63u, grp = threadIdx.x >> 6;
+  const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);  // lanes per row = next power of two >= sw
+  const uint32_t x = threadIdx.x & ((1u << lshift) - 1), grp = threadIdx.x >> lshift, ngrp = kThreads >> lshift;
   if (x >= sw) return;
   const float4* w4 = reinterpret_cast<const float4*>(taby);
   const uint32_t* lo = taby + 4 * ty.brows_total;
   const uint32_t* rows = lo + ty.nb;
   const uint32_t* first = rows + ty.nb;
   const uint32_t xs = swz_src(x);
-  for (uint32_t ob = grp; ob < ty.nb; ob += kThreads / 64) {
+  for (uint32_t ob = grp; ob < ty.nb; ob += ngrp) {
     const uint32_t n = rows[ob];
     const float4* wp = w4 + first[ob];
     const float4* sp = src + lo[ob] * kSrcStride + xs;
@@ -1193,13 +1218,14 @@ __device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp,
 template <int MODE>
 __device__ __forceinline__ void vertical_plain(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
                                                const AxisTab& ty, const uint32_t* taby) {
-  const uint32_t x = threadIdx.x & 63u, grp = threadIdx.x >> 6;
+  const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);
+  const uint32_t x = threadIdx.x & ((1u << lshift) - 1), grp = threadIdx.x >> lshift, ngrp = kThreads >> lshift;
   if (x >= sw) return;
   const uint32_t* left = taby;
   const uint32_t* cnt = taby + dh;
   const float* w = reinterpret_cast<const float*>(taby + 2 * dh);
   const uint32_t xs = swz_src(x);
-  for (uint32_t oy = grp; oy < dh; oy += kThreads / 64) {
+  for (uint32_t oy = grp; oy < dh; oy += ngrp) {
     const uint32_t n = cnt[oy];
     const float* wr = w + oy * ty.stride;
     const float4* sp = src + left[oy] * kSrcStride + xs;
@@ -1285,20 +1311,15 @@ __device__ __forceinline__ void resample_staged(const FastSmem& sm, uint32_t sw,
   else horizontal_plain<MODE>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
 }
 
-__device__ __forceinline__ void stage_axis(const AxisTab& t, bool blocked, const uint32_t* __restrict__ pool, uint32_t* dst) {
-  if (blocked) stage_words(pool + t.boff, t.bwords, dst);
-  else stage_words(pool + t.off, 2 * t.n_out + t.n_out * t.stride, dst);
-}
-
 // ---- encode side: 64x64-or-smaller tiles of the pitched image -> packed payload -----------------------------
 template <bool FUSED>
 __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
                                                              const pxz_block_desc* __restrict__ descs,
                                                              const uint32_t* __restrict__ tabidx, uint8_t* __restrict__ payload,
-                                                             const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool,
-                                                             uint32_t max_tmp_px) {
+                                                             const AxisTab* __restrict__ tabs, uint32_t ntabs,
+                                                             const uint32_t* __restrict__ pool, uint32_t max_tmp_px) {
   extern __shared__ float s_dyn[];
-  const FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
+  FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
   const uint32_t tid = threadIdx.x;
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t qpr = g.bw >> 2;  // 16-byte quads per full tile row
@@ -1309,8 +1330,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
     qrow[j] = q / qpr;
     qcol[j] = (q - qrow[j] * qpr) * 4;
   }
+  for (uint32_t i = tid; i < ntabs * (sizeof(AxisTab) / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(sm.atab)[i] = __ldg(reinterpret_cast<const uint32_t*>(tabs) + i);
+  __syncthreads();
 
-  uint4 cur[4];
   auto prefetch = [&](uint32_t b, uint4(&v)[4]) {
     if (b >= nblocks) return;
     const Tile t = tile_of(g, b);
@@ -1320,16 +1343,44 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
       v[j] = (qrow[j] < t.th && qcol[j] < t.tw) ? ldg_nc_v4(base + (size_t)qrow[j] * pitch + (size_t)qcol[j] * 4)
                                                  : make_uint4(0xFF000000u, 0xFF000000u, 0xFF000000u, 0xFF000000u);
   };
+  // tables of block `b` (descriptor d, table indices ti) -> table buffer `buf`; always commits one cp.async group
+  auto stage_tables = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti, uint32_t buf) {
+    if (b < nblocks) {
+      const Tile t = tile_of(g, b);
+      if (!(t.tw == d.w && t.th == d.h)) {
+        uint32_t* dst = sm.tab + buf * 2 * kFastMaxTabWords;
+        stage_axis_async(sm.atab[ti >> 16], y_blocked(d.h), pool, dst);
+        stage_axis_async(sm.atab[ti & 0xFFFFu], x_blocked(d.w, d.h), pool, dst + kFastMaxTabWords);
+      }
+    }
+    cp_async_commit();
+  };
+
   uint32_t b = blockIdx.x;
+  uint4 cur[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cur[j] = make_uint4(0, 0, 0, 0);
   prefetch(b, cur);
-  for (; b < nblocks; b += gridDim.x) {
+  pxz_block_desc dcur{}, dnxt{};
+  uint32_t ticur = 0, tinxt = 0;
+  if (b < nblocks) { dcur = descs[b]; ticur = tabidx[b]; }
+  if (b + gridDim.x < nblocks) { dnxt = descs[b + gridDim.x]; tinxt = tabidx[b + gridDim.x]; }
+  stage_tables(b, dcur, ticur, 0);
+  for (uint32_t it = 0; b < nblocks; b += gridDim.x, ++it) {
+    const uint32_t buf = it & 1;
     const Tile t = tile_of(g, b);
-    const pxz_block_desc d = descs[b];
-    const uint32_t ti = tabidx[b];
+    const pxz_block_desc d = dcur;
+    const uint32_t ti = ticur;
+    // everything the next block needs is requested now and consumed one iteration later
     uint4 nxt[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) nxt[j] = make_uint4(0, 0, 0, 0);
     prefetch(b + gridDim.x, nxt);
+    pxz_block_desc dnn{};
+    uint32_t tinn = 0;
+    if (b + 2 * gridDim.x < nblocks) { dnn = descs[b + 2 * gridDim.x]; tinn = tabidx[b + 2 * gridDim.x]; }
+    stage_tables(b + gridDim.x, dnxt, tinxt, buf ^ 1);
+
     uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset);
     const uint32_t sw = t.tw, sh = t.th, dw = d.w, dh = d.h;
     if (sw == dw && sh == dh) {
@@ -1342,10 +1393,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
         }
       }
     } else {
-      const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
-      const bool yb = dh >= 8, xb = dw >= 8 && dh >= 8;
-      stage_axis(ty, yb, pool, sm.taby);
-      stage_axis(tx, xb, pool, sm.tabx);
+      const AxisTab tx = sm.atab[ti & 0xFFFFu], ty = sm.atab[ti >> 16];
+      const bool yb = y_blocked(dh), xb = x_blocked(dw, dh);
+      sm.taby = sm.tab + buf * 2 * kFastMaxTabWords;
+      sm.tabx = sm.taby + kFastMaxTabWords;
       uint32_t aand = 0xFF000000u;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1358,6 +1409,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
           o[swz_src(qcol[j] + 3)] = px_to_f4(cur[j].w);
         }
       }
+      cp_async_wait_keep1();  // this block's tables (requested one iteration ago) have landed
       const bool opaque = __syncthreads_and(aand == 0xFF000000u) != 0;  // also the barrier after staging
       auto put = [&](uint32_t oy, uint32_t ox, uint32_t n, const uint32_t(&px)[4]) {
         uint32_t* o = dst + (size_t)oy * dw + ox;
@@ -1372,6 +1424,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    dcur = dnxt; ticur = tinxt;
+    dnxt = dnn; tinxt = tinn;
   }
 }
 
@@ -1381,18 +1435,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
                                                              const pxz_block_desc* __restrict__ descs,
                                                              const uint32_t* __restrict__ tabidx,
                                                              const uint8_t* __restrict__ payload,
-                                                             const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool,
-                                                             uint32_t max_tmp_px) {
+                                                             const AxisTab* __restrict__ tabs, uint32_t ntabs,
+                                                             const uint32_t* __restrict__ pool, uint32_t max_tmp_px) {
   extern __shared__ float s_dyn[];
-  const FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
+  FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
   const uint32_t tid = threadIdx.x;
   const uint32_t nblocks = g.cols * g.rows;
+  for (uint32_t i = tid; i < ntabs * (sizeof(AxisTab) / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(sm.atab)[i] = __ldg(reinterpret_cast<const uint32_t*>(tabs) + i);
+  __syncthreads();
 
-  uint32_t cur[16];
-  pxz_block_desc dcur;
-  auto prefetch = [&](uint32_t b, uint32_t(&v)[16], pxz_block_desc& d) {
-    if (b >= nblocks) { d.w = 0; d.h = 0; d.offset = 0; return; }
-    d = descs[b];
+  auto prefetch = [&](uint32_t b, uint32_t(&v)[16], const pxz_block_desc& d) {
+    if (b >= nblocks) return;
     const uint32_t n = (uint32_t)d.w * d.h;
     const uint32_t* p = reinterpret_cast<const uint32_t*>(payload + d.offset);
 #pragma unroll
@@ -1401,15 +1455,43 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
       v[j] = i < n ? __ldg(p + i) : 0xFF000000u;
     }
   };
+  auto stage_tables = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti, uint32_t buf) {
+    if (b < nblocks) {
+      const Tile t = tile_of(g, b);
+      if (!(t.tw == d.w && t.th == d.h)) {
+        uint32_t* dst = sm.tab + buf * 2 * kFastMaxTabWords;
+        stage_axis_async(sm.atab[ti >> 16], y_blocked(t.th), pool, dst);
+        stage_axis_async(sm.atab[ti & 0xFFFFu], x_blocked(t.tw, t.th), pool, dst + kFastMaxTabWords);
+      }
+    }
+    cp_async_commit();
+  };
+
+  // descriptors run two blocks ahead: the pixel prefetch of the next block needs its descriptor
   uint32_t b = blockIdx.x;
+  pxz_block_desc dcur{}, dnxt{};
+  uint32_t ticur = 0, tinxt = 0;
+  if (b < nblocks) { dcur = descs[b]; ticur = tabidx[b]; }
+  if (b + gridDim.x < nblocks) { dnxt = descs[b + gridDim.x]; tinxt = tabidx[b + gridDim.x]; }
+  uint32_t cur[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cur[j] = 0xFF000000u;
   prefetch(b, cur, dcur);
-  for (; b < nblocks; b += gridDim.x) {
+  stage_tables(b, dcur, ticur, 0);
+  for (uint32_t it = 0; b < nblocks; b += gridDim.x, ++it) {
+    const uint32_t buf = it & 1;
     const Tile t = tile_of(g, b);
     const pxz_block_desc d = dcur;
-    const uint32_t ti = tabidx[b];
+    const uint32_t ti = ticur;
     uint32_t nxt[16];
-    pxz_block_desc dnxt;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nxt[j] = 0xFF000000u;
     prefetch(b + gridDim.x, nxt, dnxt);
+    pxz_block_desc dnn{};
+    uint32_t tinn = 0;
+    if (b + 2 * gridDim.x < nblocks) { dnn = descs[b + 2 * gridDim.x]; tinn = tabidx[b + 2 * gridDim.x]; }
+    stage_tables(b + gridDim.x, dnxt, tinxt, buf ^ 1);
+
     uint8_t* dst = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
     const uint32_t sw = d.w, sh = d.h, dw = t.tw, dh = t.th;
     const bool pow2 = (sw & (sw - 1)) == 0;
@@ -1424,10 +1506,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
         }
       }
     } else {
-      const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
-      const bool yb = dh >= 8, xb = dw >= 8 && dh >= 8;
-      stage_axis(ty, yb, pool, sm.taby);
-      stage_axis(tx, xb, pool, sm.tabx);
+      const AxisTab tx = sm.atab[ti & 0xFFFFu], ty = sm.atab[ti >> 16];
+      const bool yb = y_blocked(dh), xb = x_blocked(dw, dh);
+      sm.taby = sm.tab + buf * 2 * kFastMaxTabWords;
+      sm.tabx = sm.taby + kFastMaxTabWords;
       uint32_t aand = 0xFF000000u;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -1438,6 +1520,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
           sm.src[y * kSrcStride + swz_src(x)] = px_to_f4(cur[j]);
         }
       }
+      cp_async_wait_keep1();
       const bool opaque = __syncthreads_and((aand & 0xFF000000u) == 0xFF000000u) != 0;
       auto put = [&](uint32_t oy, uint32_t ox, uint32_t n, const uint32_t(&px)[4]) {
         uint32_t* o = reinterpret_cast<uint32_t*>(dst + (size_t)oy * pitch) + ox;
@@ -1455,7 +1538,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
-    dcur = dnxt;
+    dcur = dnxt; ticur = tinxt;
+    dnxt = dnn; tinxt = tinn;
   }
 }
 
@@ -1592,33 +1676,35 @@ int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (
 
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
-                            uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words, uint8_t* scratch,
-                            size_t scratch_per_cta, int grid, bool fused, cudaStream_t s, int sm_count, uint64_t* launches) {
+                            uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
+                            uint8_t* scratch, size_t scratch_per_cta, int grid, bool fused, cudaStream_t s, int sm_count,
+                            uint64_t* launches) {
   cudaError_t e;
   ++*launches;
   // RGBA fast paths: tiles <= 64x64 with 16-byte aligned rows
   const bool fast = g.C == 4 && g.bw <= 64 && g.bh <= 64 && (g.bw % 4 == 0) && (g.W % 4 == 0) && (pitch % 16 == 0) &&
                     ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && max_src_px <= (uint32_t)kFastMaxPx && max_src_dim <= 64u &&
-                    max_tmp_px <= (uint32_t)kFastMaxPx && max_tab_words <= (uint32_t)kFastMaxTabWords && scratch == nullptr;
+                    max_tmp_px <= (uint32_t)kFastMaxPx && max_tab_words <= (uint32_t)kFastMaxTabWords &&
+                    ntabs <= (uint32_t)kFastMaxTabs && scratch == nullptr;
   if (fast) {
-    const size_t smem = (size_t)(kFastMaxPx + max_tmp_px) * sizeof(float4) + 2 * (size_t)kFastMaxTabWords * sizeof(uint32_t);
+    const size_t smem = fast_smem_bytes(max_tmp_px);
     const int fgrid = clamp_grid((long long)g.cols * g.rows, (long long)sm_count * 2);
     if (direction == 0 && !fused) {
       e = set_smem(k_shrink_rgba<false>, smem);
       if (e != cudaSuccess) return e;
-      k_shrink_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+      k_shrink_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
     } else if (direction == 0) {
       e = set_smem(k_shrink_rgba<true>, smem);
       if (e != cudaSuccess) return e;
-      k_shrink_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+      k_shrink_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
     } else if (!fused) {
       e = set_smem(k_expand_rgba<false>, smem);
       if (e != cudaSuccess) return e;
-      k_expand_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+      k_expand_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
     } else {
       e = set_smem(k_expand_rgba<true>, smem);
       if (e != cudaSuccess) return e;
-      k_expand_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, max_tmp_px);
+      k_expand_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
     }
     return cudaGetLastError();
   }
