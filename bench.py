@@ -165,6 +165,7 @@ def workload_config(args, batch: int, sample_rows: int | None = None) -> dict:
         "width": IMG_W, "height": IMG_H, "channels": 4, "block": BS, "metric": "oklab_mad", "factor": FACTOR,
         "filter_down": "Lanczos3", "filter_up": "Lanczos3", "images_per_step_per_gpu": batch,
         "sharding": "independent images per rank, no data-path collective",
+        "streams_per_gpu": getattr(args, "streams", 1),
         "cache": "inputs larger than L2 (batch x 132.7 MB per step)",
         "resize_semantics": "image_rs (the branch pinned by the reference's fixtures)",
     }
@@ -203,13 +204,19 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dev_imgs = [t.to(dev, non_blocking=True) for t in host_imgs]
         dev_out = torch.empty((IMG_H, IMG_W, 4), dtype=torch.uint8, device=dev)
         stream.synchronize()
-        wrapped = [ctx.image_wrap(t.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for t in dev_imgs]
-        wrapped_out = ctx.image_wrap(dev_out.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4)
+        # device-resident leg: `--streams` contexts (one CUDA stream each) take the images of a step in turn, so the
+        # latency-bound kernels of one image (guard-band recompute, plan) overlap the throughput kernels of another
+        n_streams = max(1, min(args.streams, batch))
+        streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
+        ctxs = [ctx] + [N.Context(local_rank, cuda_stream=st.cuda_stream) for st in streams[1:]]
+        outs = [dev_out] + [torch.empty_like(dev_out) for _ in range(n_streams - 1)]
+        wrapped = [ctxs[i % n_streams].image_wrap(t.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for i, t in enumerate(dev_imgs)]
+        wrapped_out = [ctxs[k].image_wrap(outs[k].data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for k in range(n_streams)]
 
         def step_device():
-            for im in wrapped:
+            for i, im in enumerate(wrapped):
                 pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
-                pl.expand_to_image(FILTER_UP, wrapped_out)
+                pl.expand_to_image(FILTER_UP, wrapped_out[i % n_streams])
                 pl.free()
 
         # payload sizes (for the algorithmic-byte counts), untimed
@@ -223,7 +230,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
         for _ in range(args.warmup):
             step_device()
-        stream.synchronize()
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -231,13 +238,20 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
         sampler.start()
         time.sleep(0.25)
-        launches0 = ctx.launch_count()
-        ctx.profile_enable(True)
+        launches0 = sum(c.launch_count() for c in ctxs)
+        for c in ctxs:
+            c.profile_enable(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.time()
-        ev0.record(stream)
+        ev0.record(stream)               # the timed region starts on the launching stream ...
+        for st in streams[1:]:
+            st.wait_event(ev0)           # ... and every other stream starts after it
         for _ in range(args.steps):
             step_device()
+        for st in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(st)
+            stream.wait_event(e)         # the launching stream joins all the others before the end event
         ev1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -245,10 +259,33 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         if world > 1:
             dist.barrier()
         elapsed_ms = ev0.elapsed_time(ev1)
-        prof = ctx.profile_read()
-        ctx.profile_enable(False)
-        launches = ctx.launch_count() - launches0
+        prof = {}
+        for c in ctxs:
+            for name, (ms, n) in c.profile_read().items():
+                a, b = prof.get(name, (0.0, 0))
+                prof[name] = (a + ms, b + n)
+            c.profile_enable(False)
+        launches = sum(c.launch_count() for c in ctxs) - launches0
         clocks = sampler.stop(t_wall0, t_wall1)
+        # per-kernel durations without cross-stream contention: the same K steps again on the launching stream only
+        prof_overlapped = prof
+        if n_streams > 1:
+            solo = [ctx.image_wrap(t.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for t in dev_imgs]
+            ctx.profile_enable(True)
+            ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev2.record(stream)
+            for _ in range(args.steps):
+                for im in solo:
+                    pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+                    pl.expand_to_image(FILTER_UP, wrapped_out[0])
+                    pl.free()
+            ev3.record(stream)
+            stream.synchronize()
+            solo_ms = ev2.elapsed_time(ev3)
+            prof = ctx.profile_read()
+            ctx.profile_enable(False)
+        else:
+            solo_ms = elapsed_ms
 
         # ---- e2e: same work through the C ABI with pinned host buffers ---------------------------------
         # `E2E_WORKERS` host threads, each with its own context (= its own stream) and pinned staging buffers, take
@@ -346,13 +383,20 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 us = ms / n * 1e3
                 gbs = algo.get(name, 0) / (us * 1e-6) / 1e9
                 kernels[name] = {"us": round(us, 2), "launches": int(n), "algo_GBps": round(gbs, 1),
-                                 "frac": round(gbs / peak, 4), "share": round(ms / elapsed_ms, 4)}
+                                 "frac": round(gbs / peak, 4), "share": round(ms / solo_ms, 4)}
+                if n_streams > 1 and name in prof_overlapped and prof_overlapped[name][1]:
+                    kernels[name]["us_in_timed_region"] = round(prof_overlapped[name][0] / prof_overlapped[name][1] * 1e3, 2)
         dom = max(kernels, key=lambda k: kernels[k]["us"] * kernels[k]["launches"]) if kernels else None
         roofline = None
         if dom:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["algo_GBps"], "peak": peak,
                         "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": int(algo[dom]), "avg_launch_us": kernels[dom]["us"]}
+                        "algorithmic_bytes_per_launch": int(algo[dom]), "avg_launch_us": kernels[dom]["us"],
+                        "timing": ("CUDA events around every launch; single-stream pass of the same K steps right after the "
+                                   "timed region (in the 2-stream timed region kernels of different images overlap: see "
+                                   "kernels[*].us_in_timed_region)") if n_streams > 1 else
+                                  "CUDA events around every launch inside the timed region",
+                        "single_stream_value_MPps": round(world * batch * IMG_W * IMG_H / 1e6 * args.steps / (solo_ms / 1e3), 1)}
         # whole encode+decode stage against the roofline (image read once + payload written, payload read + image written)
         stage_bytes = (4 * n_px + mean_payload + 16 * nblocks) + (mean_payload + 16 * nblocks + 4 * n_px)
         per_image_s = elapsed_ms / 1e3 / (args.steps * batch)
@@ -389,6 +433,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="8K images per rank per step")
+    ap.add_argument("--streams", type=int, default=2, help="contexts / CUDA streams of the device-resident leg")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads (contexts) of the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
