@@ -1073,7 +1073,8 @@ __global__ void __launch_bounds__(kThreads) k_resample(int direction, uint8_t* _
 // Same arithmetic and accumulation order as k_resample (so the pixels stay bit-identical), but
 //   * the next block's source is prefetched into registers while the current one is resampled
 //     (persistent CTAs, grid-stride), so global-load latency is off the critical path;
-//   * the source block is converted u8 -> f32 once, into shared memory (row stride 64, XOR swizzle);
+//   * the source block stays packed RGBA8 in shared memory (16 KB, row stride 64 px) and is converted to f32 as it
+//     is read by the vertical pass, which keeps three CTAs resident per SM;
 //   * outputs are produced in groups of 4 that share one walk over the source samples (blocked tap
 //     tables, AxisTab::boff): one 16-byte source load + one broadcast 16-byte weight load feed 16
 //     multiply-adds, so the kernel is bound by the FP32 pipe and not by shared-memory bandwidth;
@@ -1082,13 +1083,16 @@ __global__ void __launch_bounds__(kThreads) k_resample(int direction, uint8_t* _
 //   * descriptors, table indices and the tap tables themselves run one block ahead (cp.async into a second
 //     shared-memory table buffer), so no dependent global load sits between two blocks.
 // ------------------------------------------------------------------------------------------------
+#ifndef PXZ_RESAMPLE_MINBLOCKS
+#define PXZ_RESAMPLE_MINBLOCKS 3
+#endif
 constexpr int kFastMaxPx = 4096;
 constexpr int kFastMaxTabWords = 768;   // one staged table section (checked on the host: max_tab_words)
 constexpr int kFastMaxTabs = 128;       // AxisTab entries cached in shared memory (checked on the host)
-constexpr int kSrcStride = 64;          // float4 per source row in shared memory
+constexpr int kSrcStride = 64;          // pixels (u32) per source row in shared memory
 
 struct FastSmem {
-  float4* src;        // [64][64], column index swizzled by swz_src()
+  uint32_t* src;      // [64][64] packed RGBA8
   float4* tmp;        // [dh][ts], ts = sw rounded up to 8, column index XORed with (row & 7)
   uint32_t* tab;      // [2 buffers][2 axes (y, x)][kFastMaxTabWords]
   AxisTab* atab;      // [kFastMaxTabs]
@@ -1097,13 +1101,13 @@ struct FastSmem {
 };
 
 __host__ __device__ constexpr size_t fast_smem_bytes(uint32_t max_tmp_px) {
-  return (size_t)(kFastMaxPx + max_tmp_px) * 16 + 4 * (size_t)kFastMaxTabWords * 4 + (size_t)kFastMaxTabs * sizeof(AxisTab);
+  return (size_t)kFastMaxPx * 4 + (size_t)max_tmp_px * 16 + 4 * (size_t)kFastMaxTabWords * 4 + (size_t)kFastMaxTabs * sizeof(AxisTab);
 }
 
 __device__ __forceinline__ FastSmem carve_fast_smem(float* base, uint32_t max_tmp_px) {
   FastSmem s;
-  s.src = reinterpret_cast<float4*>(base);
-  s.tmp = s.src + kFastMaxPx;
+  s.src = reinterpret_cast<uint32_t*>(base);
+  s.tmp = reinterpret_cast<float4*>(s.src + kFastMaxPx);
   s.tab = reinterpret_cast<uint32_t*>(s.tmp + max_tmp_px);
   s.atab = reinterpret_cast<AxisTab*>(s.tab + 4 * kFastMaxTabWords);
   s.taby = s.tab;
@@ -1127,11 +1131,9 @@ __device__ __forceinline__ void stage_axis_async(const AxisTab& t, bool blocked,
 __device__ __forceinline__ bool y_blocked(uint32_t dh) { return dh >= 8; }
 __device__ __forceinline__ bool x_blocked(uint32_t dw, uint32_t dh) { return dw >= 8 && dh >= 8; }
 
-// quad-mapped stores (lane l writes pixels 4l+i) and column-mapped loads are both conflict free
-__device__ __forceinline__ uint32_t swz_src(uint32_t x) { return x ^ ((x >> 3) & 7u); }
-
+template <int MODE>
 __device__ __forceinline__ float4 px_to_f4(uint32_t w) {
-  return make_float4(byte_to_float<0>(w), byte_to_float<1>(w), byte_to_float<2>(w), byte_to_float<3>(w));
+  return make_float4(byte_to_float<0>(w), byte_to_float<1>(w), byte_to_float<2>(w), (MODE & 1) ? byte_to_float<3>(w) : 0.f);
 }
 
 // NumCast::from(FloatNearest(clamp(t, 0, 255))): round half away from zero, without F2I/I2F.  For t >= 0 that is
@@ -1179,7 +1181,7 @@ struct StagedTab {
 
 // ---- vertical_sample: src [sh][64] -> tmp [dh][ts] ---------------------------------------------------------------
 template <int MODE>
-__device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
+__device__ __forceinline__ void vertical_blocked(const uint32_t* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
                                                  const AxisTab& ty, const uint32_t* taby) {
   const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);  // lanes per row = next power of two >= sw
   const uint32_t x = threadIdx.x & ((1u << lshift) - 1), grp = threadIdx.x >> lshift, ngrp = kThreads >> lshift;
@@ -1188,22 +1190,21 @@ __device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp,
   const uint32_t* lo = taby + 4 * ty.brows_total;
   const uint32_t* rows = lo + ty.nb;
   const uint32_t* first = rows + ty.nb;
-  const uint32_t xs = swz_src(x);
   for (uint32_t ob = grp; ob < ty.nb; ob += ngrp) {
     const uint32_t n = rows[ob];
     const float4* wp = w4 + first[ob];
-    const float4* sp = src + lo[ob] * kSrcStride + xs;
+    const uint32_t* sp = src + lo[ob] * kSrcStride + x;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     uint32_t r = 0;
     for (; r + 2 <= n; r += 2) {
-      const float4 p0 = sp[0], p1 = sp[kSrcStride];
+      const float4 p0 = px_to_f4<MODE>(sp[0]), p1 = px_to_f4<MODE>(sp[kSrcStride]);
       const float4 w0 = wp[r], w1 = wp[r + 1];
       mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
       mac<MODE>(a0, p1, w1.x); mac<MODE>(a1, p1, w1.y); mac<MODE>(a2, p1, w1.z); mac<MODE>(a3, p1, w1.w);
       sp += 2 * kSrcStride;
     }
     if (r < n) {
-      const float4 p0 = sp[0];
+      const float4 p0 = px_to_f4<MODE>(sp[0]);
       const float4 w0 = wp[r];
       mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
     }
@@ -1216,7 +1217,7 @@ __device__ __forceinline__ void vertical_blocked(const float4* src, float4* tmp,
 }
 
 template <int MODE>
-__device__ __forceinline__ void vertical_plain(const float4* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
+__device__ __forceinline__ void vertical_plain(const uint32_t* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
                                                const AxisTab& ty, const uint32_t* taby) {
   const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);
   const uint32_t x = threadIdx.x & ((1u << lshift) - 1), grp = threadIdx.x >> lshift, ngrp = kThreads >> lshift;
@@ -1224,21 +1225,21 @@ __device__ __forceinline__ void vertical_plain(const float4* src, float4* tmp, u
   const uint32_t* left = taby;
   const uint32_t* cnt = taby + dh;
   const float* w = reinterpret_cast<const float*>(taby + 2 * dh);
-  const uint32_t xs = swz_src(x);
   for (uint32_t oy = grp; oy < dh; oy += ngrp) {
     const uint32_t n = cnt[oy];
     const float* wr = w + oy * ty.stride;
-    const float4* sp = src + left[oy] * kSrcStride + xs;
+    const uint32_t* sp = src + left[oy] * kSrcStride + x;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t k = 0;
     for (; k + 4 <= n; k += 4) {
-      const float4 p0 = sp[0], p1 = sp[kSrcStride], p2 = sp[2 * kSrcStride], p3 = sp[3 * kSrcStride];
+      const float4 p0 = px_to_f4<MODE>(sp[0]), p1 = px_to_f4<MODE>(sp[kSrcStride]);
+      const float4 p2 = px_to_f4<MODE>(sp[2 * kSrcStride]), p3 = px_to_f4<MODE>(sp[3 * kSrcStride]);
       const float w0 = wr[k], w1 = wr[k + 1], w2 = wr[k + 2], w3 = wr[k + 3];
       mac<MODE>(acc, p0, w0); mac<MODE>(acc, p1, w1); mac<MODE>(acc, p2, w2); mac<MODE>(acc, p3, w3);
       sp += 4 * kSrcStride;
     }
     for (; k < n; ++k) {
-      mac<MODE>(acc, sp[0], wr[k]);
+      mac<MODE>(acc, px_to_f4<MODE>(sp[0]), wr[k]);
       sp += kSrcStride;
     }
     tmp[oy * ts + (x ^ (oy & 7u))] = acc;
@@ -1313,7 +1314,7 @@ __device__ __forceinline__ void resample_staged(const FastSmem& sm, uint32_t sw,
 
 // ---- encode side: 64x64-or-smaller tiles of the pitched image -> packed payload -----------------------------
 template <bool FUSED>
-__global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
+__global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_shrink_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
                                                              const pxz_block_desc* __restrict__ descs,
                                                              const uint32_t* __restrict__ tabidx, uint8_t* __restrict__ payload,
                                                              const AxisTab* __restrict__ tabs, uint32_t ntabs,
@@ -1401,13 +1402,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         aand &= (cur[j].x & cur[j].y) & (cur[j].z & cur[j].w);  // out-of-tile quads were filled with alpha 255
-        if (qrow[j] < sh && qcol[j] < sw) {
-          float4* o = sm.src + qrow[j] * kSrcStride;
-          o[swz_src(qcol[j] + 0)] = px_to_f4(cur[j].x);
-          o[swz_src(qcol[j] + 1)] = px_to_f4(cur[j].y);
-          o[swz_src(qcol[j] + 2)] = px_to_f4(cur[j].z);
-          o[swz_src(qcol[j] + 3)] = px_to_f4(cur[j].w);
-        }
+        if (qrow[j] < sh && qcol[j] < sw) *reinterpret_cast<uint4*>(sm.src + qrow[j] * kSrcStride + qcol[j]) = cur[j];
       }
       cp_async_wait_keep1();  // this block's tables (requested one iteration ago) have landed
       const bool opaque = __syncthreads_and(aand == 0xFF000000u) != 0;  // also the barrier after staging
@@ -1431,7 +1426,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_shrink_rgba(const uint8_t* __re
 
 // ---- decode side: packed payload blocks -> 64x64-or-smaller tiles of the pitched image (expand + paste) ------
 template <bool FUSED>
-__global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict__ img, size_t pitch, Geom g,
+__global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgba(uint8_t* __restrict__ img, size_t pitch, Geom g,
                                                              const pxz_block_desc* __restrict__ descs,
                                                              const uint32_t* __restrict__ tabidx,
                                                              const uint8_t* __restrict__ payload,
@@ -1517,7 +1512,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_expand_rgba(uint8_t* __restrict
         aand &= cur[j];
         if (i < sw * sh) {
           const uint32_t y = pow2 ? (i >> sshift) : (i / sw), x = i - y * sw;
-          sm.src[y * kSrcStride + swz_src(x)] = px_to_f4(cur[j]);
+          sm.src[y * kSrcStride + x] = cur[j];
         }
       }
       cp_async_wait_keep1();
@@ -1688,7 +1683,7 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                     ntabs <= (uint32_t)kFastMaxTabs && scratch == nullptr;
   if (fast) {
     const size_t smem = fast_smem_bytes(max_tmp_px);
-    const int fgrid = clamp_grid((long long)g.cols * g.rows, (long long)sm_count * 2);
+    const int fgrid = clamp_grid((long long)g.cols * g.rows, (long long)sm_count * PXZ_RESAMPLE_MINBLOCKS);
     if (direction == 0 && !fused) {
       e = set_smem(k_shrink_rgba<false>, smem);
       if (e != cudaSuccess) return e;
