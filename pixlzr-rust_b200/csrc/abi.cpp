@@ -53,6 +53,17 @@ struct ProfRec {
 
 }  // namespace
 
+// device buffers of a released payload, kept by the context for the next pxz_shrink / pxz_payload_upload so that
+// steady-state calls neither touch the allocator nor share blocks with other streams' contexts
+struct PayloadBufs {
+  pxz_block_desc* d_descs = nullptr;
+  uint32_t* d_tabidx = nullptr;
+  uint8_t* d_pixels = nullptr;
+  uint64_t* d_total = nullptr;
+  size_t nblocks = 0;
+  uint64_t capacity = 0;
+};
+
 struct pxz_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -78,6 +89,7 @@ struct pxz_ctx {
   std::map<TabKey, TabSet> tabs;
   void* comm = nullptr;
   bool fast_resample = false;
+  std::vector<PayloadBufs> payload_cache;  // at most kPayloadCacheMax entries
   // per-kernel timing
   bool profiling = false;
   std::vector<ProfRec> prof_open;
@@ -94,9 +106,12 @@ struct pxz_image {
   bool owned;
 };
 
+constexpr size_t kPayloadCacheMax = 4;
+
 struct pxz_payload {
   pxz_ctx* ctx;
   Geom g;
+  size_t nblocks_cap = 0;
   pxz_block_desc* d_descs = nullptr;
   uint32_t* d_tabidx = nullptr;
   uint8_t* d_pixels = nullptr;
@@ -294,10 +309,18 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
 
 void payload_release(pxz_payload* p) {
   if (!p) return;
-  dev_free(p->ctx, p->d_descs);
-  dev_free(p->ctx, p->d_tabidx);
-  dev_free(p->ctx, p->d_pixels);
-  dev_free(p->ctx, p->d_total);
+  pxz_ctx* ctx = p->ctx;
+  if (p->d_descs && p->d_tabidx && p->d_pixels && p->d_total && ctx->payload_cache.size() < kPayloadCacheMax) {
+    PayloadBufs b;
+    b.d_descs = p->d_descs; b.d_tabidx = p->d_tabidx; b.d_pixels = p->d_pixels; b.d_total = p->d_total;
+    b.nblocks = p->nblocks_cap; b.capacity = p->capacity;
+    ctx->payload_cache.push_back(b);  // stream order makes the reuse safe: later work on this ctx runs after ours
+  } else {
+    dev_free(ctx, p->d_descs);
+    dev_free(ctx, p->d_tabidx);
+    dev_free(ctx, p->d_pixels);
+    dev_free(ctx, p->d_total);
+  }
   delete p;
 }
 
@@ -380,6 +403,10 @@ void pxz_ctx_destroy(pxz_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) nccl_comm_destroy(ctx->comm);
+  for (auto& b : ctx->payload_cache) {
+    dev_free(ctx, b.d_descs); dev_free(ctx, b.d_tabidx); dev_free(ctx, b.d_pixels); dev_free(ctx, b.d_total);
+  }
+  ctx->payload_cache.clear();
   for (auto& kv : ctx->tabs) {
     dev_free(ctx, kv.second.d_tabs);
     dev_free(ctx, kv.second.d_pool);
@@ -608,14 +635,32 @@ static pxz_status payload_new(pxz_ctx* ctx, const Geom& g, uint64_t capacity, px
   if (!p) return fail(ctx, PXZ_E_OOM, "host allocation failed");
   p->ctx = ctx;
   p->g = g;
-  p->capacity = capacity;
   const size_t nblocks = (size_t)g.cols * g.rows;
+  // a cached set that is large enough (smallest fit)
+  int best = -1;
+  for (size_t i = 0; i < ctx->payload_cache.size(); ++i) {
+    const PayloadBufs& b = ctx->payload_cache[i];
+    if (b.nblocks >= nblocks && b.capacity >= capacity && (best < 0 || b.capacity < ctx->payload_cache[best].capacity)) best = (int)i;
+  }
+  if (best >= 0) {
+    const PayloadBufs b = ctx->payload_cache[best];
+    ctx->payload_cache.erase(ctx->payload_cache.begin() + best);
+    p->d_descs = b.d_descs; p->d_tabidx = b.d_tabidx; p->d_pixels = b.d_pixels; p->d_total = b.d_total;
+    p->nblocks_cap = b.nblocks; p->capacity = b.capacity;
+    *out = p;
+    return PXZ_OK;
+  }
+  p->capacity = capacity;
+  p->nblocks_cap = nblocks;
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&p->d_descs, nblocks * sizeof(pxz_block_desc))) != PXZ_OK ||
       (st = dev_alloc(ctx, (void**)&p->d_tabidx, nblocks * 4)) != PXZ_OK ||
       (st = dev_alloc(ctx, (void**)&p->d_pixels, capacity)) != PXZ_OK ||
       (st = dev_alloc(ctx, (void**)&p->d_total, 8)) != PXZ_OK) {
-    payload_release(p);
+    // partial allocations must not enter the cache
+    dev_free(ctx, p->d_descs); dev_free(ctx, p->d_tabidx); dev_free(ctx, p->d_pixels); dev_free(ctx, p->d_total);
+    p->d_descs = nullptr; p->d_tabidx = nullptr; p->d_pixels = nullptr; p->d_total = nullptr;
+    delete p;
     return st;
   }
   *out = p;
