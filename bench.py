@@ -386,11 +386,18 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                  "frac": round(gbs / peak, 4), "share": round(ms / solo_ms, 4)}
                 if n_streams > 1 and name in prof_overlapped and prof_overlapped[name][1]:
                     kernels[name]["us_in_timed_region"] = round(prof_overlapped[name][0] / prof_overlapped[name][1] * 1e3, 2)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except OSError:
+            pass
         dom = max(kernels, key=lambda k: kernels[k]["us"] * kernels[k]["launches"]) if kernels else None
         roofline = None
         if dom:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["algo_GBps"], "peak": peak,
-                        "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic.get(dom),
+                        "traffic_source": "profiles/r01_traffic.json (ncu --set full capture of the same workload)" if dom in traffic else None,
+                        "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(algo[dom]), "avg_launch_us": kernels[dom]["us"],
                         "timing": ("CUDA events around every launch; single-stream pass of the same K steps right after the "
                                    "timed region (in the 2-stream timed region kernels of different images overlap: see "

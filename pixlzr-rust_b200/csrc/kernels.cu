@@ -619,9 +619,10 @@ __global__ void __launch_bounds__(kThreads) k_band_list(const float* __restrict_
 }
 
 // list == nullptr: every tile (PXZ_FLAG_EXACT_VALUES); else the *count tiles of the list, one per CTA round-robin
+constexpr int kExactThreads = 1024;  // wide CTA: the per-pixel conversion is parallel, only the sums are sequential
 template <int C>
-__global__ void __launch_bounds__(kThreads) k_mad_exact(const uint8_t* __restrict__ img, size_t pitch, Geom g, float* vx,
-                                                        const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(kExactThreads) k_mad_exact(const uint8_t* __restrict__ img, size_t pitch, Geom g, float* vx,
+                                                             const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
   extern __shared__ float s_dyn[];
   float* s_val = s_dyn;  // 4 * kExactStride
   __shared__ float s_lut256[256];
@@ -1607,15 +1608,15 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
     if (e != cudaSuccess) return e;
   }
   ++*launches;
-  const int grid = clamp_grid(ntiles, (long long)sm_count * 3);
+  const int grid = clamp_grid(ntiles, (long long)sm_count * 2);
   if (g.C == 4) {
     e = set_smem(k_mad_exact<4>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<4><<<grid, kThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
+    k_mad_exact<4><<<grid, kExactThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
   } else {
     e = set_smem(k_mad_exact<3>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<3><<<grid, kThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
+    k_mad_exact<3><<<grid, kExactThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
   }
   return cudaGetLastError();
 }
