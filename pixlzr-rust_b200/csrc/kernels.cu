@@ -1608,15 +1608,17 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
     if (e != cudaSuccess) return e;
   }
   ++*launches;
-  const int grid = clamp_grid(ntiles, (long long)sm_count * 2);
+  // few banded tiles: one wide CTA per tile (latency); every tile: three narrow CTAs per SM (throughput)
+  const int threads = banded ? kExactThreads : kThreads;
+  const int grid = clamp_grid(ntiles, (long long)sm_count * (banded ? 2 : 3));
   if (g.C == 4) {
     e = set_smem(k_mad_exact<4>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<4><<<grid, kExactThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
+    k_mad_exact<4><<<grid, threads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
   } else {
     e = set_smem(k_mad_exact<3>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<3><<<grid, kExactThreads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
+    k_mad_exact<3><<<grid, threads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
   }
   return cudaGetLastError();
 }
