@@ -383,3 +383,50 @@ def test_fast_resample_within_one_lsb(filt):
         print(f"filter {filt}: shrink differing px {float((d > 0).mean()):.2e}, expand differing px {float((d2 > 0).mean()):.2e}, "
               f"PSNR vs reference decode {psnr(out, want):.1f} dB")
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# RGBA fast paths with a NON-opaque alpha channel (the opaque shortcut must not trigger), and mixed images
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("filt", [0, 2, 4])
+def test_rgba_fast_path_with_translucent_alpha(ctx, filt):
+    img = synth(512, 320, 4, seed=7)  # odd seed: random alpha
+    assert img[..., 3].min() < 255
+    img[64:192, 128:320, 3] = 255     # a few fully opaque tiles in between: both branches in one launch
+    for factor, flags in ((1.0, 0), (0.4, N.FLAG_EXACT_VALUES)):
+        ref = O.shrink(img, 64, 64, O.METRIC_OKLAB_MAD, factor, filt, nthreads=8)
+        descs, pixels, _ = gpu_shrink(ctx, img, 64, 64, N.METRIC_OKLAB_MAD, factor, filt, flags)
+        assert_same_payload(descs, pixels, ref, exact_values=bool(flags), scale=10 * factor)
+        pl = ctx.payload_upload(512, 320, 64, 64, 4, descs, pixels)
+        out = pl.expand(filt)
+        pl.free()
+        assert np.array_equal(out, O.expand(ref, filt, nthreads=8))
+    want, _ = O.analyze(img, 64, 64, O.METRIC_OKLAB_MAD, nthreads=8)
+    d = ctx.image_upload(img)
+    fast, _ = d.analyze(64, 64, N.METRIC_OKLAB_MAD, 0)
+    exact, _ = d.analyze(64, 64, N.METRIC_OKLAB_MAD, N.FLAG_EXACT_VALUES)
+    d.free()
+    assert np.array_equal(exact.view("<u4"), want.view("<u4"))
+    assert rel_close(fast, want, abs_=fast_tol(64 * 64))
+
+
+def test_random_shapes_seeded(ctx):
+    """Seeded sweep over image / block shapes (trailing blocks of every residue, tiny images, both channel counts)."""
+    rng = np.random.default_rng(2024)
+    for it in range(24):
+        c = int(rng.choice([3, 4]))
+        bw, bh = int(rng.choice([8, 16, 24, 32, 64, 96])), int(rng.choice([8, 16, 32, 48, 64, 80]))
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+        if c == 4 and rng.random() < 0.5:
+            w = max(4, w // 4 * 4)  # exercise the aligned RGBA fast paths too
+        filt = int(rng.choice(FILTERS))
+        factor = float(rng.choice([0.2, 1.0, 3.0]))
+        img = synth(w, h, c, seed=it)
+        ref = O.shrink(img, bw, bh, O.METRIC_OKLAB_MAD, factor, filt, nthreads=8)
+        descs, pixels, _ = gpu_shrink(ctx, img, bw, bh, N.METRIC_OKLAB_MAD, factor, filt)
+        assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"]), (it, w, h, c, bw, bh)
+        assert np.array_equal(pixels, ref.payload), (it, w, h, c, bw, bh, filt)
+        pl = ctx.payload_upload(w, h, bw, bh, c, descs, pixels)
+        out = pl.expand(filt)
+        pl.free()
+        assert np.array_equal(out, O.expand(ref, filt, nthreads=8)), (it, w, h, c, bw, bh, filt)
