@@ -133,6 +133,13 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
  * same threshold table as the device plan kernel. */
 pxz_status pxz_reduce_dims(float v0, float v1, uint32_t w, uint32_t h, uint32_t* out_w, uint32_t* out_h, float* stored);
 
+/* Host helper / diagnostic: the tap table the resample kernels apply for one axis, n_in -> n_out samples with
+ * `filter` (image 0.25.5 sample loops behind PixlzrBlock::resize, block.rs:282-290): first tap `left[o]`, tap count
+ * `count[o]` and normalised f32 weights `weights[o * max_taps + i]` per output o.  Returns the largest tap count
+ * (> max_taps means the arrays were too small and nothing was written) or a negative pxz_status. */
+int32_t pxz_resample_table(uint32_t n_in, uint32_t n_out, pxz_filter filter, uint32_t* left, uint32_t* count, float* weights,
+                           uint32_t max_taps);
+
 /* ---- payload ---------------------------------------------------------------------------- */
 pxz_status pxz_payload_info(pxz_ctx* ctx, const pxz_payload* p, uint32_t* w, uint32_t* h, uint32_t* bw, uint32_t* bh,
                             uint32_t* cols, uint32_t* rows, uint32_t* channels, uint64_t* bytes);

@@ -51,6 +51,7 @@ SYMBOLS = {
     "pxz_analyze": (_i, [_vp, _vp, _u32, _u32, _i, _u32, _vp, _vp]),
     "pxz_shrink": (_i, [_vp, _vp, _u32, _u32, _i, C.c_float, _i, _u32, _P(_vp)]),
     "pxz_reduce_dims": (_i, [C.c_float, C.c_float, _u32, _u32, _P(_u32), _P(_u32), _P(C.c_float)]),
+    "pxz_resample_table": (C.c_int32, [_u32, _u32, _i, _vp, _vp, _vp, _u32]),
     "pxz_payload_info": (_i, [_vp, _vp] + [_P(_u32)] * 7 + [_P(_u64)]),
     "pxz_payload_download": (_i, [_vp, _vp, _vp, _vp]),
     "pxz_payload_upload": (_i, [_vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _u64, _P(_vp)]),
@@ -319,6 +320,18 @@ def comm_unique_id() -> bytes:
     if st != OK:
         raise PixlzrError(st, "pxz_comm_unique_id (is libnccl.so.2 loadable?)")
     return bytes(buf)
+
+
+def resample_table(n_in: int, n_out: int, filt: int):
+    """(left, count, weights[n_out, taps]) of one resample axis as the kernels apply it."""
+    max_taps = max(1, n_in)
+    left = np.zeros(n_out, np.uint32)
+    count = np.zeros(n_out, np.uint32)
+    w = np.zeros((n_out, max_taps), np.float32)
+    rc = lib().pxz_resample_table(n_in, n_out, int(filt), ptr(left), ptr(count), ptr(w), max_taps)
+    if rc < 0 or rc > max_taps:
+        raise PixlzrError(rc if rc < 0 else E_ARG, "pxz_resample_table")
+    return left, count, w[:, :rc].copy()
 
 
 def device_count() -> int:

@@ -774,6 +774,24 @@ pxz_status pxz_reduce_dims(float v0, float v1, uint32_t w, uint32_t h, uint32_t*
   return PXZ_OK;
 }
 
+int32_t pxz_resample_table(uint32_t n_in, uint32_t n_out, pxz_filter filter, uint32_t* left, uint32_t* count, float* weights,
+                           uint32_t max_taps) {
+  if (!left || !count || !weights || n_in == 0 || n_out == 0) return PXZ_E_ARG;
+  std::vector<uint32_t> pool;
+  AxisTab t;
+  if (!build_axis_table(n_in, n_out, (int)filter, &pool, &t)) return PXZ_E_ARG;
+  if (t.stride > max_taps) return (int32_t)t.stride;
+  for (uint32_t o = 0; o < n_out; ++o) {
+    left[o] = pool[t.off + o];
+    count[o] = pool[t.off + n_out + o];
+    for (uint32_t i = 0; i < max_taps; ++i) {
+      uint32_t bits = i < t.stride ? pool[t.off + 2 * n_out + (size_t)o * t.stride + i] : 0u;
+      memcpy(&weights[(size_t)o * max_taps + i], &bits, 4);
+    }
+  }
+  return (int32_t)t.stride;
+}
+
 // ---- payload ------------------------------------------------------------------------------------------
 static pxz_status payload_bytes(pxz_ctx* ctx, const pxz_payload* cp, uint64_t* bytes) {
   pxz_payload* p = const_cast<pxz_payload*>(cp);

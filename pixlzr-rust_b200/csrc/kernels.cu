@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
         sl += o.l; sm += o.m; ss += o.s;
         asum = __dp4a(w4[k], 0x01000000u, asum);  // out-of-tile quads were loaded as zeros
       }
+#ifdef PXZ_MAD_SCHED_FENCE
+      asm volatile("" ::: "memory");  // keep the quads' LDS / MUFU bursts apart (MIO queue pressure)
+#endif
     }
     // the source quads are dead now: fetch the next tile while pass 2 and the reductions run
 #pragma unroll

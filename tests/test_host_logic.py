@@ -148,3 +148,15 @@ def test_pixlzrblock_accessors():
     assert px.shape == (10000, 4)
     same = b.resize(100, 100, P.FilterType.Lanczos3)  # same size: clone, no GPU involved
     assert same.data is not b.data and np.array_equal(same.data, b.data)
+
+
+@pytest.mark.parametrize("filt", range(5))
+def test_resample_tables_match_oracle_bit_for_bit(filt):
+    """The host-built tap tables the kernels apply are the image-crate weights of the oracle, bit for bit."""
+    pairs = [(64, 64), (64, 32), (64, 16), (64, 8), (64, 4), (64, 2), (64, 1), (56, 28), (56, 7), (17, 9), (17, 3), (32, 64),
+             (16, 64), (8, 64), (1, 64), (2, 56), (28, 56), (9, 17), (3, 2), (5, 200), (200, 3), (1, 1), (100, 10)]
+    for n_in, n_out in pairs:
+        l0, c0, w0 = O.axis_weights(n_in, n_out, filt)
+        l1, c1, w1 = N.resample_table(n_in, n_out, filt)
+        assert np.array_equal(l0, l1) and np.array_equal(c0, c1), (n_in, n_out)
+        assert w0.shape == w1.shape and np.array_equal(w0.view(np.uint32), w1.view(np.uint32)), (n_in, n_out)
