@@ -1504,6 +1504,18 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgb
           *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + (size_t)x * 4) = cur[j];
         }
       }
+    } else if (sw == 1 && sh == 1) {
+      // a 1x1 block: every output has exactly one tap whose normalised weight is w / w = 1.0 in both passes, so the
+      // tile is the source pixel replicated — for every filter.  16-byte stores, no staging, no barrier.
+      const uint32_t p = __ldg(reinterpret_cast<const uint32_t*>(payload + d.offset));
+      const uint4 v = make_uint4(p, p, p, p);
+      const uint32_t qpr = (dw + 3) >> 2;
+      for (uint32_t q = tid; q < qpr * dh; q += kThreads) {
+        const uint32_t y = q / qpr, x = (q - y * qpr) << 2;
+        uint8_t* o = dst + (size_t)y * pitch + (size_t)x * 4;
+        if (x + 4 <= dw) *reinterpret_cast<uint4*>(o) = v;
+        else for (uint32_t k = x; k < dw; ++k) reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch)[k] = p;
+      }
     } else {
       const AxisTab tx = sm.atab[ti & 0xFFFFu], ty = sm.atab[ti >> 16];
       const bool yb = y_blocked(dh), xb = x_blocked(dw, dh);
