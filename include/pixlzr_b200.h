@@ -156,6 +156,15 @@ void pxz_payload_free(pxz_payload* p);
 pxz_status pxz_expand(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, uint8_t* host_out, size_t host_pitch);
 pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, pxz_image* out);
 
+/* ---- quadtree processing: tree::process_custom (src/process/tree.rs:23-83) with before = |x-avg|, after = identity.
+ * Blocks whose value is below |threshold| are reduced and re-expanded (filter_down / filter_up); the others are split
+ * again with halved block size until the size reaches max(min, 4), where they stay unchanged.  A negative threshold
+ * inverts the test at the top level only, as the reference does (the recursion receives |threshold|).  `out` has the
+ * geometry of `img` (the reference pastes into an RGBA8 canvas: add alpha 255 for RGB inputs).  Block sizes must stay
+ * exact when halved (divisible by 2^(levels-1)), else PXZ_E_UNSUPPORTED. */
+pxz_status pxz_tree_process(pxz_ctx* ctx, const pxz_image* img, float threshold, uint32_t bw, uint32_t bh, uint32_t min_bw,
+                            uint32_t min_bh, pxz_filter filter_down, pxz_filter filter_up, pxz_image* out);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------
  * Only PXZ_FLAG_NORMALISE_GLOBAL needs communication: one all-reduce of {min, -max} per
  * metric component over NCCL on the context's stream.  Rank 0 creates the id and shares its

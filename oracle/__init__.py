@@ -71,6 +71,8 @@ def lib():
         L.pxo_shrink.restype = C.c_int64
         L.pxo_expand.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.pxo_tree_process.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.pxo_qoi_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]
         L.pxo_qoi_encode.restype = C.c_int64
         L.pxo_qoi_decode.argtypes = [C.c_void_p, C.c_size_t, u32p, u32p, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
@@ -212,6 +214,18 @@ def expand(s: Shrunk, filter_up: int, nthreads: int = 1) -> np.ndarray:
                           s.channels, filter_up, _ptr(out), out.strides[0], nthreads)
     if rc != 0:
         raise ValueError("pxo_expand failed")
+    return out
+
+
+def tree_process(img: np.ndarray, threshold: float, bw: int, bh: int, min_bw: int = 4, min_bh: int = 4,
+                 filter_down: int = LANCZOS3, filter_up: int = NEAREST) -> np.ndarray:
+    """tree::process_custom (process/tree.rs:23-83); same channel count as the input."""
+    w, h, c, pitch = _check_img(img)
+    out = np.zeros((h, w, c), np.uint8)
+    rc = lib().pxo_tree_process(_ptr(img), w, h, c, pitch, threshold, bw, bh, min_bw, min_bh, filter_down, filter_up,
+                                _ptr(out), out.strides[0])
+    if rc != 0:
+        raise ValueError("pxo_tree_process failed")
     return out
 
 

@@ -644,6 +644,50 @@ int pxo_expand(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, 
   return err ? -1 : 0;
 }
 
+/* process/tree.rs:23-83, literally: `img` is the (sub-)image of this recursion level, tightly packed. */
+static std::vector<uint8_t> tree_rec(const std::vector<uint8_t>& img, uint32_t w, uint32_t h, int C, float threshold,
+                                     uint32_t bw, uint32_t bh, uint32_t min_bw, uint32_t min_bh, int fdown, int fup) {
+  const uint32_t mbw = std::max(min_bw, 4u), mbh = std::max(min_bh, 4u); /* :33-34 */
+  if (bw <= mbw || bh <= mbh) return img;                                 /* :35-37 image.clone() */
+  const bool is_positive = threshold >= 0.0f;                             /* :38 */
+  const float thr = fabsf(threshold);                                     /* :39 */
+  std::vector<uint8_t> out((size_t)w * h * C, 0);
+  const uint32_t cols = ceil_div_f64(w, bw), rows = ceil_div_f64(h, bh);
+  for (uint32_t by = 0; by < rows; ++by) {
+    for (uint32_t bx = 0; bx < cols; ++bx) {
+      const uint32_t x0 = bx * bw, y0 = by * bh;
+      const uint32_t w0 = std::min(bw, w - x0), h0 = std::min(bh, h - y0);
+      std::vector<uint8_t> blk((size_t)w0 * h0 * C);
+      for (uint32_t y = 0; y < h0; ++y) memcpy(&blk[(size_t)y * w0 * C], &img[((size_t)(y0 + y) * w + x0) * C], (size_t)w0 * C);
+      const float value = block_mad(blk.data(), (size_t)w0 * C, w0, h0, C); /* after = identity, :97 */
+      std::vector<uint8_t> res;
+      if ((value >= thr) ^ is_positive) { /* :56 */
+        uint32_t ow, oh;
+        pxo_reduce_dims(value, value, w0, h0, &ow, &oh, nullptr);
+        std::vector<uint8_t> small((size_t)ow * oh * C);
+        resize_image_rs(blk.data(), w0, h0, C, small.data(), ow, oh, fdown);
+        res.resize((size_t)w0 * h0 * C);
+        resize_image_rs(small.data(), ow, oh, C, res.data(), w0, h0, fup);
+      } else {
+        /* :68-76 — note that the recursion receives the ABSOLUTE threshold */
+        res = tree_rec(blk, w0, h0, C, thr, bw >> 1, bh >> 1, mbw, mbh, fdown, fup);
+      }
+      for (uint32_t y = 0; y < h0; ++y) memcpy(&out[((size_t)(y0 + y) * w + x0) * C], &res[(size_t)y * w0 * C], (size_t)w0 * C);
+    }
+  }
+  return out;
+}
+
+int pxo_tree_process(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pitch, float threshold, uint32_t bw, uint32_t bh,
+                     uint32_t min_bw, uint32_t min_bh, int filter_down, int filter_up, uint8_t* out, size_t out_pitch) {
+  if (!img || !out || (C != 3 && C != 4) || w == 0 || h == 0 || bw == 0 || bh == 0) return -1;
+  std::vector<uint8_t> tight((size_t)w * h * C);
+  for (uint32_t y = 0; y < h; ++y) memcpy(&tight[(size_t)y * w * C], img + (size_t)y * pitch, (size_t)w * C);
+  std::vector<uint8_t> res = tree_rec(tight, w, h, C, threshold, bw, bh, min_bw, min_bh, filter_down, filter_up);
+  for (uint32_t y = 0; y < h; ++y) memcpy(out + (size_t)y * out_pitch, &res[(size_t)y * w * C], (size_t)w * C);
+  return 0;
+}
+
 int64_t pxo_qoi_encode(const uint8_t* px, uint32_t w, uint32_t h, int channels, uint8_t* out, size_t cap) {
   return qoi_encode(px, w, h, channels, out, cap);
 }

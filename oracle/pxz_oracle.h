@@ -78,6 +78,14 @@ int pxo_expand(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, 
                uint32_t bw, uint32_t bh, int channels, int filter_up, uint8_t* out,
                size_t out_pitch, int nthreads);
 
+/* tree::process_custom (process/tree.rs:23-83) with before = |x-avg|, after = identity: quadtree of blocks, a block
+   whose value is below the threshold is reduced + re-expanded, the others are split again with halved block size
+   until the size reaches max(min, 4).  Output has the input's channel count (the reference pastes into an RGBA8
+   canvas: alpha 255 is added by the caller for RGB inputs).  parity unpinned: no reference fixture exercises it. */
+int pxo_tree_process(const uint8_t* img, uint32_t w, uint32_t h, int channels, size_t pitch, float threshold,
+                     uint32_t bw, uint32_t bh, uint32_t min_bw, uint32_t min_bh, int filter_down, int filter_up,
+                     uint8_t* out, size_t out_pitch);
+
 /* ---- container (encoding/mod.rs:40-242) + QOI (qoi 0.4.1) --------------------------- */
 /* returns bytes written (or needed if out == NULL / cap too small -> negative of needed) */
 int64_t pxo_qoi_encode(const uint8_t* px, uint32_t w, uint32_t h, int channels, uint8_t* out,

@@ -17,6 +17,8 @@ from .api import (  # noqa: F401
     process,
     process_custom,
     reduce_image_section,
+    tree_process,
+    tree_process_custom,
 )
 from . import _native as native  # noqa: F401
 from . import sharding  # noqa: F401

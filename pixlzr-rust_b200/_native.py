@@ -58,6 +58,7 @@ SYMBOLS = {
     "pxz_payload_free": (None, [_vp]),
     "pxz_expand": (_i, [_vp, _vp, _i, _vp, _sz]),
     "pxz_expand_to_image": (_i, [_vp, _vp, _i, _vp]),
+    "pxz_tree_process": (_i, [_vp, _vp, C.c_float, _u32, _u32, _u32, _u32, _i, _i, _vp]),
     "pxz_comm_unique_id": (_i, [_vp]),
     "pxz_comm_init": (_i, [_vp, _i, _i, _vp]),
     "pxz_comm_destroy": (None, [_vp]),
@@ -230,6 +231,11 @@ class Image:
         self.ctx.check(lib().pxz_shrink(self.ctx.handle, self._h, bw, bh, metric, factor, int(filter_down), flags,
                                         C.byref(h)))
         return Payload(self.ctx, h)
+
+    def tree_process(self, threshold: float, bw: int, bh: int, min_bw: int, min_bh: int, filter_down: int, filter_up: int,
+                     out: "Image"):
+        self.ctx.check(lib().pxz_tree_process(self.ctx.handle, self._h, threshold, bw, bh, min_bw, min_bh, int(filter_down),
+                                              int(filter_up), out.handle))
 
     def free(self):
         if self._h:

@@ -349,6 +349,34 @@ def process(image: np.ndarray, block_size: int, ctx: Optional[N.Context] = None)
     return process_custom(image, block_size, block_size, FilterType.Lanczos3, FilterType.Nearest, ctx)
 
 
+def tree_process_custom(image: np.ndarray, threshold: float, block_size: Tuple[int, int], min_block_size: Tuple[int, int],
+                        filters: Tuple[FilterType, FilterType], ctx: Optional[N.Context] = None) -> np.ndarray:
+    """tree::process_custom (process/tree.rs:23-83) with the closures tree::process uses (|x-avg|, identity).
+    Returns RGBA8 like the reference's canvas, except when the block size is already at the minimum: then the input
+    comes back unchanged (tree.rs:35-37: `image.clone()`)."""
+    image = _check_image(image)
+    bw, bh = block_size
+    if bw <= max(min_block_size[0], 4) or bh <= max(min_block_size[1], 4):
+        return image.copy()
+    ctx = ctx or default_context()
+    d = ctx.image_upload(image)
+    out = ctx.image_alloc(image.shape[1], image.shape[0], image.shape[2])
+    try:
+        d.tree_process(threshold, bw, bh, min_block_size[0], min_block_size[1], int(filters[0]), int(filters[1]), out)
+        res = out.download()
+    finally:
+        out.free()
+        d.free()
+    if res.shape[2] == 3:
+        res = np.concatenate([res, np.full(res.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    return res
+
+
+def tree_process(image: np.ndarray, block_size: int, threshold: float, ctx: Optional[N.Context] = None) -> np.ndarray:
+    """tree::process (process/tree.rs:89-109): Lanczos3 down, Nearest up, minimum block 4."""
+    return tree_process_custom(image, threshold, (block_size, block_size), (4, 4), (FilterType.Lanczos3, FilterType.Nearest), ctx)
+
+
 def parse_shrinking_factor(s: str) -> float:
     """src/bin/main.rs:47-68: [+|-][1/]D[.D]; unparsable numbers fall back to 1.0."""
     pos, invert, negative = 0, False, False

@@ -683,6 +683,7 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   vm.factor = factor;
   vm.mode = (metric == PXZ_METRIC_SOBEL_DIR) ? 2 : ((flags & PXZ_FLAG_AFTER_IDENTITY) ? 1 : 0);
   vm.normalise = normalise ? 1 : 0;
+  vm.extra_thr = NAN;
 
   // with global normalisation every value depends on the exact min and max, so the Oklab path
   // runs in reference order for all blocks
@@ -723,8 +724,8 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   cudaError_t e;
   {
     ProfScope prof(ctx, K_PLAN);
-    e = launch_plan(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, g, vm, ctx->d_minmax, ctx->thr, p->d_descs,
-                    p->d_tabidx, p->d_total, ctx->d_scan, ctx->stream, &ctx->launches);
+    e = launch_plan(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, g, vm, ctx->d_minmax, ctx->thr, nullptr,
+                    p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, ctx->stream, &ctx->launches);
   }
   if (e != cudaSuccess) {
     payload_release(p);
@@ -921,6 +922,80 @@ pxz_status pxz_expand(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, 
   st = pxz_expand_to_image(ctx, p, filter_up, im);
   if (st == PXZ_OK) st = pxz_image_download(ctx, im, host_out, host_pitch);
   pxz_image_free(im);
+  return st;
+}
+
+// ---- quadtree processing (process/tree.rs:23-109) ---------------------------------------------------------
+pxz_status pxz_tree_process(pxz_ctx* ctx, const pxz_image* img, float threshold, uint32_t bw, uint32_t bh, uint32_t min_bw,
+                            uint32_t min_bh, pxz_filter filter_down, pxz_filter filter_up, pxz_image* out) {
+  if (!ctx || !img || !out) return PXZ_E_ARG;
+  cudaSetDevice(ctx->device);
+  if ((int)filter_down < 0 || (int)filter_down > 4 || (int)filter_up < 0 || (int)filter_up > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
+  if (out->w != img->w || out->h != img->h || out->c != img->c) return fail(ctx, PXZ_E_ARG, "output image geometry mismatch");
+  if (bw == 0 || bh == 0) return fail(ctx, PXZ_E_ARG, "block size must be >= 1");
+  // unchanged pixels (blocks that reach the minimum size, tree.rs:35-37) come straight from the source
+  PXZ_CUDA(ctx, cudaMemcpy2DAsync(out->d, out->pitch, img->d, img->pitch, (size_t)img->w * img->c, img->h, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+  const uint32_t mbw = std::max(min_bw, 4u), mbh = std::max(min_bh, 4u);  // :33-34
+  int levels = 0;
+  while ((bw >> levels) > mbw && (bh >> levels) > mbh) ++levels;
+  if (levels == 0) return PXZ_OK;  // :35-37: image.clone()
+  // the reference splits every block relative to its own origin; the levels form global grids only when the halved
+  // sizes stay exact, which is what the accelerated path covers
+  if ((bw & ((1u << (levels - 1)) - 1)) || (bh & ((1u << (levels - 1)) - 1)))
+    return fail(ctx, PXZ_E_UNSUPPORTED, "tree processing needs block sizes divisible by 2^(levels-1)");
+  const bool positive = threshold >= 0.0f;  // :38
+  const float thr = fabsf(threshold);       // :39
+
+  uint8_t* d_leaf = nullptr;
+  uint8_t* d_rec[2] = {nullptr, nullptr};
+  Geom gl;
+  pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw >> (levels - 1), bh >> (levels - 1), &gl);
+  if (st != PXZ_OK) return st;
+  const size_t max_blocks = (size_t)gl.cols * gl.rows;
+  if ((st = dev_alloc(ctx, (void**)&d_leaf, max_blocks)) != PXZ_OK) return st;
+  if ((st = dev_alloc(ctx, (void**)&d_rec[0], max_blocks)) != PXZ_OK || (st = dev_alloc(ctx, (void**)&d_rec[1], max_blocks)) != PXZ_OK) {
+    dev_free(ctx, d_leaf); dev_free(ctx, d_rec[0]); dev_free(ctx, d_rec[1]);
+    return st;
+  }
+  uint32_t parent_cols = 0;
+  for (int lv = 0; lv < levels && st == PXZ_OK; ++lv) {
+    Geom g;
+    st = make_geom(ctx, img->w, img->h, img->c, bw >> lv, bh >> lv, &g);
+    if (st != PXZ_OK) break;
+    ValueMap vm;
+    vm.factor = 1.0f; vm.mode = 1; vm.normalise = 0;  // after = identity (tree.rs:97)
+    vm.extra_thr = thr;
+    st = run_analysis(ctx, img, g, PXZ_METRIC_OKLAB_MAD, false, &vm);
+    if (st != PXZ_OK) break;
+    cudaError_t e = launch_tree_mask(ctx->d_vx, g, lv == 0 ? nullptr : d_rec[(lv - 1) & 1], parent_cols, thr,
+                                     (lv == 0 ? positive : true) ? 1 : 0,  // the recursion receives |threshold| (:70)
+                                     d_leaf, d_rec[lv & 1], ctx->stream, &ctx->launches);
+    if (e != cudaSuccess) { st = fail(ctx, PXZ_E_CUDA, std::string("tree mask: ") + cudaGetErrorString(e)); break; }
+    parent_cols = g.cols;
+    pxz_payload* p = nullptr;
+    st = payload_new(ctx, g, (uint64_t)g.W * g.H * g.C, &p);
+    if (st != PXZ_OK) break;
+    p->spec = spec_for_geom(g);
+    auto pad8 = [](uint32_t v) { return (v + 7u) & ~7u; };
+    p->max_small_px = g.bw * g.bh;
+    p->max_small_dim = std::max(g.bw, g.bh);
+    p->max_tmp_down = ((g.bh + 1) / 2) * pad8(g.bw);
+    p->max_tmp_up = g.bh * pad8((g.bw + 1) / 2);
+    vm.extra_thr = NAN;
+    e = launch_plan(ctx->d_vx, nullptr, g, vm, ctx->d_minmax, ctx->thr, d_leaf, p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan,
+                    ctx->stream, &ctx->launches);
+    if (e != cudaSuccess) st = fail(ctx, PXZ_E_CUDA, std::string("plan: ") + cudaGetErrorString(e));
+    TabSet ts;
+    if (st == PXZ_OK) st = get_tabset(ctx, *p->spec, (int)filter_down, 0, &ts);
+    if (st == PXZ_OK) st = run_resample(ctx, 0, img->d, img->pitch, p, ts, g.bw * g.bh, std::max(g.bw, g.bh), p->max_tmp_down);
+    if (st == PXZ_OK) st = get_tabset(ctx, *p->spec, (int)filter_up, 1, &ts);
+    if (st == PXZ_OK) st = run_resample(ctx, 1, out->d, out->pitch, p, ts, p->max_small_px, p->max_small_dim, p->max_tmp_up);
+    payload_release(p);
+  }
+  dev_free(ctx, d_leaf);
+  dev_free(ctx, d_rec[0]);
+  dev_free(ctx, d_rec[1]);
   return st;
 }
 

@@ -605,6 +605,7 @@ __device__ __forceinline__ bool in_guard_band(float raw, bool opaque, int C, con
   for (int k = 0; k < kmax; ++k) {  // thr[k] separates level k+1 (below) from k (at or above)
     if (fabsf(pv - thr.thr[k]) <= tol) return true;
   }
+  if (vm.extra_thr == vm.extra_thr && fabsf(v0 - vm.extra_thr) <= tol) return true;  // quadtree split decision
   // the kink of parse_value at v = -1 (1 + v = 0) maps to 1 px on both sides
   return false;
 }
@@ -833,7 +834,8 @@ struct ScanState {
 
 __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx, const float* __restrict__ vy, Geom g,
                                                    ValueMap vm, const float* __restrict__ minmax, LevelThresholds thr,
-                                                   pxz_block_desc* __restrict__ descs, uint32_t* __restrict__ tabidx,
+                                                   const uint8_t* __restrict__ mask, pxz_block_desc* __restrict__ descs,
+                                                   uint32_t* __restrict__ tabidx,
                                                    unsigned long long* __restrict__ total, ScanState* st) {
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_warp[kThreads / 32];
@@ -869,6 +871,7 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
       const uint32_t ix = (0u * 2u + cx) * kLevelsPerClass + min(k0, (uint32_t)kMaxLevel);
       const uint32_t iy = (1u * 2u + cy) * kLevelsPerClass + min(k1, (uint32_t)kMaxLevel);
       tix[j] = ix | (iy << 16);
+      if (mask != nullptr && mask[b] == 0) { dw[j] = 0; dh[j] = 0; }  // not a leaf of this quadtree level
       sz[j] = (unsigned long long)dw[j] * dh[j] * g.C;
       tsum += sz[j];
     }
@@ -979,6 +982,7 @@ __global__ void __launch_bounds__(kThreads) k_resample(int direction, uint8_t* _
   for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const Tile t = tile_of(g, b);
     const pxz_block_desc d = descs[b];
+    if (d.w == 0 || d.h == 0) continue;  // masked out (quadtree levels)
     uint8_t* tile_ptr = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
     uint8_t* blk_ptr = payload + d.offset;
     const uint8_t* src;
@@ -1352,7 +1356,7 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_shrink_rgb
   auto stage_tables = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti, uint32_t buf) {
     if (b < nblocks) {
       const Tile t = tile_of(g, b);
-      if (!(t.tw == d.w && t.th == d.h)) {
+      if (d.w != 0 && d.h != 0 && !(t.tw == d.w && t.th == d.h)) {
         uint32_t* dst = sm.tab + buf * 2 * kFastMaxTabWords;
         stage_axis_async(sm.atab[ti >> 16], y_blocked(d.h), pool, dst);
         stage_axis_async(sm.atab[ti & 0xFFFFu], x_blocked(d.w, d.h), pool, dst + kFastMaxTabWords);
@@ -1388,7 +1392,9 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_shrink_rgb
 
     uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset);
     const uint32_t sw = t.tw, sh = t.th, dw = d.w, dh = d.h;
-    if (sw == dw && sh == dh) {
+    if (dw == 0 || dh == 0) {
+      // masked out (quadtree levels): nothing to write
+    } else if (sw == dw && sh == dh) {
       // block.rs:279-281: clone.  The tile is contiguous in the payload (4-byte aligned only).
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1457,7 +1463,7 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgb
   auto stage_tables = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti, uint32_t buf) {
     if (b < nblocks) {
       const Tile t = tile_of(g, b);
-      if (!(t.tw == d.w && t.th == d.h)) {
+      if (d.w != 0 && d.h != 0 && !(t.tw == d.w && t.th == d.h)) {
         uint32_t* dst = sm.tab + buf * 2 * kFastMaxTabWords;
         stage_axis_async(sm.atab[ti >> 16], y_blocked(t.th), pool, dst);
         stage_axis_async(sm.atab[ti & 0xFFFFu], x_blocked(t.tw, t.th), pool, dst + kFastMaxTabWords);
@@ -1494,8 +1500,10 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgb
     uint8_t* dst = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
     const uint32_t sw = d.w, sh = d.h, dw = t.tw, dh = t.th;
     const bool pow2 = (sw & (sw - 1)) == 0;
-    const uint32_t sshift = 31 - __clz(sw);
-    if (sw == dw && sh == dh) {
+    const uint32_t sshift = 31 - __clz(sw | 1u);
+    if (sw == 0 || sh == 0) {
+      // masked out (quadtree levels): the tile keeps what the output image already holds
+    } else if (sw == dw && sh == dh) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const uint32_t i = tid + j * kThreads;
@@ -1552,6 +1560,19 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgb
     dcur = dnxt; ticur = tinxt;
     dnxt = dnn; tinxt = tinn;
   }
+}
+
+// quadtree level decision (process/tree.rs:47-77)
+__global__ void __launch_bounds__(kThreads) k_tree_mask(const float* __restrict__ vx, Geom g, const uint8_t* __restrict__ parent_recurse,
+                                                        uint32_t parent_cols, float thr, int positive, uint8_t* __restrict__ leaf,
+                                                        uint8_t* __restrict__ recurse) {
+  const uint32_t b = blockIdx.x * kThreads + threadIdx.x;
+  if (b >= g.cols * g.rows) return;
+  const uint32_t by = b / g.cols, bx = b - by * g.cols;
+  const bool active = parent_recurse == nullptr || parent_recurse[(by >> 1) * parent_cols + (bx >> 1)] != 0;
+  const bool reduce = (vx[b] >= thr) != (positive != 0);  // (value >= threshold) ^ is_positive; NaN >= thr is false
+  leaf[b] = (uint8_t)(active && reduce);
+  recurse[b] = (uint8_t)(active && !reduce);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1656,6 +1677,14 @@ cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g
   return cudaGetLastError();
 }
 
+cudaError_t launch_tree_mask(const float* vx, const Geom& g, const uint8_t* parent_recurse, uint32_t parent_cols, float thr,
+                             int positive, uint8_t* leaf, uint8_t* recurse, cudaStream_t s, uint64_t* launches) {
+  const uint32_t n = g.cols * g.rows;
+  ++*launches;
+  k_tree_mask<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(vx, g, parent_recurse, parent_cols, thr, positive, leaf, recurse);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* minmax4, cudaStream_t s, uint64_t* launches) {
   ++*launches;
   k_minmax<<<1, 1024, 0, s>>>(vx, vy, n, minmax4);
@@ -1668,14 +1697,14 @@ size_t plan_scan_state_bytes(uint32_t nblocks) {
 }
 
 cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
-                        const LevelThresholds& thr, pxz_block_desc* descs, uint32_t* tabidx, uint64_t* total_bytes,
-                        void* scan_state, cudaStream_t s, uint64_t* launches) {
+                        const LevelThresholds& thr, const uint8_t* mask, pxz_block_desc* descs, uint32_t* tabidx,
+                        uint64_t* total_bytes, void* scan_state, cudaStream_t s, uint64_t* launches) {
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t tiles = (nblocks + kPlanTile - 1) / kPlanTile;
   cudaError_t e = cudaMemsetAsync(scan_state, 0, plan_scan_state_bytes(nblocks), s);
   if (e != cudaSuccess) return e;
   ++*launches;
-  k_plan<<<tiles, kThreads, 0, s>>>(vx, vy, g, vm, minmax, thr, descs, tabidx,
+  k_plan<<<tiles, kThreads, 0, s>>>(vx, vy, g, vm, minmax, thr, mask, descs, tabidx,
                                     reinterpret_cast<unsigned long long*>(total_bytes),
                                     reinterpret_cast<ScanState*>(scan_state));
   return cudaGetLastError();

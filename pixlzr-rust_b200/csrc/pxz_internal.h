@@ -39,6 +39,7 @@ struct ValueMap {
   float factor;
   int mode;       // 0: MAD * factor * 10 | 1: MAD identity | 2: Sobel (hz,vr) * factor
   int normalise;  // 0/1; minmax = {min_x, -max_x, min_y, -max_y} on device
+  float extra_thr;  // tree processing: an additional decision threshold on the value (NaN = none), process/tree.rs:56
 };
 
 struct LevelThresholds {
@@ -65,9 +66,14 @@ cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g
                                  int sm_count, uint64_t* launches);
 cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* minmax4, cudaStream_t s,
                           uint64_t* launches);
+// mask (may be NULL): blocks with mask[b] == 0 get an empty descriptor (w = h = 0) and are skipped by the resample
 cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
-                        const LevelThresholds& thr, pxz_block_desc* descs, uint32_t* tabidx, uint64_t* total_bytes,
-                        void* scan_state, cudaStream_t s, uint64_t* launches);
+                        const LevelThresholds& thr, const uint8_t* mask, pxz_block_desc* descs, uint32_t* tabidx,
+                        uint64_t* total_bytes, void* scan_state, cudaStream_t s, uint64_t* launches);
+// quadtree level (process/tree.rs:47-77): leaf[b] = active && ((v >= thr) ^ positive), recurse[b] = active && !that,
+// where active = recurse flag of the parent block one level up (NULL parent = every block is active)
+cudaError_t launch_tree_mask(const float* vx, const Geom& g, const uint8_t* parent_recurse, uint32_t parent_cols, float thr,
+                             int positive, uint8_t* leaf, uint8_t* recurse, cudaStream_t s, uint64_t* launches);
 size_t plan_scan_state_bytes(uint32_t nblocks);
 // direction 0: image tiles -> payload (shrink); 1: payload -> image tiles (expand)
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,

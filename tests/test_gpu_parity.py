@@ -430,3 +430,33 @@ def test_random_shapes_seeded(ctx):
         out = pl.expand(filt)
         pl.free()
         assert np.array_equal(out, O.expand(ref, filt, nthreads=8)), (it, w, h, c, bw, bh, filt)
+
+
+# ---------------------------------------------------------------------------------------------
+# quadtree processing (process/tree.rs) — SURVEY 8f N3
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,bs,thr", [("Big-Ruscher.png", 128, 0.02), ("Big-Ruscher.png", 128, 0.005), ("Big-Ruscher.png", 64, -0.01),
+                                         ("base.png", 128, 0.03), ("base.png", 32, 0.01), ("image.png", 256, 0.004)])
+def test_tree_process(name, bs, thr):
+    img = load_png(name)
+    want = O.tree_process(img, thr, bs, bs)
+    got = P.tree_process(img, bs, thr)
+    assert got.shape == img.shape[:2] + (4,)
+    if img.shape[2] == 3:
+        assert (got[..., 3] == 255).all()
+        got = got[..., :3]
+    assert np.array_equal(got, want)
+    assert not np.array_equal(got, img)  # something was reduced
+
+
+def test_tree_process_edge_cases(ctx):
+    img = synth(300, 200, 4, seed=5)
+    # block size already at the minimum: the input comes back unchanged (tree.rs:35-37)
+    assert np.array_equal(P.tree_process(img, 4, 0.01), img)
+    # custom filters / minimum block size
+    want = O.tree_process(img, 0.02, 64, 32, 8, 8, O.CATMULLROM, O.TRIANGLE)
+    got = P.tree_process_custom(img, 0.02, (64, 32), (8, 8), (P.FilterType.CatmullRom, P.FilterType.Triangle))
+    assert np.array_equal(got, want)
+    # halved sizes that stop being exact are refused, not approximated
+    with pytest.raises(N.PixlzrError):
+        P.tree_process(img, 100, 0.01)
