@@ -1153,80 +1153,148 @@ __device__ __forceinline__ uint32_t to_u8_bits(float t) {
 }
 __device__ __forceinline__ uint32_t to_u8_fast(float t) { return to_u8_bits(t) & 0xFFu; }
 
+// ---- packed f32x2 arithmetic (sm_100a FFMA2: two f32 lanes per issue slot) ---------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float lo2(u64 v) { float a, b; unpk2(v, a, b); return a; }
+__device__ __forceinline__ float hi2(u64 v) { float a, b; unpk2(v, a, b); return b; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// 1.0 and -0.0 as *run-time* values (kernel arguments).  The reference rounds the product and the sum of a tap
+// separately (t += p * w without contraction); written as fma(p, w, -0) and fma(product, 1, t) those are two
+// exactly-rounded operations in the packed pipe, and because ptxas cannot know the two constants it can neither fold
+// them away nor contract the pair into one FFMA2 (it does both when they are literals, even across asm volatile).
+struct TapK {
+  u64 one2, nz2;
+  float one, nz;
+};
+__device__ __forceinline__ TapK make_tapk(float rt_one, float rt_negzero) {
+  TapK k;
+  k.one = rt_one; k.nz = rt_negzero;
+  k.one2 = pk2(rt_one, rt_one);
+  k.nz2 = pk2(rt_negzero, rt_negzero);
+  return k;
+}
+
 // MODE bit 0: the alpha channel is computed; bit 1: fused multiply-add (PXZ "fast resample": not bit-exact,
 // pixels stay within +-1 LSB of the reference order)
 template <int MODE>
-__device__ __forceinline__ void mac(float4& acc, const float4& p, float w) {
-  if (MODE & 2) {
-    acc.x = fmaf(p.x, w, acc.x);
-    acc.y = fmaf(p.y, w, acc.y);
-    acc.z = fmaf(p.z, w, acc.z);
-    if (MODE & 1) acc.w = fmaf(p.w, w, acc.w);
-  } else {
-    acc.x = __fadd_rn(acc.x, __fmul_rn(p.x, w));
-    acc.y = __fadd_rn(acc.y, __fmul_rn(p.y, w));
-    acc.z = __fadd_rn(acc.z, __fmul_rn(p.z, w));
-    if (MODE & 1) acc.w = __fadd_rn(acc.w, __fmul_rn(p.w, w));
-  }
+__device__ __forceinline__ u64 mac2(u64 acc, u64 p, u64 w, const TapK& k) {
+  if (MODE & 2) return fma2(p, w, acc);
+  return fma2(fma2(p, w, k.nz2), k.one2, acc);
 }
 template <int MODE>
-__device__ __forceinline__ uint32_t pack_px(const float4& a) {
-  // byte 0 of each rounded channel, gathered with two byte permutes
-  const uint32_t rg = __byte_perm(to_u8_bits(a.x), to_u8_bits(a.y), 0x0040);                              // {r, g, r, r}
-  const uint32_t ba = __byte_perm(to_u8_bits(a.z), (MODE & 1) ? to_u8_bits(a.w) : 0x000000FFu, 0x0040);  // {b, a, b, b}
-  return __byte_perm(rg, ba, 0x5410);                                                                    // {r, g, b, a}
+__device__ __forceinline__ float mac1(float acc, float p, float w) {
+  if (MODE & 2) return fmaf(p, w, acc);
+  return __fadd_rn(acc, __fmul_rn(p, w));
+}
+__device__ __forceinline__ uint32_t pack_bits(uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+  // byte 0 of each rounded channel, gathered with byte permutes
+  return __byte_perm(__byte_perm(r, g, 0x0040), __byte_perm(b, a, 0x0040), 0x5410);
 }
 
-// One staged axis table: either the blocked form (outputs in groups of 4) or the per-output form.
-struct StagedTab {
-  bool blocked;
-  uint32_t n_out, stride, nb;
-  const uint32_t* base;  // shared memory
-  // blocked: w4 at base, then lo | rows | first
-  __device__ __forceinline__ const float4* w4() const { return reinterpret_cast<const float4*>(base); }
-  __device__ __forceinline__ const uint32_t* blo(uint32_t rows_total) const { return base + 4 * rows_total; }
+// Four outputs that share one walk over the source samples: per channel the accumulators of outputs (0,1) and (2,3)
+// sit in one f32x2 register pair each, the sample is broadcast and the weights of the four outputs arrive as one
+// 16-byte row — 2 FFMA2 issue slots per channel and sample in fused mode, 4 in exact mode (8 scalar before).
+template <int MODE>
+struct Acc4 {
+  static constexpr int NC = (MODE & 1) ? 4 : 3;
+  u64 a01[NC], a23[NC];
+  __device__ __forceinline__ Acc4() {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a01[c] = a23[c] = 0ull;
+  }
+  __device__ __forceinline__ void step(const float4& p, const ulonglong2& w, const TapK& k) {
+    const float pc[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const u64 pp = pk2(pc[c], pc[c]);
+      a01[c] = mac2<MODE>(a01[c], pp, w.x, k);
+      a23[c] = mac2<MODE>(a23[c], pp, w.y, k);
+    }
+  }
+  __device__ __forceinline__ float4 out(int j) const {  // j is a compile-time constant at every call site
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const u64 q = (j < 2) ? a01[c] : a23[c];
+      v[c] = (j & 1) ? hi2(q) : lo2(q);
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+  }
 };
+
+// One output: channels paired as (r, g) and (b, a); without alpha the blue channel stays scalar.
+template <int MODE>
+struct Acc1 {
+  u64 rg, ba;
+  float b;
+  __device__ __forceinline__ Acc1() : rg(0ull), ba(0ull), b(0.f) {}
+  __device__ __forceinline__ void step(u64 prg, u64 pba, float pb, float w, const TapK& k) {
+    const u64 ww = pk2(w, w);
+    rg = mac2<MODE>(rg, prg, ww, k);
+    if (MODE & 1) ba = mac2<MODE>(ba, pba, ww, k);
+    else b = mac1<MODE>(b, pb, w);
+  }
+  __device__ __forceinline__ float4 out() const {
+    float r, g, bb, a;
+    unpk2(rg, r, g);
+    if (MODE & 1) unpk2(ba, bb, a);
+    else { bb = b; a = 0.f; }
+    return make_float4(r, g, bb, a);
+  }
+};
+
+template <int MODE>
+__device__ __forceinline__ uint32_t pack_px(const float4& a) {
+  return pack_bits(to_u8_bits(a.x), to_u8_bits(a.y), to_u8_bits(a.z), (MODE & 1) ? to_u8_bits(a.w) : 0x000000FFu);
+}
 
 // ---- vertical_sample: src [sh][64] -> tmp [dh][ts] ---------------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void vertical_blocked(const uint32_t* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
-                                                 const AxisTab& ty, const uint32_t* taby) {
+                                                 const AxisTab& ty, const uint32_t* taby, const TapK& k) {
   const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);  // lanes per row = next power of two >= sw
   const uint32_t x = threadIdx.x & ((1u << lshift) - 1), grp = threadIdx.x >> lshift, ngrp = kThreads >> lshift;
   if (x >= sw) return;
-  const float4* w4 = reinterpret_cast<const float4*>(taby);
+  const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(taby);
   const uint32_t* lo = taby + 4 * ty.brows_total;
   const uint32_t* rows = lo + ty.nb;
   const uint32_t* first = rows + ty.nb;
   for (uint32_t ob = grp; ob < ty.nb; ob += ngrp) {
     const uint32_t n = rows[ob];
-    const float4* wp = w4 + first[ob];
+    const ulonglong2* wp = w4 + first[ob];
     const uint32_t* sp = src + lo[ob] * kSrcStride + x;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    Acc4<MODE> acc;
     uint32_t r = 0;
     for (; r + 2 <= n; r += 2) {
       const float4 p0 = px_to_f4<MODE>(sp[0]), p1 = px_to_f4<MODE>(sp[kSrcStride]);
-      const float4 w0 = wp[r], w1 = wp[r + 1];
-      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
-      mac<MODE>(a0, p1, w1.x); mac<MODE>(a1, p1, w1.y); mac<MODE>(a2, p1, w1.z); mac<MODE>(a3, p1, w1.w);
+      const ulonglong2 w0 = wp[r], w1 = wp[r + 1];
+      acc.step(p0, w0, k);
+      acc.step(p1, w1, k);
       sp += 2 * kSrcStride;
     }
-    if (r < n) {
-      const float4 p0 = px_to_f4<MODE>(sp[0]);
-      const float4 w0 = wp[r];
-      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
-    }
+    if (r < n) acc.step(px_to_f4<MODE>(sp[0]), wp[r], k);
     const uint32_t oy = ob * 4;
-    tmp[(oy + 0) * ts + (x ^ ((oy + 0) & 7u))] = a0;
-    if (oy + 1 < dh) tmp[(oy + 1) * ts + (x ^ ((oy + 1) & 7u))] = a1;
-    if (oy + 2 < dh) tmp[(oy + 2) * ts + (x ^ ((oy + 2) & 7u))] = a2;
-    if (oy + 3 < dh) tmp[(oy + 3) * ts + (x ^ ((oy + 3) & 7u))] = a3;
+    tmp[(oy + 0) * ts + (x ^ ((oy + 0) & 7u))] = acc.out(0);
+    if (oy + 1 < dh) tmp[(oy + 1) * ts + (x ^ ((oy + 1) & 7u))] = acc.out(1);
+    if (oy + 2 < dh) tmp[(oy + 2) * ts + (x ^ ((oy + 2) & 7u))] = acc.out(2);
+    if (oy + 3 < dh) tmp[(oy + 3) * ts + (x ^ ((oy + 3) & 7u))] = acc.out(3);
   }
 }
 
 template <int MODE>
 __device__ __forceinline__ void vertical_plain(const uint32_t* src, float4* tmp, uint32_t sw, uint32_t ts, uint32_t dh,
-                                               const AxisTab& ty, const uint32_t* taby) {
+                                               const AxisTab& ty, const uint32_t* taby, const TapK& k) {
   const uint32_t lshift = sw <= 1 ? 0 : 32 - __clz(sw - 1);
   const uint32_t x = threadIdx.x & ((1u << lshift) - 1), grp = threadIdx.x >> lshift, ngrp = kThreads >> lshift;
   if (x >= sw) return;
@@ -1237,28 +1305,31 @@ __device__ __forceinline__ void vertical_plain(const uint32_t* src, float4* tmp,
     const uint32_t n = cnt[oy];
     const float* wr = w + oy * ty.stride;
     const uint32_t* sp = src + left[oy] * kSrcStride + x;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t k = 0;
-    for (; k + 4 <= n; k += 4) {
-      const float4 p0 = px_to_f4<MODE>(sp[0]), p1 = px_to_f4<MODE>(sp[kSrcStride]);
-      const float4 p2 = px_to_f4<MODE>(sp[2 * kSrcStride]), p3 = px_to_f4<MODE>(sp[3 * kSrcStride]);
-      const float w0 = wr[k], w1 = wr[k + 1], w2 = wr[k + 2], w3 = wr[k + 3];
-      mac<MODE>(acc, p0, w0); mac<MODE>(acc, p1, w1); mac<MODE>(acc, p2, w2); mac<MODE>(acc, p3, w3);
+    Acc1<MODE> acc;
+    auto tap = [&](uint32_t word, float wk) {
+      const float4 p = px_to_f4<MODE>(word);
+      acc.step(pk2(p.x, p.y), pk2(p.z, p.w), p.z, wk, k);
+    };
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+      const uint32_t q0 = sp[0], q1 = sp[kSrcStride], q2 = sp[2 * kSrcStride], q3 = sp[3 * kSrcStride];
+      const float w0 = wr[i], w1 = wr[i + 1], w2 = wr[i + 2], w3 = wr[i + 3];
+      tap(q0, w0); tap(q1, w1); tap(q2, w2); tap(q3, w3);
       sp += 4 * kSrcStride;
     }
-    for (; k < n; ++k) {
-      mac<MODE>(acc, px_to_f4<MODE>(sp[0]), wr[k]);
+    for (; i < n; ++i) {
+      tap(sp[0], wr[i]);
       sp += kSrcStride;
     }
-    tmp[oy * ts + (x ^ (oy & 7u))] = acc;
+    tmp[oy * ts + (x ^ (oy & 7u))] = acc.out();
   }
 }
 
 // ---- horizontal_sample: tmp [dh][ts] -> packed RGBA pixels, written through `put(oy, ox, n, px[4])` ------------------
 template <int MODE, typename Put>
 __device__ __forceinline__ void horizontal_blocked(const float4* tmp, uint32_t ts, uint32_t dw, uint32_t dh, const AxisTab& tx,
-                                                   const uint32_t* tabx, Put put) {
-  const float4* w4 = reinterpret_cast<const float4*>(tabx);
+                                                   const uint32_t* tabx, const TapK& k, Put put) {
+  const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(tabx);
   const uint32_t* lo = tabx + 4 * tx.brows_total;
   const uint32_t* rows = lo + tx.nb;
   const uint32_t* first = rows + tx.nb;
@@ -1268,31 +1339,27 @@ __device__ __forceinline__ void horizontal_blocked(const float4* tmp, uint32_t t
     const uint32_t oy = i & ((1u << hshift) - 1), ob = i >> hshift;
     if (oy >= dh) continue;
     const uint32_t n = rows[ob], c0 = lo[ob], s7 = oy & 7u;
-    const float4* wp = w4 + first[ob];
+    const ulonglong2* wp = w4 + first[ob];
     const float4* trow = tmp + oy * ts;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    Acc4<MODE> acc;
     uint32_t c = 0;
     for (; c + 2 <= n; c += 2) {
       const float4 p0 = trow[(c0 + c) ^ s7], p1 = trow[(c0 + c + 1) ^ s7];
-      const float4 w0 = wp[c], w1 = wp[c + 1];
-      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
-      mac<MODE>(a0, p1, w1.x); mac<MODE>(a1, p1, w1.y); mac<MODE>(a2, p1, w1.z); mac<MODE>(a3, p1, w1.w);
+      const ulonglong2 w0 = wp[c], w1 = wp[c + 1];
+      acc.step(p0, w0, k);
+      acc.step(p1, w1, k);
     }
-    if (c < n) {
-      const float4 p0 = trow[(c0 + c) ^ s7];
-      const float4 w0 = wp[c];
-      mac<MODE>(a0, p0, w0.x); mac<MODE>(a1, p0, w0.y); mac<MODE>(a2, p0, w0.z); mac<MODE>(a3, p0, w0.w);
-    }
+    if (c < n) acc.step(trow[(c0 + c) ^ s7], wp[c], k);
     const uint32_t ox = ob * 4;
     const uint32_t nvalid = min(4u, dw - ox);
-    uint32_t px[4] = {pack_px<MODE>(a0), pack_px<MODE>(a1), pack_px<MODE>(a2), pack_px<MODE>(a3)};
+    uint32_t px[4] = {pack_px<MODE>(acc.out(0)), pack_px<MODE>(acc.out(1)), pack_px<MODE>(acc.out(2)), pack_px<MODE>(acc.out(3))};
     put(oy, ox, nvalid, px);
   }
 }
 
 template <int MODE, typename Put>
 __device__ __forceinline__ void horizontal_plain(const float4* tmp, uint32_t ts, uint32_t dw, uint32_t dh, const AxisTab& tx,
-                                                 const uint32_t* tabx, Put put) {
+                                                 const uint32_t* tabx, const TapK& k, Put put) {
   const uint32_t* left = tabx;
   const uint32_t* cnt = tabx + dw;
   const float* w = reinterpret_cast<const float*>(tabx + 2 * dw);
@@ -1300,10 +1367,13 @@ __device__ __forceinline__ void horizontal_plain(const float4* tmp, uint32_t ts,
     const uint32_t oy = i / dw, ox = i - oy * dw, s7 = oy & 7u;
     const uint32_t n = cnt[ox], c0 = left[ox];
     const float* wr = w + ox * tx.stride;
-    const float4* trow = tmp + oy * ts;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t k = 0; k < n; ++k) mac<MODE>(acc, trow[(c0 + k) ^ s7], wr[k]);
-    uint32_t px[4] = {pack_px<MODE>(acc), 0, 0, 0};
+    const ulonglong2* trow = reinterpret_cast<const ulonglong2*>(tmp + oy * ts);
+    Acc1<MODE> acc;
+    for (uint32_t t = 0; t < n; ++t) {
+      const ulonglong2 p = trow[(c0 + t) ^ s7];
+      acc.step(p.x, p.y, lo2(p.y), wr[t], k);
+    }
+    uint32_t px[4] = {pack_px<MODE>(acc.out()), 0, 0, 0};
     put(oy, ox, 1u, px);
   }
 }
@@ -1311,13 +1381,13 @@ __device__ __forceinline__ void horizontal_plain(const float4* tmp, uint32_t ts,
 // the two passes for one staged block; `put` writes up to 4 horizontally adjacent output pixels
 template <int MODE, typename Put>
 __device__ __forceinline__ void resample_staged(const FastSmem& sm, uint32_t sw, uint32_t dw, uint32_t dh, const AxisTab& tx,
-                                                const AxisTab& ty, bool yblocked, bool xblocked, Put put) {
+                                                const AxisTab& ty, bool yblocked, bool xblocked, const TapK& k, Put put) {
   const uint32_t ts = (sw + 7u) & ~7u;
-  if (yblocked) vertical_blocked<MODE>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
-  else vertical_plain<MODE>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby);
+  if (yblocked) vertical_blocked<MODE>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby, k);
+  else vertical_plain<MODE>(sm.src, sm.tmp, sw, ts, dh, ty, sm.taby, k);
   __syncthreads();
-  if (xblocked) horizontal_blocked<MODE>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
-  else horizontal_plain<MODE>(sm.tmp, ts, dw, dh, tx, sm.tabx, put);
+  if (xblocked) horizontal_blocked<MODE>(sm.tmp, ts, dw, dh, tx, sm.tabx, k, put);
+  else horizontal_plain<MODE>(sm.tmp, ts, dw, dh, tx, sm.tabx, k, put);
 }
 
 // ---- encode side: 64x64-or-smaller tiles of the pitched image -> packed payload -----------------------------
@@ -1326,9 +1396,10 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_shrink_rgb
                                                              const pxz_block_desc* __restrict__ descs,
                                                              const uint32_t* __restrict__ tabidx, uint8_t* __restrict__ payload,
                                                              const AxisTab* __restrict__ tabs, uint32_t ntabs,
-                                                             const uint32_t* __restrict__ pool, uint32_t max_tmp_px) {
+                                                             const uint32_t* __restrict__ pool, uint32_t max_tmp_px, float rt_one, float rt_negzero) {
   extern __shared__ float s_dyn[];
   FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
+  const TapK tapk = make_tapk(rt_one, rt_negzero);
   const uint32_t tid = threadIdx.x;
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t qpr = g.bw >> 2;  // 16-byte quads per full tile row
@@ -1423,8 +1494,8 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_shrink_rgb
         if (n > 2) o[2] = px[2];
         if (n > 3) o[3] = px[3];
       };
-      if (opaque) resample_staged<(FUSED ? 2 : 0)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
-      else resample_staged<(FUSED ? 3 : 1)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      if (opaque) resample_staged<(FUSED ? 2 : 0)>(sm, sw, dw, dh, tx, ty, yb, xb, tapk, put);
+      else resample_staged<(FUSED ? 3 : 1)>(sm, sw, dw, dh, tx, ty, yb, xb, tapk, put);
       __syncthreads();
     }
 #pragma unroll
@@ -1441,9 +1512,10 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgb
                                                              const uint32_t* __restrict__ tabidx,
                                                              const uint8_t* __restrict__ payload,
                                                              const AxisTab* __restrict__ tabs, uint32_t ntabs,
-                                                             const uint32_t* __restrict__ pool, uint32_t max_tmp_px) {
+                                                             const uint32_t* __restrict__ pool, uint32_t max_tmp_px, float rt_one, float rt_negzero) {
   extern __shared__ float s_dyn[];
   FastSmem sm = carve_fast_smem(s_dyn, max_tmp_px);
+  const TapK tapk = make_tapk(rt_one, rt_negzero);
   const uint32_t tid = threadIdx.x;
   const uint32_t nblocks = g.cols * g.rows;
   for (uint32_t i = tid; i < ntabs * (sizeof(AxisTab) / 4); i += kThreads)
@@ -1551,8 +1623,8 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgb
           if (n > 2) o[2] = px[2];
         }
       };
-      if (opaque) resample_staged<(FUSED ? 2 : 0)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
-      else resample_staged<(FUSED ? 3 : 1)>(sm, sw, dw, dh, tx, ty, yb, xb, put);
+      if (opaque) resample_staged<(FUSED ? 2 : 0)>(sm, sw, dw, dh, tx, ty, yb, xb, tapk, put);
+      else resample_staged<(FUSED ? 3 : 1)>(sm, sw, dw, dh, tx, ty, yb, xb, tapk, put);
       __syncthreads();
     }
 #pragma unroll
@@ -1734,19 +1806,19 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
     if (direction == 0 && !fused) {
       e = set_smem(k_shrink_rgba<false>, smem);
       if (e != cudaSuccess) return e;
-      k_shrink_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
+      k_shrink_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px, 1.0f, -0.0f);
     } else if (direction == 0) {
       e = set_smem(k_shrink_rgba<true>, smem);
       if (e != cudaSuccess) return e;
-      k_shrink_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
+      k_shrink_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px, 1.0f, -0.0f);
     } else if (!fused) {
       e = set_smem(k_expand_rgba<false>, smem);
       if (e != cudaSuccess) return e;
-      k_expand_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
+      k_expand_rgba<false><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px, 1.0f, -0.0f);
     } else {
       e = set_smem(k_expand_rgba<true>, smem);
       if (e != cudaSuccess) return e;
-      k_expand_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px);
+      k_expand_rgba<true><<<fgrid, kThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, ntabs, pool, max_tmp_px, 1.0f, -0.0f);
     }
     return cudaGetLastError();
   }
