@@ -39,6 +39,7 @@ struct TabSet {  // device copy of the axis tables of one (spec, filter, directi
   uint32_t* d_pool = nullptr;
   uint32_t max_words = 0;  // largest single table (left | count | weights), in 32-bit words
   uint32_t ntabs = 0;
+  bool warp_ok = false;    // every table has the form the warp-per-tile kernels need
 };
 
 using TabKey = std::tuple<std::vector<uint32_t>, std::vector<uint32_t>, int, int>;
@@ -81,6 +82,8 @@ struct pxz_ctx {
   uint32_t* d_list = nullptr;  // [values_cap + 1]: banded tile indices, last word = count
   size_t values_cap = 0;
   float* d_minmax = nullptr;
+  uint32_t* d_tile_counter = nullptr;  // work counter of the warp-per-tile resample kernels (they leave it at 0)
+  bool warp_kernels = true;            // PXZ_RESAMPLE_KERNELS=cta selects the CTA-per-tile kernels instead
   void* d_scan = nullptr;
   size_t scan_cap = 0;
   uint8_t* d_scratch = nullptr;
@@ -265,7 +268,11 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
   }
   TabSet ts;
   ts.ntabs = (uint32_t)tabs.size();
-  for (const AxisTab& t : tabs) ts.max_words = std::max(ts.max_words, std::max(2 * t.n_out + t.n_out * t.stride, t.bwords));
+  ts.warp_ok = true;
+  for (const AxisTab& t : tabs) {
+    ts.max_words = std::max(ts.max_words, std::max(2 * t.n_out + t.n_out * t.stride, t.bwords));
+    if (direction == 1 && t.goff == 0xFFFFFFFFu) ts.warp_ok = false;
+  }
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_tabs, tabs.size() * sizeof(AxisTab))) != PXZ_OK) return st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_pool, pool.size() * 4)) != PXZ_OK) return st;
@@ -279,7 +286,7 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
 }
 
 pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch, const pxz_payload* p, const TabSet& ts,
-                        uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px) {
+                        uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, const uint8_t* opaque_flags = nullptr) {
   const Geom& g = p->g;
   const uint32_t nblocks = g.cols * g.rows;
   size_t smem = resample_smem_bytes(max_src_px, max_tmp_px, g.C);
@@ -302,7 +309,8 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   }
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
-                                ts.ntabs, max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, ctx->stream, ctx->sm_count,
+                                ts.ntabs, max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, opaque_flags,
+                                ctx->warp_kernels ? ctx->d_tile_counter : nullptr, ts.warp_ok, ctx->stream, ctx->sm_count,
                                 &ctx->launches));
   return PXZ_OK;
 }
@@ -364,7 +372,9 @@ pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx*
   ctx->band.abs_raw = 8.0e-6f; // fast arithmetic, absolute (SFU cube roots; measured <= 4e-6)
   if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
   if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
+  if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->warp_kernels = strcmp(e, "cta") != 0;
   if (cudaMalloc((void**)&ctx->d_minmax, 4 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->d_tile_counter, 64) != cudaSuccess || cudaMemset(ctx->d_tile_counter, 0, 64) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_total, 64) != cudaSuccess) {
     cudaGetLastError();
     delete ctx;
@@ -421,6 +431,7 @@ void pxz_ctx_destroy(pxz_ctx* ctx) {
   for (auto& r : ctx->prof_open) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
   cudaFree(ctx->d_minmax);
+  cudaFree(ctx->d_tile_counter);
   cudaFreeHost(ctx->h_total);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -733,7 +744,10 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   }
   TabSet ts;
   st = get_tabset(ctx, *p->spec, (int)filter_down, 0, &ts);
-  if (st == PXZ_OK) st = run_resample(ctx, 0, img->d, img->pitch, p, ts, g.bw * g.bh, std::max(g.bw, g.bh), p->max_tmp_down);
+  // the fast Oklab-MAD pass also told which tiles are fully opaque: their alpha channel needs no arithmetic
+  const uint8_t* opaque_flags = (metric == PXZ_METRIC_OKLAB_MAD && !exact_all) ? ctx->d_opaque : nullptr;
+  if (st == PXZ_OK)
+    st = run_resample(ctx, 0, img->d, img->pitch, p, ts, g.bw * g.bh, std::max(g.bw, g.bh), p->max_tmp_down, opaque_flags);
   if (st != PXZ_OK) {
     payload_release(p);
     return st;

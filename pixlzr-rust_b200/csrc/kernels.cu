@@ -1647,6 +1647,14 @@ __global__ void __launch_bounds__(kThreads) k_tree_mask(const float* __restrict_
   recurse[b] = (uint8_t)(active && !reduce);
 }
 
+#ifndef PXZ_SHRINK_WARP_CTAS
+#define PXZ_SHRINK_WARP_CTAS 3
+#endif
+#ifndef PXZ_EXPAND_WARP_CTAS
+#define PXZ_EXPAND_WARP_CTAS 6
+#endif
+#include "resample_warp.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
@@ -1791,8 +1799,8 @@ int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
-                            uint8_t* scratch, size_t scratch_per_cta, int grid, bool fused, cudaStream_t s, int sm_count,
-                            uint64_t* launches) {
+                            uint8_t* scratch, size_t scratch_per_cta, int grid, bool fused, const uint8_t* opaque_flags,
+                            uint32_t* tile_counter, bool warp_tables, cudaStream_t s, int sm_count, uint64_t* launches) {
   cudaError_t e;
   ++*launches;
   // RGBA fast paths: tiles <= 64x64 with 16-byte aligned rows
@@ -1800,6 +1808,22 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                     ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && max_src_px <= (uint32_t)kFastMaxPx && max_src_dim <= 64u &&
                     max_tmp_px <= (uint32_t)kFastMaxPx && max_tab_words <= (uint32_t)kFastMaxTabWords &&
                     ntabs <= (uint32_t)kFastMaxTabs && scratch == nullptr;
+  if (fast && warp_tables && tile_counter != nullptr) {
+    // warp-per-tile kernels (resample_warp.cuh)
+    const long long ntiles = (long long)g.cols * g.rows;
+    if (direction == 0) {
+      const size_t smem = (size_t)kWarpsPerCta * kShrinkStripPx * sizeof(float4);
+      const int wgrid = clamp_grid((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)sm_count * PXZ_SHRINK_WARP_CTAS);
+      if (fused) k_shrink_warp<true><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      else k_shrink_warp<false><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+    } else {
+      const size_t smem = (size_t)kWarpsPerCta * kExpandStripPx * sizeof(float4);
+      const int wgrid = clamp_grid((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)sm_count * PXZ_EXPAND_WARP_CTAS);
+      if (fused) k_expand_warp<true><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      else k_expand_warp<false><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+    }
+    return cudaGetLastError();
+  }
   if (fast) {
     const size_t smem = fast_smem_bytes(max_tmp_px);
     const int fgrid = clamp_grid((long long)g.cols * g.rows, (long long)sm_count * PXZ_RESAMPLE_MINBLOCKS);

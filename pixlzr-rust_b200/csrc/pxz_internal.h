@@ -22,9 +22,20 @@ constexpr uint32_t kLevelOnePixel = 0xFFu; // "level 0" / below every threshold:
 //   window) | lo[nb] | rows[nb] | first[nb] (index of the group's first float4)
 // A kernel walks source samples lo .. lo+rows once per group and feeds 4 accumulators, so each accumulator still
 // receives its taps in ascending order (adding p * 0 is exact).
+//
+// Two more forms serve the warp-per-tile kernels (k_shrink_warp / k_expand_warp):
+//  * slide form at `soff` (downscale, n_in >= n_out; pool offset is a multiple of 4 words): n_in rows of 8 floats —
+//    row r holds, for every accumulator slot s < slots, the weight of the output o with o % slots == s whose
+//    (zero-trimmed) window contains source sample r, else +0 — followed by done[n_in]: how many outputs (in ascending
+//    order) receive their last tap at sample r.  One walk over the source samples feeds all live outputs, so every
+//    sample is loaded and converted once and no multiply is wasted; each accumulator still sees its taps in
+//    ascending order.  slots in {2, 4, 6}; 0 = the table has no slide form (more than 6 outputs live at once).
+//  * gather8 form at `goff` (upscale, every output has <= 8 taps): n_out rows of 8 floats (weights, +0 padded),
+//    then left[n_out].  goff = 0xFFFFFFFF if an output has more than 8 taps.
 struct AxisTab {
   uint32_t n_in, n_out, stride, off;
   uint32_t boff, nb, brows_total, bwords;
+  uint32_t soff, slots, goff, pad_;
 };
 
 // Geometry of the block grid over a pitched image.
@@ -79,8 +90,8 @@ size_t plan_scan_state_bytes(uint32_t nblocks);
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
-                            uint8_t* scratch, size_t scratch_per_cta, int grid_hint, bool fused, cudaStream_t s, int sm_count,
-                            uint64_t* launches);
+                            uint8_t* scratch, size_t scratch_per_cta, int grid_hint, bool fused, const uint8_t* opaque_flags,
+                            uint32_t* tile_counter, bool warp_tables, cudaStream_t s, int sm_count, uint64_t* launches);
 size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
 int resample_grid(int sm_count, uint32_t nblocks);
 

@@ -111,11 +111,12 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
       memcpy(&(*pool)[wbase + (size_t)o * stride + i], &w, sizeof(float));
     }
   }
-  // blocked form: groups of 4 consecutive outputs share one walk over the source samples
+  // blocked form: groups of 4 consecutive outputs share one walk over the source samples.  Groups with identical
+  // weight rows (the interior groups of an integer ratio) share one copy, so most lanes of a warp read one address.
   while (pool->size() % 4) pool->push_back(0u);
   const uint32_t nb = (n_out + 3) / 4;
   std::vector<uint32_t> lo(nb), rows(nb), first(nb);
-  uint32_t total_rows = 0;
+  std::vector<uint32_t> w4;  // unique groups, 4 words per source sample
   for (uint32_t b = 0; b < nb; ++b) {
     uint32_t l = lefts[4 * b], h = 0;
     for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
@@ -124,27 +125,90 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
     }
     lo[b] = l;
     rows[b] = h - l;
-    first[b] = total_rows;
-    total_rows += rows[b];
+    std::vector<uint32_t> grp((size_t)rows[b] * 4, 0u);  // +0.0f everywhere
+    for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
+      const uint32_t o = 4 * b + j;
+      for (uint32_t i = 0; i < counts[o]; ++i) grp[(size_t)(lefts[o] + i - l) * 4 + j] = (*pool)[wbase + (size_t)o * stride + i];
+    }
+    bool found = false;
+    for (uint32_t p = 0; p < b && !found; ++p) {
+      if (rows[p] == rows[b] && std::equal(grp.begin(), grp.end(), w4.begin() + (size_t)first[p] * 4)) {
+        first[b] = first[p];
+        found = true;
+      }
+    }
+    if (!found) {
+      first[b] = (uint32_t)(w4.size() / 4);
+      w4.insert(w4.end(), grp.begin(), grp.end());
+    }
   }
   tab->boff = (uint32_t)pool->size();
   tab->nb = nb;
-  tab->brows_total = total_rows;
+  tab->brows_total = (uint32_t)(w4.size() / 4);
   const size_t w4base = pool->size();
-  pool->resize(w4base + (size_t)total_rows * 4, 0u);  // +0.0f everywhere
-  for (uint32_t b = 0; b < nb; ++b) {
-    for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
-      const uint32_t o = 4 * b + j;
-      for (uint32_t i = 0; i < counts[o]; ++i) {
-        const uint32_t r = lefts[o] + i - lo[b];
-        (*pool)[w4base + ((size_t)first[b] + r) * 4 + j] = (*pool)[wbase + (size_t)o * stride + i];
-      }
-    }
-  }
+  pool->insert(pool->end(), w4.begin(), w4.end());
   pool->insert(pool->end(), lo.begin(), lo.end());
   pool->insert(pool->end(), rows.begin(), rows.end());
   pool->insert(pool->end(), first.begin(), first.end());
   tab->bwords = (uint32_t)(pool->size() - w4base);
+
+  // ---- slide form (see pxz_internal.h) ----
+  tab->soff = 0;
+  tab->slots = 0;
+  tab->goff = 0xFFFFFFFFu;
+  tab->pad_ = 0;
+  auto weight_of = [&](uint32_t o, uint32_t i) {
+    float w;
+    memcpy(&w, &(*pool)[wbase + (size_t)o * stride + i], sizeof(float));
+    return w;
+  };
+  if (n_in >= n_out) {
+    // zero-trimmed windows: a tap whose weight is exactly 0 adds p * 0 = +-0 to an accumulator that is never -0
+    std::vector<uint32_t> tl(n_out), tr(n_out);
+    bool ok = true;
+    for (uint32_t o = 0; o < n_out; ++o) {
+      uint32_t a = 0, b = counts[o];
+      while (a < b && weight_of(o, a) == 0.0f) ++a;
+      while (b > a && weight_of(o, b - 1) == 0.0f) --b;
+      if (a == b) { a = 0; b = 1; }  // all-zero row cannot happen (the weights sum to 1); keep one tap
+      tl[o] = lefts[o] + a;
+      tr[o] = lefts[o] + b;
+      if (o > 0 && (tl[o] < tl[o - 1] || tr[o] < tr[o - 1])) ok = false;  // outputs must start and finish in order
+    }
+    uint32_t max_live = 0;
+    if (ok) {
+      for (uint32_t r = 0; r < n_in; ++r) {
+        uint32_t live = 0;
+        for (uint32_t o = 0; o < n_out; ++o) live += (tl[o] <= r && r < tr[o]) ? 1u : 0u;
+        max_live = std::max(max_live, live);
+      }
+    }
+    const uint32_t slots = max_live <= 2 ? 2u : max_live <= 4 ? 4u : max_live <= 6 ? 6u : 0u;
+    if (ok && slots) {
+      // with windows ordered on both ends the live outputs at any sample are consecutive, so o % slots never collides
+      while (pool->size() % 4) pool->push_back(0u);
+      const size_t sbase = pool->size();
+      pool->resize(sbase + (size_t)n_in * 8 + n_in, 0u);
+      for (uint32_t o = 0; o < n_out; ++o) {
+        for (uint32_t r = tl[o]; r < tr[o]; ++r)
+          (*pool)[sbase + (size_t)r * 8 + (o % slots)] = (*pool)[wbase + (size_t)o * stride + (r - lefts[o])];
+        (*pool)[sbase + (size_t)n_in * 8 + (tr[o] - 1)] += 1u;
+      }
+      tab->soff = (uint32_t)sbase;
+      tab->slots = slots;
+    }
+  }
+  // ---- gather8 form ----
+  if (n_in <= n_out && stride <= 7) {  // the expand kernel keeps a 7-sample window
+    while (pool->size() % 4) pool->push_back(0u);
+    const size_t gbase = pool->size();
+    pool->resize(gbase + (size_t)n_out * 8 + n_out, 0u);
+    for (uint32_t o = 0; o < n_out; ++o) {
+      for (uint32_t i = 0; i < counts[o]; ++i) (*pool)[gbase + (size_t)o * 8 + i] = (*pool)[wbase + (size_t)o * stride + i];
+      (*pool)[gbase + (size_t)n_out * 8 + o] = lefts[o];
+    }
+    tab->goff = (uint32_t)gbase;
+  }
   return true;
 }
 
