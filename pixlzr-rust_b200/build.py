@@ -13,9 +13,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libpixlzr_b200.so")
+OUT = os.environ.get("PXZ_OUT") or os.path.join(HERE, "libpixlzr_b200.so")
 SOURCES = ["kernels.cu", "abi.cpp", "tables.cpp", "container.cpp", "nccl_dyn.cpp"]
-HEADERS = ["pxz_internal.h", "pxz_host.h", "srgb_lut.inc", os.path.join("..", "..", "include", "pixlzr_b200.h")]
+HEADERS = ["pxz_internal.h", "pxz_host.h", "srgb_lut.inc", "resample_warp.cuh", os.path.join("..", "..", "include", "pixlzr_b200.h")]
 NVCC = os.environ.get("PXZ_NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = [
@@ -38,7 +38,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    cmd = [NVCC] + FLAGS + os.environ.get("PXZ_EXTRA_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:

@@ -1651,7 +1651,7 @@ __global__ void __launch_bounds__(kThreads) k_tree_mask(const float* __restrict_
 #define PXZ_SHRINK_WARP_CTAS 3
 #endif
 #ifndef PXZ_EXPAND_WARP_CTAS
-#define PXZ_EXPAND_WARP_CTAS 6
+#define PXZ_EXPAND_WARP_CTAS 4
 #endif
 #include "resample_warp.cuh"
 
@@ -1812,12 +1812,19 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
     // warp-per-tile kernels (resample_warp.cuh)
     const long long ntiles = (long long)g.cols * g.rows;
     if (direction == 0) {
-      const size_t smem = (size_t)kWarpsPerCta * kShrinkStripPx * sizeof(float4);
-      const int wgrid = clamp_grid((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)sm_count * PXZ_SHRINK_WARP_CTAS);
-      if (fused) k_shrink_warp<true><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
-      else k_shrink_warp<false><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      const size_t smem = (size_t)kShrinkWarps * kShrinkWarpBytes;
+      const int wgrid = clamp_grid((ntiles + kShrinkWarps - 1) / kShrinkWarps, (long long)sm_count * PXZ_SHRINK_WARP_CTAS);
+      if (fused) {
+        e = set_smem(k_shrink_warp<true>, smem);
+        if (e != cudaSuccess) return e;
+        k_shrink_warp<true><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      } else {
+        e = set_smem(k_shrink_warp<false>, smem);
+        if (e != cudaSuccess) return e;
+        k_shrink_warp<false><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      }
     } else {
-      const size_t smem = (size_t)kWarpsPerCta * kExpandStripPx * sizeof(float4);
+      const size_t smem = (size_t)kWarpsPerCta * kExpandWarpBytes;
       const int wgrid = clamp_grid((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)sm_count * PXZ_EXPAND_WARP_CTAS);
       if (fused) k_expand_warp<true><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
       else k_expand_warp<false><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
@@ -1860,5 +1867,11 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
   }
   return cudaGetLastError();
 }
+
+#ifdef PXZ_WARP_STATS
+extern "C" int pxz_debug_warp_stats(unsigned long long* out, int n_words) {
+  return (int)cudaMemcpyFromSymbol(out, g_warp_stats, sizeof(unsigned long long) * (size_t)n_words);
+}
+#endif
 
 }  // namespace pxz

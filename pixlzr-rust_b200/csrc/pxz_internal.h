@@ -30,12 +30,16 @@ constexpr uint32_t kLevelOnePixel = 0xFFu; // "level 0" / below every threshold:
 //    order) receive their last tap at sample r.  One walk over the source samples feeds all live outputs, so every
 //    sample is loaded and converted once and no multiply is wasted; each accumulator still sees its taps in
 //    ascending order.  slots in {2, 4, 6}; 0 = the table has no slide form (more than 6 outputs live at once).
-//  * gather8 form at `goff` (upscale, every output has <= 8 taps): n_out rows of 8 floats (weights, +0 padded),
-//    then left[n_out].  goff = 0xFFFFFFFF if an output has more than 8 taps.
+//  * gather8 form at `goff` (upscale, every output has <= 7 taps): n_out rows of 8 floats (weights, +0 padded),
+//    then left[n_out]; at `gpoff` (multiple of 4 words) ceil(n_out / 2) rows of 8 float pairs
+//    (w[2p][i], w[2p+1][i]): two output rows with the same first tap run as the two lanes of one f32x2 operation.
+//    goff = 0xFFFFFFFF if an output has more than 7 taps.
+//  bpad: upscale tables store every blocked group with bpad (2, 4 or 8) rows; 0 = own lengths.
 struct AxisTab {
   uint32_t n_in, n_out, stride, off;
   uint32_t boff, nb, brows_total, bwords;
-  uint32_t soff, slots, goff, pad_;
+  uint32_t soff, slots, goff, gpoff;
+  uint32_t bpad, pad0_, pad1_, pad2_;
 };
 
 // Geometry of the block grid over a pitched image.

@@ -2,28 +2,41 @@
 //
 // Every warp owns one tile at a time (tiles are handed out through an atomic counter), so there is no CTA barrier
 // anywhere and a light tile never idles the threads of a heavy one:
-//   * shrink: the source tile is streamed from global memory exactly once, row by row (lane = columns x and x + 32);
-//     the vertical pass keeps all live output rows in registers ("slide" table form, pxz_internal.h) and emits one
-//     finished row of f32 intermediates at a time into an 8-row shared-memory strip; whenever the strip is full the
-//     warp runs the horizontal pass over it and writes the packed payload pixels.
+//   * shrink: the source tile is streamed from global memory exactly once through a 16-row cp.async ring in shared
+//     memory (lane = columns 2x and 2x + 1); the vertical pass keeps all live output rows in registers ("slide" table
+//     form, pxz_internal.h) and emits one finished row of f32 intermediates at a time into an 8-row strip; whenever
+//     the strip is full the warp runs the horizontal pass over it and writes the packed payload pixels.
 //   * expand: the (small) source block is streamed once through a 7-row register window of converted samples; two
 //     rows of intermediates at a time go through shared memory to the horizontal pass, which writes the image tile
 //     (the paste is fused: 16-byte stores into the pitched image).
 // Arithmetic order per output is the reference's (ascending taps, product and sum rounded separately), on the packed
-// f32x2 pipe (Acc4 / Acc1 / mac2 in kernels.cu).
+// f32x2 pipe (Acc4 / mac2 in kernels.cu).
 #pragma once
 
-constexpr int kWarpCtaThreads = 128;  // 4 warps
+#ifndef PXZ_SHRINK_WARPS
+#define PXZ_SHRINK_WARPS 4
+#endif
+#ifndef PXZ_RING_ROWS
+#define PXZ_RING_ROWS 16
+#endif
+constexpr int kWarpCtaThreads = 128;  // expand: 4 warps per CTA
 constexpr int kWarpsPerCta = kWarpCtaThreads / 32;
+constexpr int kShrinkWarps = PXZ_SHRINK_WARPS;
+constexpr int kShrinkCtaThreads = kShrinkWarps * 32;
 constexpr int kStripRows = 8;         // shrink: rows of intermediates per horizontal batch
-constexpr int kStripStride = 64;      // float4 per strip row
-constexpr int kShrinkStripPx = kStripRows * kStripStride;
-constexpr int kExpandStripPx = 2 * kStripStride;
+constexpr int kStripStride = 65;      // float4 per strip row: 64 + 1, so 8 rows of one column sit in 8 different banks
+constexpr int kRingRows = PXZ_RING_ROWS;  // shrink: source rows in flight per warp (x 256 B)
+constexpr int kHTabWords = 512;       // shrink: per-warp copy of the tile's horizontal table (2 KB), else read via L1
+constexpr int kShrinkWarpBytes = kStripRows * kStripStride * 16 + kRingRows * 64 * 4 + kHTabWords * 4;
+constexpr int kExpandRow1 = 68;       // expand: second strip row starts at 64 + pad (pad chosen per tile, <= 4)
+constexpr int kExpandWarpBytes = (kExpandRow1 + 64 + 8) * 16;
 
-__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
-  uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-  return r;
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // next tile of this warp (lane 0 asks, everybody gets the answer).  Every warp draws exactly one index >= ntiles; the
@@ -37,9 +50,125 @@ __device__ __forceinline__ uint32_t next_tile(uint32_t* counter, uint32_t ntiles
   return __shfl_sync(0xffffffffu, b, 0);
 }
 
+#ifdef PXZ_WARP_STATS
+// debug build only: per-warp start / end time (ns) and tile counts of the last warp-kernel launch
+__device__ unsigned long long g_warp_stats[8192 * 4];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 // ---- shrink ------------------------------------------------------------------------------------------------------
+constexpr uint32_t kBlockedFrom = 8;  // outputs per row from which the horizontal pass walks groups of 4 (else scalar chains)
+// The horizontal table of a tile as the pass reads it: from kBlockedFrom outputs the blocked form (w4 rows | lo | rows | first), else the
+// per-output form (left | count | weights).  `tab` points at a per-warp shared-memory copy when it fits, else at the pool.
+struct HTab {
+  const uint32_t* tab;
+  uint32_t nb, brows_total, stride;
+};
+__device__ __forceinline__ HTab stage_htab(const AxisTab& tx, uint32_t dw, const uint32_t* __restrict__ pool, uint32_t* smem_tab) {
+  const uint32_t lane = threadIdx.x & 31u;
+  HTab h;
+  h.nb = tx.nb; h.brows_total = tx.brows_total; h.stride = tx.stride;
+  const uint32_t* src = dw >= kBlockedFrom ? pool + tx.boff : pool + tx.off;
+  const uint32_t words = dw >= kBlockedFrom ? tx.bwords : 2 * dw + dw * tx.stride;
+  if (words <= (uint32_t)kHTabWords) {
+    for (uint32_t i = lane; i < words; i += 32) smem_tab[i] = __ldg(src + i);
+    h.tab = smem_tab;
+  } else {
+    h.tab = src;
+  }
+  return h;
+}
+
+// horizontal pass over `nrows` strip rows (output rows row0 .. row0 + nrows - 1) -> payload block at dst
+template <int MODE>
+__device__ __forceinline__ void shrink_horizontal(const float4* strip, uint32_t row0, uint32_t nrows, uint32_t dw, const HTab& ht,
+                                                  uint32_t* dst, const TapK& k) {
+  const uint32_t lane = threadIdx.x & 31u;
+  if (dw >= kBlockedFrom) {
+    // groups of 4 outputs share one walk (blocked table form); item = (strip row, group): the 8 lanes of a
+    // shared-memory phase read the same column of 8 different rows = 8 different banks (row stride 65)
+    const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(ht.tab);
+    const uint32_t* lo = ht.tab + 4 * ht.brows_total;
+    const uint32_t* rows = lo + ht.nb;
+    const uint32_t* first = rows + ht.nb;
+    for (uint32_t i = lane; i < ht.nb * kStripRows; i += 32) {
+      const uint32_t r = i & (kStripRows - 1), ob = i / kStripRows;
+      if (r >= nrows) continue;
+      const uint32_t n = rows[ob];
+      const ulonglong2* wp = w4 + first[ob];
+      const float4* tp = strip + r * kStripStride + lo[ob];
+      Acc4<MODE> acc;
+      uint32_t c = n;
+      for (; c >= 2; c -= 2) {
+        const float4 p0 = tp[0], p1 = tp[1];
+        const ulonglong2 w0 = wp[0], w1 = wp[1];
+        acc.step(p0, w0, k);
+        acc.step(p1, w1, k);
+        tp += 2;
+        wp += 2;
+      }
+      if (c) acc.step(tp[0], wp[0], k);
+      const uint32_t ox = ob * 4, nvalid = min(4u, dw - ox);
+      uint32_t* o = dst + (size_t)(row0 + r) * dw + ox;
+      o[0] = pack_px<MODE>(acc.out(0));
+      if (nvalid > 1) o[1] = pack_px<MODE>(acc.out(1));
+      if (nvalid > 2) o[2] = pack_px<MODE>(acc.out(2));
+      if (nvalid > 3) o[3] = pack_px<MODE>(acc.out(3));
+    }
+  } else {
+    // few outputs: one scalar chain per (row, output, channel)
+    const uint32_t* left = ht.tab;
+    const uint32_t* cnt = left + dw;
+    const float* w = reinterpret_cast<const float*>(left + 2 * dw);
+    const uint32_t total = nrows * dw * 4;
+    for (uint32_t i = lane; i < total; i += 32) {
+      const uint32_t c = i & 3u, j = i >> 2, r = j / dw, ox = j - r * dw;
+      uint32_t byte = 0xFFu;
+      if ((MODE & 1) || c < 3) {
+        const uint32_t n = cnt[ox];
+        const float* wr = w + ox * ht.stride;
+        const float* tp = reinterpret_cast<const float*>(strip + r * kStripStride + left[ox]) + c;
+        float a = 0.f;
+        uint32_t t = 0;
+        for (; t + 4 <= n; t += 4) {
+          const float p0 = tp[0], p1 = tp[4], p2 = tp[8], p3 = tp[12];
+          const float w0 = wr[t], w1 = wr[t + 1], w2 = wr[t + 2], w3 = wr[t + 3];
+          a = mac1<MODE>(a, p0, w0); a = mac1<MODE>(a, p1, w1); a = mac1<MODE>(a, p2, w2); a = mac1<MODE>(a, p3, w3);
+          tp += 16;
+        }
+        for (; t < n; ++t) {
+          a = mac1<MODE>(a, tp[0], wr[t]);
+          tp += 4;
+        }
+        byte = to_u8_fast(a);
+      }
+      reinterpret_cast<uint8_t*>(dst)[((size_t)(row0 + r) * dw + ox) * 4 + c] = (uint8_t)byte;
+    }
+  }
+}
+
+// Everything the vertical pass of one tile keeps between two horizontal batches (all in registers).
+template <int MODE>
+struct ShrinkRun {
+  static constexpr int NC = (MODE & 1) ? 4 : 3;
+  u64 acc[2][NC][3];             // [column][channel][slot pair]; tables with fewer slots use the first pairs
+  const ulonglong2* wp;          // slide table row of source row r
+  const uint32_t* dp;            // done[r]
+  ulonglong2 wa_n;               // table row of source row r, requested one row ahead
+  u64 wb_n;
+  uint32_t nd_n;
+  uint32_t r;                    // next source row
+  uint32_t pend;                 // outputs finished by row r - 1 that still have to be emitted
+  uint32_t o_next, slot, batch0; // next output row, its accumulator slot, first output row of the strip
+  uint32_t ob;                   // blocked fallback: next group of 4 output rows
+};
+
 template <int MODE, int NP, int S>
-__device__ __forceinline__ void take_slot(u64 (&acc)[2][(MODE & 1) ? 4 : 3][NP], float4& v0, float4& v1) {
+__device__ __forceinline__ void take_slot3(u64 (&acc)[2][(MODE & 1) ? 4 : 3][3], float4& v0, float4& v1) {
   constexpr int NC = (MODE & 1) ? 4 : 3;
   constexpr int jp = S / 2;
   constexpr bool high = (S & 1) != 0;
@@ -58,292 +187,285 @@ __device__ __forceinline__ void take_slot(u64 (&acc)[2][(MODE & 1) ? 4 : 3][NP],
   v1 = make_float4(b[0], b[1], b[2], b[3]);
 }
 
-// horizontal pass over `nrows` strip rows (output rows row0 .. row0 + nrows - 1) -> payload block at dst
-template <int MODE>
-__device__ __forceinline__ void shrink_horizontal(const float4* strip, uint32_t row0, uint32_t nrows, uint32_t dw, const AxisTab& tx,
-                                                  const uint32_t* __restrict__ pool, uint32_t* dst, const TapK& k) {
-  const uint32_t lane = threadIdx.x & 31u;
-  if (dw >= 16) {
-    // groups of 4 outputs share one walk (blocked table form); item = (strip row, group), 8 rows per group so that
-    // the 8 lanes of a shared-memory phase read 8 different rows (the row-XOR swizzle makes them 8 different banks)
-    const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(pool + tx.boff);
-    const uint32_t* lo = pool + tx.boff + 4 * tx.brows_total;
-    const uint32_t* rows = lo + tx.nb;
-    const uint32_t* first = rows + tx.nb;
-    for (uint32_t i = lane; i < tx.nb * kStripRows; i += 32) {
-      const uint32_t r = i & (kStripRows - 1), ob = i / kStripRows;
-      if (r >= nrows) continue;
-      const uint32_t n = __ldg(rows + ob), c0 = __ldg(lo + ob), s7 = r & 7u;
-      const ulonglong2* wp = w4 + __ldg(first + ob);
-      const float4* trow = strip + r * kStripStride;
-      Acc4<MODE> acc;
-      uint32_t c = 0;
-      for (; c + 2 <= n; c += 2) {
-        const float4 p0 = trow[(c0 + c) ^ s7], p1 = trow[(c0 + c + 1) ^ s7];
-        const ulonglong2 w0 = __ldg(wp + c), w1 = __ldg(wp + c + 1);
-        acc.step(p0, w0, k);
-        acc.step(p1, w1, k);
-      }
-      if (c < n) acc.step(trow[(c0 + c) ^ s7], __ldg(wp + c), k);
-      const uint32_t ox = ob * 4, nvalid = min(4u, dw - ox);
-      uint32_t* o = dst + (size_t)(row0 + r) * dw + ox;
-      o[0] = pack_px<MODE>(acc.out(0));
-      if (nvalid > 1) o[1] = pack_px<MODE>(acc.out(1));
-      if (nvalid > 2) o[2] = pack_px<MODE>(acc.out(2));
-      if (nvalid > 3) o[3] = pack_px<MODE>(acc.out(3));
-    }
-  } else {
-    // few outputs: one scalar chain per (row, output, channel)
-    const uint32_t* left = pool + tx.off;
-    const uint32_t* cnt = left + dw;
-    const float* w = reinterpret_cast<const float*>(left + 2 * dw);
-    const uint32_t total = nrows * dw * 4;
-    for (uint32_t i = lane; i < total; i += 32) {
-      const uint32_t c = i & 3u, j = i >> 2, r = j / dw, ox = j - r * dw;
-      uint32_t byte = 0xFFu;
-      if ((MODE & 1) || c < 3) {
-        const uint32_t n = __ldg(cnt + ox), l = __ldg(left + ox), s7 = r & 7u;
-        const float* wr = w + ox * tx.stride;
-        const float* trow = reinterpret_cast<const float*>(strip + r * kStripStride) + c;
-        float a = 0.f;
-        uint32_t t = 0;
-        for (; t + 4 <= n; t += 4) {
-          const float p0 = trow[((l + t) ^ s7) << 2], p1 = trow[((l + t + 1) ^ s7) << 2];
-          const float p2 = trow[((l + t + 2) ^ s7) << 2], p3 = trow[((l + t + 3) ^ s7) << 2];
-          const float w0 = __ldg(wr + t), w1 = __ldg(wr + t + 1), w2 = __ldg(wr + t + 2), w3 = __ldg(wr + t + 3);
-          a = mac1<MODE>(a, p0, w0); a = mac1<MODE>(a, p1, w1); a = mac1<MODE>(a, p2, w2); a = mac1<MODE>(a, p3, w3);
-        }
-        for (; t < n; ++t) a = mac1<MODE>(a, trow[((l + t) ^ s7) << 2], __ldg(wr + t));
-        byte = to_u8_fast(a);
-      }
-      reinterpret_cast<uint8_t*>(dst)[((size_t)(row0 + r) * dw + ox) * 4 + c] = (uint8_t)byte;
-    }
-  }
-}
-
-// vertical pass with the slide table: A accumulator slots (A / 2 register pairs) per column and channel
+// vertical pass with the slide table, A accumulator slots (A / 2 register pairs) per column and channel: consumes
+// source rows until the strip holds kStripRows finished rows or the last output row is out
 template <int MODE, int A>
-__device__ __forceinline__ void shrink_tile_slide(const uint8_t* __restrict__ img, size_t pitch, const Tile& t,
-                                                  const pxz_block_desc& d, const AxisTab& tx, const AxisTab& ty,
-                                                  const uint32_t* __restrict__ pool, float4* strip, uint8_t* __restrict__ payload,
-                                                  const TapK& k) {
+__device__ __forceinline__ void shrink_vrun(ShrinkRun<MODE>& st, const uint8_t* tile0, size_t pitch, uint32_t sw, uint32_t sh,
+                                            uint32_t dh, float4* strip, uint32_t* ring, const TapK& k) {
   constexpr int NC = (MODE & 1) ? 4 : 3;
   constexpr int NP = A / 2;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t sw = t.tw, sh = t.th, dw = d.w, dh = d.h;
-  const bool has0 = lane < sw, has1 = lane + 32 < sw;
-  const uint8_t* col0 = img + (size_t)t.y0 * pitch + (size_t)(t.x0 + lane) * 4;
-  u64 acc[2][NC][NP];
-#pragma unroll
-  for (int c = 0; c < NC; ++c)
-#pragma unroll
-    for (int j = 0; j < NP; ++j) acc[0][c][j] = acc[1][c][j] = 0ull;
-  const ulonglong2* wrow = reinterpret_cast<const ulonglong2*>(pool + ty.soff);
-  const uint32_t* done = pool + ty.soff + 8 * ty.n_in;
-  uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset);
-  uint32_t o_next = 0, slot = 0, batch0 = 0;
-
-  auto emit = [&]() {
-    float4 v0, v1;
-    switch (slot) {
-      case 0: take_slot<MODE, NP, 0>(acc, v0, v1); break;
-      case 1: take_slot<MODE, NP, 1>(acc, v0, v1); break;
-      case 2: if (A > 2) take_slot<MODE, NP, (A > 2 ? 2 : 0)>(acc, v0, v1); break;
-      case 3: if (A > 2) take_slot<MODE, NP, (A > 2 ? 3 : 0)>(acc, v0, v1); break;
-      case 4: if (A > 4) take_slot<MODE, NP, (A > 4 ? 4 : 0)>(acc, v0, v1); break;
-      default: if (A > 4) take_slot<MODE, NP, (A > 4 ? 5 : 0)>(acc, v0, v1); break;
+  const uint32_t crow = lane >> 4, cchunk = lane & 15u;
+  const bool ccol = cchunk * 4 < sw;
+  for (;;) {
+    while (st.pend > 0 && st.o_next - st.batch0 < (uint32_t)kStripRows) {
+      float4 v0, v1;
+      switch (st.slot) {
+        case 0: take_slot3<MODE, NP, 0>(st.acc, v0, v1); break;
+        case 1: take_slot3<MODE, NP, 1>(st.acc, v0, v1); break;
+        case 2: if (A > 2) take_slot3<MODE, NP, (A > 2 ? 2 : 0)>(st.acc, v0, v1); break;
+        case 3: if (A > 2) take_slot3<MODE, NP, (A > 2 ? 3 : 0)>(st.acc, v0, v1); break;
+        case 4: if (A > 4) take_slot3<MODE, NP, (A > 4 ? 4 : 0)>(st.acc, v0, v1); break;
+        default: if (A > 4) take_slot3<MODE, NP, (A > 4 ? 5 : 0)>(st.acc, v0, v1); break;
+      }
+      float4* srow = strip + (st.o_next - st.batch0) * kStripStride + 2 * lane;
+      srow[0] = v0;
+      srow[1] = v1;
+      ++st.o_next;
+      st.slot = (st.slot + 1 == (uint32_t)A) ? 0u : st.slot + 1;
+      --st.pend;
     }
-    const uint32_t rr = o_next - batch0;
-    strip[rr * kStripStride + (lane ^ (rr & 7u))] = v0;
-    strip[rr * kStripStride + 32 + (lane ^ (rr & 7u))] = v1;
-    ++o_next;
-    slot = (slot + 1 == (uint32_t)A) ? 0u : slot + 1;
-    if (o_next - batch0 == (uint32_t)kStripRows || o_next == dh) {
+    if (st.o_next - st.batch0 == (uint32_t)kStripRows || st.o_next == dh) return;
+    const uint32_t r = st.r;
+    if ((r & 1u) == 0) {
+      cp_async_wait<kRingRows / 2 - 1>();  // the pair of rows (r, r + 1) has landed
       __syncwarp();
-      shrink_horizontal<MODE>(strip, batch0, o_next - batch0, dw, tx, pool, dst, k);
-      __syncwarp();
-      batch0 = o_next;
     }
-  };
-
-  // source rows run 4 ahead of the arithmetic through a small register queue
-  uint32_t qa[4], qb[4];
-  auto load_row = [&](uint32_t r, uint32_t& a, uint32_t& b) {
-    const uint8_t* p = col0 + (size_t)r * pitch;
-    a = (r < sh && has0) ? ldg_stream_u32(p) : 0u;
-    b = (r < sh && has1) ? ldg_stream_u32(p + 128) : 0u;
-  };
-#pragma unroll
-  for (int j = 0; j < 4; ++j) load_row((uint32_t)j, qa[j], qb[j]);
-#pragma unroll 1
-  for (uint32_t r = 0; r < sh; ++r) {
-    const uint32_t wa_ = qa[0], wb_ = qb[0];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { qa[j] = qa[j + 1]; qb[j] = qb[j + 1]; }
-    load_row(r + 4, qa[3], qb[3]);
+    const uint2 px = *reinterpret_cast<const uint2*>(ring + (r & (kRingRows - 1)) * 64 + 2 * lane);
     u64 w[NP];
-    const ulonglong2 wa = __ldg(wrow + 2 * r);
-    w[0] = wa.x;
-    if (NP > 1) w[NP > 1 ? 1 : 0] = wa.y;
-    if (NP > 2) w[NP > 2 ? 2 : 0] = __ldg(reinterpret_cast<const u64*>(wrow + 2 * r + 1));
-    const uint32_t nd = __ldg(done + r);
-    const float4 pa = px_to_f4<MODE>(wa_), pb = px_to_f4<MODE>(wb_);
+    w[0] = st.wa_n.x;
+    if (NP > 1) w[NP > 1 ? 1 : 0] = st.wa_n.y;
+    if (NP > 2) w[NP > 2 ? 2 : 0] = st.wb_n;
+    st.pend = st.nd_n;
+    st.wp += 2;
+    ++st.dp;
+    if (r + 1 < sh) {  // the table row of the next source row is requested before this row's arithmetic
+      st.wa_n = __ldg(st.wp);
+      if (NP > 2) st.wb_n = __ldg(reinterpret_cast<const u64*>(st.wp + 1));
+      st.nd_n = __ldg(st.dp);
+    }
+    const float4 pa = px_to_f4<MODE>(px.x), pb = px_to_f4<MODE>(px.y);
     const float ca[4] = {pa.x, pa.y, pa.z, pa.w}, cb[4] = {pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const u64 ppa = pk2(ca[c], ca[c]), ppb = pk2(cb[c], cb[c]);
 #pragma unroll
       for (int jp = 0; jp < NP; ++jp) {
-        acc[0][c][jp] = mac2<MODE>(acc[0][c][jp], ppa, w[jp], k);
-        acc[1][c][jp] = mac2<MODE>(acc[1][c][jp], ppb, w[jp], k);
+        st.acc[0][c][jp] = mac2<MODE>(st.acc[0][c][jp], ppa, w[jp], k);
+        st.acc[1][c][jp] = mac2<MODE>(st.acc[1][c][jp], ppb, w[jp], k);
       }
     }
-    for (uint32_t i = 0; i < nd; ++i) emit();
+    st.r = r + 1;
+    if ((st.r & 1u) == 0 || st.r == sh) {
+      // both rows of the pair are consumed: refill their ring slots with the pair 8 ahead
+      __syncwarp();
+      const uint32_t rn = ((st.r + 1) & ~1u) - 2 + kRingRows + crow;
+      if (rn < sh && ccol) cp_async_16(ring + (rn & (kRingRows - 1)) * 64 + cchunk * 4, tile0 + (size_t)rn * pitch + cchunk * 16);
+      cp_async_commit();
+    }
   }
 }
 
-// vertical pass for tables without a slide form (more than 6 outputs live at once): groups of 4 output rows walk
-// their source rows straight from global memory / L1
+// vertical pass for tables without a slide form (more than 6 outputs live at once): two groups of 4 output rows per
+// call walk their source rows straight from global memory / L1
 template <int MODE>
-__device__ __forceinline__ void shrink_tile_blocked(const uint8_t* __restrict__ img, size_t pitch, const Tile& t,
-                                                    const pxz_block_desc& d, const AxisTab& tx, const AxisTab& ty,
-                                                    const uint32_t* __restrict__ pool, float4* strip, uint8_t* __restrict__ payload,
+__device__ __forceinline__ void shrink_vrun_blocked(ShrinkRun<MODE>& st, const uint8_t* tile0, size_t pitch, uint32_t sw, uint32_t dh,
+                                                    const AxisTab& ty, const uint32_t* __restrict__ pool, float4* strip,
                                                     const TapK& k) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t sw = t.tw, dw = d.w, dh = d.h;
-  const bool has0 = lane < sw, has1 = lane + 32 < sw;
-  const uint8_t* col0 = img + (size_t)t.y0 * pitch + (size_t)(t.x0 + lane) * 4;
-  uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset);
+  const bool has = 2 * lane < sw;  // tile widths are multiples of 4 here
+  const uint8_t* col0 = tile0 + (size_t)lane * 8;
   const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(pool + ty.boff);
   const uint32_t* lo = pool + ty.boff + 4 * ty.brows_total;
   const uint32_t* rows = lo + ty.nb;
   const uint32_t* first = rows + ty.nb;
-  for (uint32_t ob = 0; ob < ty.nb; ++ob) {
-    const uint32_t n = __ldg(rows + ob), r0 = __ldg(lo + ob);
-    const ulonglong2* wp = w4 + __ldg(first + ob);
+  for (uint32_t j = 0; j < 2 && st.ob < ty.nb; ++j, ++st.ob) {
+    const uint32_t n = __ldg(rows + st.ob), r0 = __ldg(lo + st.ob);
+    const ulonglong2* wp = w4 + __ldg(first + st.ob);
     Acc4<MODE> a0, a1;
     for (uint32_t r = 0; r < n; ++r) {
-      const uint8_t* p = col0 + (size_t)(r0 + r) * pitch;
-      const uint32_t w0 = has0 ? __ldg(reinterpret_cast<const uint32_t*>(p)) : 0u;
-      const uint32_t w1 = has1 ? __ldg(reinterpret_cast<const uint32_t*>(p + 128)) : 0u;
+      const uint2 px = has ? __ldg(reinterpret_cast<const uint2*>(col0 + (size_t)(r0 + r) * pitch)) : make_uint2(0u, 0u);
       const ulonglong2 w = __ldg(wp + r);
-      a0.step(px_to_f4<MODE>(w0), w, k);
-      a1.step(px_to_f4<MODE>(w1), w, k);
+      a0.step(px_to_f4<MODE>(px.x), w, k);
+      a1.step(px_to_f4<MODE>(px.y), w, k);
     }
-    const uint32_t oy = ob * 4, rr = oy & (kStripRows - 1);
-    strip[(rr + 0) * kStripStride + (lane ^ ((rr + 0) & 7u))] = a0.out(0);
-    strip[(rr + 0) * kStripStride + 32 + (lane ^ ((rr + 0) & 7u))] = a1.out(0);
-    strip[(rr + 1) * kStripStride + (lane ^ ((rr + 1) & 7u))] = a0.out(1);
-    strip[(rr + 1) * kStripStride + 32 + (lane ^ ((rr + 1) & 7u))] = a1.out(1);
-    strip[(rr + 2) * kStripStride + (lane ^ ((rr + 2) & 7u))] = a0.out(2);
-    strip[(rr + 2) * kStripStride + 32 + (lane ^ ((rr + 2) & 7u))] = a1.out(2);
-    strip[(rr + 3) * kStripStride + (lane ^ ((rr + 3) & 7u))] = a0.out(3);
-    strip[(rr + 3) * kStripStride + 32 + (lane ^ ((rr + 3) & 7u))] = a1.out(3);
-    const uint32_t filled = min(oy + 4, dh);
-    if ((ob & 1u) || ob + 1 == ty.nb) {
-      const uint32_t row0 = oy & ~(uint32_t)(kStripRows - 1);
-      __syncwarp();
-      shrink_horizontal<MODE>(strip, row0, filled - row0, dw, tx, pool, dst, k);
-      __syncwarp();
-    }
+    float4* srow = strip + (j * 4) * kStripStride + 2 * lane;
+    srow[0] = a0.out(0); srow[1] = a1.out(0);
+    srow[kStripStride] = a0.out(1); srow[kStripStride + 1] = a1.out(1);
+    srow[2 * kStripStride] = a0.out(2); srow[2 * kStripStride + 1] = a1.out(2);
+    srow[3 * kStripStride] = a0.out(3); srow[3 * kStripStride + 1] = a1.out(3);
+    st.o_next = min(dh, st.o_next + 4);
   }
+}
+
+template <int MODE>
+__device__ __forceinline__ void shrink_tile_warp(const uint8_t* __restrict__ img, size_t pitch, const Tile& t,
+                                                 const pxz_block_desc& d, const HTab& ht, const AxisTab& ty,
+                                                 const uint32_t* __restrict__ pool, float4* strip, uint32_t* ring,
+                                                 uint8_t* __restrict__ payload, const TapK& k) {
+  constexpr int NC = (MODE & 1) ? 4 : 3;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t sw = t.tw, sh = t.th, dw = d.w, dh = d.h;
+  const uint8_t* tile0 = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset);
+  ShrinkRun<MODE> st;
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) st.acc[0][c][j] = st.acc[1][c][j] = 0ull;
+  st.wp = reinterpret_cast<const ulonglong2*>(pool + ty.soff);
+  st.dp = pool + ty.soff + 8 * ty.n_in;
+  st.r = 0; st.pend = 0; st.o_next = 0; st.slot = 0; st.batch0 = 0; st.ob = 0;
+  st.wa_n = make_ulonglong2(0ull, 0ull); st.wb_n = 0ull; st.nd_n = 0;
+  const uint32_t slots = ty.slots;
+  if (slots) {
+    // cp.async ring: pair g = source rows 2g, 2g+1 (lanes 0-15 / 16-31 copy 16 bytes each); 8 pairs in flight
+    const uint32_t crow = lane >> 4, cchunk = lane & 15u;
+#pragma unroll
+    for (int g = 0; g < kRingRows / 2; ++g) {
+      const uint32_t r = 2 * g + crow;
+      if (r < sh && cchunk * 4 < sw) cp_async_16(ring + r * 64 + cchunk * 4, tile0 + (size_t)r * pitch + cchunk * 16);
+      cp_async_commit();
+    }
+    st.wa_n = __ldg(st.wp);
+    st.wb_n = slots > 4 ? __ldg(reinterpret_cast<const u64*>(st.wp + 1)) : 0ull;
+    st.nd_n = __ldg(st.dp);
+  }
+  while (st.o_next < dh) {
+    switch (slots) {
+      case 2: shrink_vrun<MODE, 2>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
+      case 4: shrink_vrun<MODE, 4>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
+      case 6: shrink_vrun<MODE, 6>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
+      default: shrink_vrun_blocked<MODE>(st, tile0, pitch, sw, dh, ty, pool, strip, k); break;
+    }
+    __syncwarp();
+    shrink_horizontal<MODE>(strip, st.batch0, st.o_next - st.batch0, dw, ht, dst, k);
+    __syncwarp();
+    st.batch0 = st.o_next;
+  }
+  if (slots) cp_async_wait<0>();
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kWarpCtaThreads) k_shrink_warp(const uint8_t* __restrict__ img, size_t pitch, Geom g,
-                                                                 const pxz_block_desc* __restrict__ descs,
-                                                                 const uint32_t* __restrict__ tabidx,
-                                                                 const uint8_t* __restrict__ opaque_flags, uint8_t* __restrict__ payload,
-                                                                 const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool,
-                                                                 uint32_t* counter, float rt_one, float rt_negzero) {
-  extern __shared__ float4 s_strip[];
-  float4* strip = s_strip + (threadIdx.x >> 5) * kShrinkStripPx;
+__global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shrink_warp(
+    const uint8_t* __restrict__ img, size_t pitch, Geom g, const pxz_block_desc* __restrict__ descs,
+    const uint32_t* __restrict__ tabidx, const uint8_t* __restrict__ opaque_flags, uint8_t* __restrict__ payload,
+    const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool, uint32_t* counter, float rt_one, float rt_negzero) {
+  extern __shared__ float4 s_warp[];
+  float4* strip = s_warp + (threadIdx.x >> 5) * (kShrinkWarpBytes / 16);
+  uint32_t* ring = reinterpret_cast<uint32_t*>(strip + kStripRows * kStripStride);
+  uint32_t* htab_smem = ring + kRingRows * 64;
   const TapK k = make_tapk(rt_one, rt_negzero);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kWarpsPerCta;
+  const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kShrinkWarps;
   constexpr int F = FUSED ? 2 : 0;
-  for (;;) {
-    const uint32_t b = next_tile(counter, ntiles, total_warps);
-    if (b >= ntiles) break;
+  // Tiles are handed out twice: the first sweep takes the expensive ones (8 or more output rows), the second the
+  // rest, so the kernel does not end on a few warps that drew a 20-microsecond tile last.
+  auto process = [&](uint32_t v, const pxz_block_desc& d, uint32_t ti) {
+    const uint32_t b = v < ntiles ? v : v - ntiles;
     const Tile t = tile_of(g, b);
-    const pxz_block_desc d = descs[b];
-    if (d.w == 0 || d.h == 0) continue;  // masked out (quadtree levels)
+    if (d.w == 0 || d.h == 0) return;  // masked out (quadtree levels)
+    const bool heavy = d.h >= 8 && !(d.w == t.tw && d.h == t.th);
+    if (heavy != (v < ntiles)) return;
     if (d.w == t.tw && d.h == t.th) {
-      // block.rs:279-281: clone.  The block is contiguous in the payload.
-      const uint8_t* src = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset);
-      for (uint32_t r0 = 0; r0 < t.th; r0 += 4) {
-        uint32_t v0[4], v1[4];
+      // block.rs:279-281: clone.  The block is contiguous in the payload (4-byte aligned only).  Two rows per
+      // instruction, 16 bytes per lane, 16 rows in flight.
+      const uint32_t rr = lane >> 4, ch = lane & 15u;
+      const bool has = ch * 4 < t.tw;
+      const uint8_t* src = img + (size_t)(t.y0 + rr) * pitch + (size_t)t.x0 * 4 + ch * 16;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(payload + d.offset) + ch * 4;
+      for (uint32_t r0 = 0; r0 < t.th; r0 += 16) {
+        uint4 v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint8_t* p = src + (size_t)(r0 + j) * pitch + lane * 4;
-          v0[j] = (r0 + j < t.th && lane < t.tw) ? ldg_stream_u32(p) : 0u;
-          v1[j] = (r0 + j < t.th && lane + 32 < t.tw) ? ldg_stream_u32(p + 128) : 0u;
-        }
+        for (int j = 0; j < 8; ++j)
+          v[j] = (r0 + 2 * j + rr < t.th && has) ? ldg_nc_v4(src + (size_t)(r0 + 2 * j) * pitch) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (r0 + j < t.th && lane < t.tw) dst[(size_t)(r0 + j) * t.tw + lane] = v0[j];
-          if (r0 + j < t.th && lane + 32 < t.tw) dst[(size_t)(r0 + j) * t.tw + lane + 32] = v1[j];
+        for (int j = 0; j < 8; ++j) {
+          if (r0 + 2 * j + rr < t.th && has) {
+            uint32_t* o = dst + (size_t)(r0 + 2 * j + rr) * t.tw;
+            o[0] = v[j].x; o[1] = v[j].y; o[2] = v[j].z; o[3] = v[j].w;
+          }
         }
       }
-      continue;
+      return;
     }
-    const uint32_t ti = tabidx[b];
-    const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
+    const AxisTab ty = tabs[ti >> 16];
+    __syncwarp();  // the previous tile's horizontal pass is done with the table copy
+    const HTab ht = stage_htab(tabs[ti & 0xFFFFu], d.w, pool, htab_smem);
+    __syncwarp();
     const bool opaque = opaque_flags != nullptr && opaque_flags[b] != 0;
-    if (opaque) {
-      switch (ty.slots) {
-        case 2: shrink_tile_slide<F, 2>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-        case 4: shrink_tile_slide<F, 4>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-        case 6: shrink_tile_slide<F, 6>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-        default: shrink_tile_blocked<F>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-      }
-    } else {
-      switch (ty.slots) {
-        case 2: shrink_tile_slide<F | 1, 2>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-        case 4: shrink_tile_slide<F | 1, 4>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-        case 6: shrink_tile_slide<F | 1, 6>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-        default: shrink_tile_blocked<F | 1>(img, pitch, t, d, tx, ty, pool, strip, payload, k); break;
-      }
-    }
+    if (opaque) shrink_tile_warp<F>(img, pitch, t, d, ht, ty, pool, strip, ring, payload, k);
+    else shrink_tile_warp<F | 1>(img, pitch, t, d, ht, ty, pool, strip, ring, payload, k);
+  };
+  // the next tile's index, descriptor and table indices are requested while the current tile is processed
+  const uint32_t nv = 2 * ntiles;
+#ifdef PXZ_WARP_STATS
+  const unsigned long long t_start = globaltimer_ns();
+  unsigned long long t_sweep2 = 0;
+  uint32_t drawn = 0;
+#endif
+  uint32_t v = next_tile(counter, nv, total_warps);
+  pxz_block_desc d{};
+  uint32_t ti = 0;
+  if (v < nv) { d = descs[v < ntiles ? v : v - ntiles]; ti = tabidx[v < ntiles ? v : v - ntiles]; }
+  while (v < nv) {
+    const uint32_t vn = next_tile(counter, nv, total_warps);
+    pxz_block_desc dn{};
+    uint32_t tin = 0;
+    if (vn < nv) { dn = descs[vn < ntiles ? vn : vn - ntiles]; tin = tabidx[vn < ntiles ? vn : vn - ntiles]; }
+#ifdef PXZ_WARP_STATS
+    if (v >= ntiles && t_sweep2 == 0) t_sweep2 = globaltimer_ns();
+    ++drawn;
+#endif
+    process(v, d, ti);
+    v = vn; d = dn; ti = tin;
   }
+#ifdef PXZ_WARP_STATS
+  if (lane == 0) {
+    const uint32_t w = blockIdx.x * kShrinkWarps + (threadIdx.x >> 5);
+    g_warp_stats[4 * w + 0] = t_start;
+    g_warp_stats[4 * w + 1] = globaltimer_ns();
+    g_warp_stats[4 * w + 2] = t_sweep2;
+    g_warp_stats[4 * w + 3] = drawn;
+  }
+#endif
 }
 
 // ---- expand ------------------------------------------------------------------------------------------------------
-// shared-memory column of intermediate sample c: odd 8-column groups flip bit 0, so that the stride-2 reads of a 2x
-// upscale (8 lanes -> 16 columns) land in 8 different 16-byte banks
-__device__ __forceinline__ uint32_t ecol(uint32_t c) { return c ^ ((c >> 3) & 1u); }
+// fixed-length walk of the horizontal pass (the table stores every group with STEPS rows, +0 weights beyond its own)
+template <int MODE, int STEPS>
+__device__ __forceinline__ void expand_walk(Acc4<MODE>& acc, const float4* tp, const ulonglong2 (&w)[8], const TapK& k) {
+#pragma unroll
+  for (int c = 0; c < STEPS; ++c) acc.step(tp[c], w[c], k);
+}
 
 template <int MODE>
 __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size_t pitch, const Tile& t, const pxz_block_desc& d,
                                                  const AxisTab& tx, const AxisTab& ty, const uint32_t* __restrict__ pool,
                                                  float4* strip, const uint8_t* __restrict__ payload, const TapK& k) {
+  constexpr int NC = (MODE & 1) ? 4 : 3;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t sw = d.w, sh = d.h, dw = t.tw, dh = t.th;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(payload + d.offset);
   uint8_t* dst = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
   const float4* g8 = reinterpret_cast<const float4*>(pool + ty.goff);
   const uint32_t* gleft = pool + ty.goff + 8 * ty.n_out;
+  const ulonglong2* gp = reinterpret_cast<const ulonglong2*>(pool + ty.gpoff);
+  // second strip row: offset so that the 8 lanes of a shared-memory phase (4 groups x 2 rows) hit 8 different banks:
+  // a 2x upscale reads every other column (odd offset), wider ratios read adjacent columns (offset 4)
+  const uint32_t row1 = 64 + ((tx.n_out == 2 * tx.n_in) ? 1u : 4u);
 
-  // horizontal: lane = (strip row, group of 4 outputs); fixed for the whole tile
-  const uint32_t hr = lane >> 4, ob = lane & 15u;
+  // horizontal: lane = (group of 4 outputs, strip row); fixed for the whole tile
+  const uint32_t hr = lane & 1u, ob = lane >> 1;
   const bool hact = ob < tx.nb;
   const uint32_t* blo = pool + tx.boff + 4 * tx.brows_total;
-  const uint32_t hn = hact ? __ldg(blo + tx.nb + ob) : 0u, hc0 = hact ? __ldg(blo + ob) : 0u;
+  const uint32_t hn = hact ? __ldg(blo + tx.nb + ob) : 0u;
+  const float4* htp = strip + hr * row1 + (hact ? __ldg(blo + ob) : 0u);
   const ulonglong2* hw = reinterpret_cast<const ulonglong2*>(pool + tx.boff) + (hact ? __ldg(blo + 2 * tx.nb + ob) : 0u);
   const uint32_t hox = ob * 4, hvalid = hact ? min(4u, dw - hox) : 0u;
+  const uint32_t bpad = tx.bpad;
+  // the walk of this lane's group is the same for every row of the tile: its weights stay in registers
+  ulonglong2 hwr[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) hwr[c] = (hact && (uint32_t)c < bpad) ? __ldg(hw + c) : make_ulonglong2(0ull, 0ull);
   auto horizontal = [&](uint32_t oy0, uint32_t nrows) {
     if (hact && hr < nrows) {
-      const float4* trow = strip + hr * kStripStride;
       Acc4<MODE> acc;
-      uint32_t c = 0;
-      for (; c + 2 <= hn; c += 2) {
-        const float4 p0 = trow[ecol(hc0 + c)], p1 = trow[ecol(hc0 + c + 1)];
-        const ulonglong2 w0 = __ldg(hw + c), w1 = __ldg(hw + c + 1);
-        acc.step(p0, w0, k);
-        acc.step(p1, w1, k);
-      }
-      if (c < hn) acc.step(trow[ecol(hc0 + c)], __ldg(hw + c), k);
+      if (bpad == 8) expand_walk<MODE, 8>(acc, htp, hwr, k);
+      else if (bpad == 4) expand_walk<MODE, 4>(acc, htp, hwr, k);
+      else if (bpad == 2) expand_walk<MODE, 2>(acc, htp, hwr, k);
+      else
+        for (uint32_t c = 0; c < hn; ++c) acc.step(htp[c], __ldg(hw + c), k);
       uint32_t* o = reinterpret_cast<uint32_t*>(dst + (size_t)(oy0 + hr) * pitch) + hox;
       const uint32_t p0 = pack_px<MODE>(acc.out(0)), p1 = pack_px<MODE>(acc.out(1));
       const uint32_t p2 = pack_px<MODE>(acc.out(2)), p3 = pack_px<MODE>(acc.out(3));
@@ -358,46 +480,75 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
   };
 
   if (sw <= 32) {
-    // vertical: lane = source column (two row groups when the block is at most 16 wide); 7-row window of converted
-    // samples in registers, advanced as the outputs' first tap moves down
-    const bool two = sw <= 16;
-    const uint32_t x = two ? (lane & 15u) : lane, rg = two ? (lane >> 4) : 0u;
+    // vertical: lane = source column; a 7-row window of converted samples lives in registers and moves down with the
+    // outputs' first tap.  Two output rows with the same first tap are the two lanes of one f32x2 accumulator.
+    const uint32_t x = lane;
     const bool vact = x < sw;
-    u64 wrg[7], wba[7];
-    float wbl[7];
-    auto conv = [&](uint32_t word, u64& rgp, u64& bap, float& bl) {
+    float win[7][NC];
+    auto conv = [&](uint32_t word, float(&o)[NC]) {
       const float4 p = px_to_f4<MODE>(word);
-      rgp = pk2(p.x, p.y);
-      bap = pk2(p.z, p.w);
-      bl = p.z;
+      o[0] = p.x; o[1] = p.y; o[2] = p.z;
+      if (NC > 3) o[NC > 3 ? 3 : 0] = p.w;
     };
 #pragma unroll
-    for (int j = 0; j < 7; ++j) conv((vact && (uint32_t)j < sh) ? __ldg(src + (size_t)j * sw + x) : 0u, wrg[j], wba[j], wbl[j]);
+    for (int j = 0; j < 7; ++j) conv((vact && (uint32_t)j < sh) ? __ldg(src + (size_t)j * sw + x) : 0u, win[j]);
     uint32_t L = 0;
     uint32_t nextpx = (vact && 7 < sh) ? __ldg(src + (size_t)7 * sw + x) : 0u;
-    auto vrow = [&](uint32_t oy, uint32_t srow) {
-      const uint32_t left = __ldg(gleft + oy);
+    auto advance = [&](uint32_t left) {
       while (L < left) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) { wrg[j] = wrg[j + 1]; wba[j] = wba[j + 1]; wbl[j] = wbl[j + 1]; }
-        conv(nextpx, wrg[6], wba[6], wbl[6]);
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) win[j][c] = win[j + 1][c];
+        conv(nextpx, win[6]);
         ++L;
         nextpx = (vact && L + 7 < sh) ? __ldg(src + (size_t)(L + 7) * sw + x) : 0u;
       }
+    };
+    auto vrow_solo = [&](uint32_t oy, uint32_t soff) {
+      advance(__ldg(gleft + oy));
       const float4 wa = __ldg(g8 + 2 * oy), wb = __ldg(g8 + 2 * oy + 1);
       const float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
-      Acc1<MODE> acc;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 7; ++j) acc.step(wrg[j], wba[j], wbl[j], w[j], k);
-      if (vact) strip[srow * kStripStride + ecol(x)] = acc.out();
+      for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a[c] = mac1<MODE>(a[c], win[j][c], w[j]);
+      if (vact) strip[soff + x] = make_float4(a[0], a[1], a[2], a[3]);
     };
+    // table rows of the next pair of output rows are requested before the horizontal pass of the current pair
+    ulonglong2 n01 = __ldg(gp), n23 = __ldg(gp + 1), n45 = __ldg(gp + 2), n67 = __ldg(gp + 3);
+    uint32_t nla = __ldg(gleft), nlb = dh > 1 ? __ldg(gleft + 1) : nla;
     for (uint32_t oy0 = 0; oy0 < dh; oy0 += 2) {
       const uint32_t nrows = min(2u, dh - oy0);
-      if (two) {
-        if (rg < nrows) vrow(oy0 + rg, rg);
+      const uint32_t la = nla, lb = nlb;
+      const ulonglong2 w01 = n01, w23 = n23, w45 = n45, w67 = n67;
+      if (oy0 + 2 < dh) {
+        const ulonglong2* wn = gp + 4 * ((oy0 >> 1) + 1);
+        n01 = __ldg(wn); n23 = __ldg(wn + 1); n45 = __ldg(wn + 2); n67 = __ldg(wn + 3);
+        nla = __ldg(gleft + oy0 + 2);
+        nlb = oy0 + 3 < dh ? __ldg(gleft + oy0 + 3) : nla;
+      }
+      if (la == lb) {
+        advance(la);
+        const u64 w[7] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x};
+        u64 a[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a[c] = 0ull;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) a[c] = mac2<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
+        if (vact) {
+          float lo_[4] = {0.f, 0.f, 0.f, 0.f}, hi_[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < NC; ++c) unpk2(a[c], lo_[c], hi_[c]);
+          strip[x] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
+          strip[row1 + x] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
+        }
       } else {
-        vrow(oy0, 0);
-        if (nrows > 1) vrow(oy0 + 1, 1);
+        vrow_solo(oy0, 0);
+        vrow_solo(oy0 + 1, row1);
       }
       __syncwarp();
       horizontal(oy0, nrows);
@@ -412,16 +563,20 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
       for (uint32_t r = 0; r < nrows; ++r) {
         const uint32_t oy = oy0 + r, left = __ldg(gleft + oy), n = __ldg(lcnt + oy);
         const float* w = reinterpret_cast<const float*>(g8 + 2 * oy);
-        Acc1<MODE> a0, a1;
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
         for (uint32_t j = 0; j < n; ++j) {
           const float wj = __ldg(w + j);
           const float4 p0 = px_to_f4<MODE>(has0 ? __ldg(src + (size_t)(left + j) * sw + lane) : 0u);
           const float4 p1 = px_to_f4<MODE>(has1 ? __ldg(src + (size_t)(left + j) * sw + lane + 32) : 0u);
-          a0.step(pk2(p0.x, p0.y), pk2(p0.z, p0.w), p0.z, wj, k);
-          a1.step(pk2(p1.x, p1.y), pk2(p1.z, p1.w), p1.z, wj, k);
+          const float c0[4] = {p0.x, p0.y, p0.z, p0.w}, c1[4] = {p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            a0[c] = mac1<MODE>(a0[c], c0[c], wj);
+            a1[c] = mac1<MODE>(a1[c], c1[c], wj);
+          }
         }
-        if (has0) strip[r * kStripStride + ecol(lane)] = a0.out();
-        if (has1) strip[r * kStripStride + ecol(lane + 32)] = a1.out();
+        if (has0) strip[r * row1 + lane] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+        if (has1) strip[r * row1 + lane + 32] = make_float4(a1[0], a1[1], a1[2], a1[3]);
       }
       __syncwarp();
       horizontal(oy0, nrows);
@@ -431,42 +586,43 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kWarpCtaThreads) k_expand_warp(uint8_t* __restrict__ img, size_t pitch, Geom g,
-                                                                 const pxz_block_desc* __restrict__ descs,
-                                                                 const uint32_t* __restrict__ tabidx, const uint8_t* __restrict__ payload,
-                                                                 const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool,
-                                                                 uint32_t* counter, float rt_one, float rt_negzero) {
-  extern __shared__ float4 s_strip[];
-  float4* strip = s_strip + (threadIdx.x >> 5) * kExpandStripPx;
+__global__ void __launch_bounds__(kWarpCtaThreads, PXZ_EXPAND_WARP_CTAS) k_expand_warp(
+    uint8_t* __restrict__ img, size_t pitch, Geom g, const pxz_block_desc* __restrict__ descs,
+    const uint32_t* __restrict__ tabidx, const uint8_t* __restrict__ payload, const AxisTab* __restrict__ tabs,
+    const uint32_t* __restrict__ pool, uint32_t* counter, float rt_one, float rt_negzero) {
+  extern __shared__ float4 s_warp[];
+  float4* strip = s_warp + (threadIdx.x >> 5) * (kExpandWarpBytes / 16);
   const TapK k = make_tapk(rt_one, rt_negzero);
   const uint32_t lane = threadIdx.x & 31u;
+  // the fixed-length walks read up to 7 strip entries past a group's own window: keep them finite (w = +0 there)
+  for (uint32_t i = lane; i < kExpandWarpBytes / 16; i += 32) strip[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
   const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kWarpsPerCta;
   constexpr int F = FUSED ? 2 : 0;
-  for (;;) {
-    const uint32_t b = next_tile(counter, ntiles, total_warps);
-    if (b >= ntiles) break;
+  // two sweeps over the tiles: resampled ones first, plain fills and copies last (short tail)
+  auto process = [&](uint32_t v, const pxz_block_desc& d, uint32_t ti) {
+    const uint32_t b = v < ntiles ? v : v - ntiles;
     const Tile t = tile_of(g, b);
-    const pxz_block_desc d = descs[b];
     const uint32_t sw = d.w, sh = d.h, dw = t.tw, dh = t.th;
-    if (sw == 0 || sh == 0) continue;  // masked out: the tile keeps what the output image already holds
+    if (sw == 0 || sh == 0) return;  // masked out: the tile keeps what the output image already holds
+    const bool heavy = !(sw == dw && sh == dh) && !(sw == 1 && sh == 1);
+    if (heavy != (v < ntiles)) return;
     uint8_t* dst = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(payload + d.offset);
     if (sw == dw && sh == dh) {
-      for (uint32_t r0 = 0; r0 < dh; r0 += 4) {
-        uint32_t v0[4], v1[4];
+      const bool has = 2 * lane < dw;
+      for (uint32_t r0 = 0; r0 < dh; r0 += 8) {
+        uint32_t v0[8], v1[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v0[j] = (r0 + j < dh && lane < dw) ? __ldg(src + (size_t)(r0 + j) * dw + lane) : 0u;
-          v1[j] = (r0 + j < dh && lane + 32 < dw) ? __ldg(src + (size_t)(r0 + j) * dw + lane + 32) : 0u;
+        for (int j = 0; j < 8; ++j) {
+          v0[j] = (r0 + j < dh && has) ? __ldcs(src + (size_t)(r0 + j) * dw + 2 * lane) : 0u;
+          v1[j] = (r0 + j < dh && has) ? __ldcs(src + (size_t)(r0 + j) * dw + 2 * lane + 1) : 0u;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t* o = reinterpret_cast<uint32_t*>(dst + (size_t)(r0 + j) * pitch);
-          if (r0 + j < dh && lane < dw) o[lane] = v0[j];
-          if (r0 + j < dh && lane + 32 < dw) o[lane + 32] = v1[j];
-        }
+        for (int j = 0; j < 8; ++j)
+          if (r0 + j < dh && has) *reinterpret_cast<uint2*>(dst + (size_t)(r0 + j) * pitch + lane * 8) = make_uint2(v0[j], v1[j]);
       }
-      continue;
+      return;
     }
     if (sw == 1 && sh == 1) {
       // every output has one tap of normalised weight w / w = 1.0 in both passes: the tile is the source pixel
@@ -479,14 +635,26 @@ __global__ void __launch_bounds__(kWarpCtaThreads) k_expand_warp(uint8_t* __rest
         if (x + 4 <= dw) *reinterpret_cast<uint4*>(o) = v;
         else for (uint32_t i = x; i < dw; ++i) reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch)[i] = p;
       }
-      continue;
+      return;
     }
-    const uint32_t ti = tabidx[b];
     const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
     uint32_t aand = 0xFF000000u;
     for (uint32_t i = lane; i < sw * sh; i += 32) aand &= __ldg(src + i);
     const bool opaque = __all_sync(0xffffffffu, (aand & 0xFF000000u) == 0xFF000000u) != 0;
     if (opaque) expand_tile_warp<F>(img, pitch, t, d, tx, ty, pool, strip, payload, k);
     else expand_tile_warp<F | 1>(img, pitch, t, d, tx, ty, pool, strip, payload, k);
+  };
+  const uint32_t nv = 2 * ntiles;
+  uint32_t v = next_tile(counter, nv, total_warps);
+  pxz_block_desc d{};
+  uint32_t ti = 0;
+  if (v < nv) { d = descs[v < ntiles ? v : v - ntiles]; ti = tabidx[v < ntiles ? v : v - ntiles]; }
+  while (v < nv) {
+    const uint32_t vn = next_tile(counter, nv, total_warps);
+    pxz_block_desc dn{};
+    uint32_t tin = 0;
+    if (vn < nv) { dn = descs[vn < ntiles ? vn : vn - ntiles]; tin = tabidx[vn < ntiles ? vn : vn - ntiles]; }
+    process(v, d, ti);
+    v = vn; d = dn; ti = tin;
   }
 }

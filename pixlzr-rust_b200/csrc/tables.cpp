@@ -117,6 +117,21 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
   const uint32_t nb = (n_out + 3) / 4;
   std::vector<uint32_t> lo(nb), rows(nb), first(nb);
   std::vector<uint32_t> w4;  // unique groups, 4 words per source sample
+  // upscale tables: every group is stored with the same number of rows (2, 4 or 8; +0 weights beyond its own), so the
+  // expand kernel runs a fixed, fully unrolled walk.  bpad = 0: groups keep their own length.
+  uint32_t bpad = 0;
+  if (n_in <= n_out) {
+    uint32_t longest = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+      uint32_t l = lefts[4 * b], h = 0;
+      for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
+        l = std::min(l, lefts[4 * b + j]);
+        h = std::max(h, lefts[4 * b + j] + counts[4 * b + j]);
+      }
+      longest = std::max(longest, h - l);
+    }
+    bpad = longest <= 2 ? 2u : longest <= 4 ? 4u : longest <= 8 ? 8u : 0u;
+  }
   for (uint32_t b = 0; b < nb; ++b) {
     uint32_t l = lefts[4 * b], h = 0;
     for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
@@ -125,14 +140,14 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
     }
     lo[b] = l;
     rows[b] = h - l;
-    std::vector<uint32_t> grp((size_t)rows[b] * 4, 0u);  // +0.0f everywhere
+    std::vector<uint32_t> grp((size_t)std::max(rows[b], bpad) * 4, 0u);  // +0.0f everywhere
     for (uint32_t j = 0; j < 4 && 4 * b + j < n_out; ++j) {
       const uint32_t o = 4 * b + j;
       for (uint32_t i = 0; i < counts[o]; ++i) grp[(size_t)(lefts[o] + i - l) * 4 + j] = (*pool)[wbase + (size_t)o * stride + i];
     }
     bool found = false;
     for (uint32_t p = 0; p < b && !found; ++p) {
-      if (rows[p] == rows[b] && std::equal(grp.begin(), grp.end(), w4.begin() + (size_t)first[p] * 4)) {
+      if (std::max(rows[p], bpad) == std::max(rows[b], bpad) && std::equal(grp.begin(), grp.end(), w4.begin() + (size_t)first[p] * 4)) {
         first[b] = first[p];
         found = true;
       }
@@ -156,7 +171,9 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
   tab->soff = 0;
   tab->slots = 0;
   tab->goff = 0xFFFFFFFFu;
-  tab->pad_ = 0;
+  tab->gpoff = 0;
+  tab->bpad = bpad;
+  tab->pad0_ = tab->pad1_ = tab->pad2_ = 0;
   auto weight_of = [&](uint32_t o, uint32_t i) {
     float w;
     memcpy(&w, &(*pool)[wbase + (size_t)o * stride + i], sizeof(float));
@@ -202,12 +219,20 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
   if (n_in <= n_out && stride <= 7) {  // the expand kernel keeps a 7-sample window
     while (pool->size() % 4) pool->push_back(0u);
     const size_t gbase = pool->size();
-    pool->resize(gbase + (size_t)n_out * 8 + n_out, 0u);
+    const uint32_t npairs = (n_out + 1) / 2;
+    const uint32_t lpad = (4u - (n_out % 4u)) % 4u;  // keep the pair rows 16-byte aligned
+    const size_t pbase = gbase + (size_t)n_out * 8 + n_out + lpad;
+    pool->resize(pbase + (size_t)npairs * 16, 0u);
     for (uint32_t o = 0; o < n_out; ++o) {
-      for (uint32_t i = 0; i < counts[o]; ++i) (*pool)[gbase + (size_t)o * 8 + i] = (*pool)[wbase + (size_t)o * stride + i];
+      for (uint32_t i = 0; i < counts[o]; ++i) {
+        const uint32_t wbits = (*pool)[wbase + (size_t)o * stride + i];
+        (*pool)[gbase + (size_t)o * 8 + i] = wbits;
+        (*pool)[pbase + (size_t)(o / 2) * 16 + 2 * i + (o & 1u)] = wbits;  // pair rows: (w_even[i], w_odd[i])
+      }
       (*pool)[gbase + (size_t)n_out * 8 + o] = lefts[o];
     }
     tab->goff = (uint32_t)gbase;
+    tab->gpoff = (uint32_t)pbase;
   }
   return true;
 }
