@@ -116,7 +116,8 @@ struct pxz_payload {
   Geom g;
   size_t nblocks_cap = 0;
   pxz_block_desc* d_descs = nullptr;
-  uint32_t* d_tabidx = nullptr;
+  uint32_t* d_tabidx = nullptr;  // [nblocks_cap] table indices, then the work-order lists (launch_plan) of capacity nblocks_cap
+  uint32_t* d_order() const { return d_tabidx + nblocks_cap; }
   uint8_t* d_pixels = nullptr;
   uint64_t capacity = 0;
   uint64_t* d_total = nullptr;
@@ -310,7 +311,7 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
                                 ts.ntabs, max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, opaque_flags,
-                                ctx->warp_kernels ? ctx->d_tile_counter : nullptr, ts.warp_ok, ctx->stream, ctx->sm_count,
+                                ctx->warp_kernels ? ctx->d_tile_counter : nullptr, p->d_order(), (uint32_t)p->nblocks_cap, ts.warp_ok, ctx->stream, ctx->sm_count,
                                 &ctx->launches));
   return PXZ_OK;
 }
@@ -665,7 +666,7 @@ static pxz_status payload_new(pxz_ctx* ctx, const Geom& g, uint64_t capacity, px
   p->nblocks_cap = nblocks;
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&p->d_descs, nblocks * sizeof(pxz_block_desc))) != PXZ_OK ||
-      (st = dev_alloc(ctx, (void**)&p->d_tabidx, nblocks * 4)) != PXZ_OK ||
+      (st = dev_alloc(ctx, (void**)&p->d_tabidx, (nblocks + order_list_words(nblocks)) * 4)) != PXZ_OK ||  // table indices | work order lists
       (st = dev_alloc(ctx, (void**)&p->d_pixels, capacity)) != PXZ_OK ||
       (st = dev_alloc(ctx, (void**)&p->d_total, 8)) != PXZ_OK) {
     // partial allocations must not enter the cache
@@ -736,7 +737,7 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   {
     ProfScope prof(ctx, K_PLAN);
     e = launch_plan(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, g, vm, ctx->d_minmax, ctx->thr, nullptr,
-                    p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, ctx->stream, &ctx->launches);
+                    p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, p->d_order(), (uint32_t)p->nblocks_cap, ctx->stream, &ctx->launches);
   }
   if (e != cudaSuccess) {
     payload_release(p);
@@ -904,6 +905,9 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_tabidx, tabidx.data(), nblocks * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(p->d_pixels, pixels, bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_total, &p->bytes, 8, cudaMemcpyHostToDevice, ctx->stream);
+  // work order of the expand kernel (blocks by cost class)
+  if (e == cudaSuccess && ensure_scratch(ctx, (uint32_t)nblocks) != PXZ_OK) e = cudaErrorMemoryAllocation;
+  if (e == cudaSuccess) e = launch_class_lists(p->d_descs, g, ctx->d_scan, p->d_order(), (uint32_t)p->nblocks_cap, ctx->stream, &ctx->launches);
   // tabidx is a pageable temporary and `pixels` may be reused by the caller right away
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
@@ -997,8 +1001,8 @@ pxz_status pxz_tree_process(pxz_ctx* ctx, const pxz_image* img, float threshold,
     p->max_tmp_down = ((g.bh + 1) / 2) * pad8(g.bw);
     p->max_tmp_up = g.bh * pad8((g.bw + 1) / 2);
     vm.extra_thr = NAN;
-    e = launch_plan(ctx->d_vx, nullptr, g, vm, ctx->d_minmax, ctx->thr, d_leaf, p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan,
-                    ctx->stream, &ctx->launches);
+    e = launch_plan(ctx->d_vx, nullptr, g, vm, ctx->d_minmax, ctx->thr, d_leaf, p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, p->d_order(),
+                    (uint32_t)p->nblocks_cap, ctx->stream, &ctx->launches);
     if (e != cudaSuccess) st = fail(ctx, PXZ_E_CUDA, std::string("plan: ") + cudaGetErrorString(e));
     TabSet ts;
     if (st == PXZ_OK) st = get_tabset(ctx, *p->spec, (int)filter_down, 0, &ts);

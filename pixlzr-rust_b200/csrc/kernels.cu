@@ -823,6 +823,16 @@ __global__ void __launch_bounds__(1024) k_minmax(const float* __restrict__ vx, c
 // plan: reduce_image_section minus the resize (operations.rs:140-156) + exclusive scan of the
 // payload sizes (single pass, decoupled look-back), producing the descriptor table.
 // ------------------------------------------------------------------------------------------------
+// Cost class of a block for the resample kernels' work order (0 = most expensive): by the larger reduced side, then
+// plain copies, then blocks a quadtree level masked out.
+constexpr int kCostClasses = 8;
+__device__ __forceinline__ uint32_t cost_class(uint32_t w, uint32_t h, uint32_t tw, uint32_t th) {
+  if (w == 0 || h == 0) return 7u;
+  if (w == tw && h == th) return 6u;
+  const uint32_t k = 31u - __clz(max(w, h));  // 0..6 for sides 1..64
+  return k >= 5u ? 0u : 5u - k;
+}
+
 constexpr int kPlanItems = 1;
 constexpr int kPlanTile = kThreads * kPlanItems;
 
@@ -836,8 +846,11 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
                                                    ValueMap vm, const float* __restrict__ minmax, LevelThresholds thr,
                                                    const uint8_t* __restrict__ mask, pxz_block_desc* __restrict__ descs,
                                                    uint32_t* __restrict__ tabidx,
-                                                   unsigned long long* __restrict__ total, ScanState* st) {
+                                                   unsigned long long* __restrict__ total, ScanState* st,
+                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ lists, uint32_t cap) {
   __shared__ unsigned int s_tile;
+  __shared__ uint32_t s_hist[kCostClasses], s_base[kCostClasses];
+  if (threadIdx.x < kCostClasses) s_hist[threadIdx.x] = 0;
   __shared__ unsigned long long s_warp[kThreads / 32];
   __shared__ unsigned long long s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -875,6 +888,25 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
       sz[j] = (unsigned long long)dw[j] * dh[j] * g.C;
       tsum += sz[j];
     }
+  }
+  __syncthreads();
+  // work order of the resample kernels: per cost class a list of block indices (lists[c * cap ...]); a block's slot is
+  // the class cursor this CTA reserved plus its rank inside the CTA.  Order inside a class does not matter.
+  uint32_t cls[kPlanItems], rank[kPlanItems];
+#pragma unroll
+  for (int j = 0; j < kPlanItems; ++j) {
+    const uint32_t b = first + j;
+    cls[j] = 0; rank[j] = 0;
+    if (b < nblocks) {
+      const Tile t = tile_of(g, b);
+      cls[j] = cost_class(dw[j], dh[j], t.tw, t.th);
+      rank[j] = atomicAdd(&s_hist[cls[j]], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid < kCostClasses) {
+    s_base[tid] = s_hist[tid] ? atomicAdd(&cursor[tid], s_hist[tid]) : 0u;
+    __threadfence();  // reserved before this CTA's scan status is published (the last CTA reads the final cursors)
   }
   // block-wide exclusive scan of tsum
   unsigned long long inc = tsum;
@@ -914,7 +946,11 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
       status[tile] = (2ull << 62) | (prefix + agg);
     }
     s_prefix = prefix;
-    if ((tile + 1) * (uint32_t)kPlanTile >= nblocks) *total = prefix + agg;
+    if ((tile + 1) * (uint32_t)kPlanTile >= nblocks) {
+      *total = prefix + agg;
+      // every other CTA has published its status, hence reserved its slots: the cursors are final
+      for (int c = 0; c < kCostClasses; ++c) lists[(size_t)kCostClasses * cap + c] = atomicAdd(&cursor[c], 0u);
+    }
   }
   __syncthreads();
   excl += s_prefix;
@@ -929,6 +965,7 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
       d.h = (uint16_t)dh[j];
       descs[b] = d;
       tabidx[b] = tix[j];
+      lists[(size_t)cls[j] * cap + s_base[cls[j]] + rank[j]] = b;
       excl += sz[j];
     }
   }
@@ -1634,6 +1671,34 @@ __global__ void __launch_bounds__(kThreads, PXZ_RESAMPLE_MINBLOCKS) k_expand_rgb
   }
 }
 
+// ---- work order of the warp-per-tile resample kernels for descriptors that came from the host (k_plan does the same
+// for its own): cursor[0..7] class cursors, cursor[8] = CTAs done; all zero on entry
+__global__ void __launch_bounds__(kThreads) k_class_lists(const pxz_block_desc* __restrict__ descs, Geom g, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ lists, uint32_t cap) {
+  __shared__ uint32_t s_hist[kCostClasses], s_base[kCostClasses];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nblocks = g.cols * g.rows;
+  if (tid < kCostClasses) s_hist[tid] = 0;
+  __syncthreads();
+  const uint32_t b = blockIdx.x * kThreads + tid;
+  uint32_t cls = 0, rank = 0;
+  if (b < nblocks) {
+    const Tile t = tile_of(g, b);
+    const pxz_block_desc d = descs[b];
+    cls = cost_class(d.w, d.h, t.tw, t.th);
+    rank = atomicAdd(&s_hist[cls], 1u);
+  }
+  __syncthreads();
+  if (tid < kCostClasses) s_base[tid] = s_hist[tid] ? atomicAdd(&cursor[tid], s_hist[tid]) : 0u;
+  __syncthreads();
+  if (b < nblocks) lists[(size_t)cls * cap + s_base[cls] + rank] = b;
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&cursor[kCostClasses], 1u) == gridDim.x - 1)
+      for (int c = 0; c < kCostClasses; ++c) lists[(size_t)kCostClasses * cap + c] = atomicAdd(&cursor[c], 0u);
+  }
+}
+
 // quadtree level decision (process/tree.rs:47-77)
 __global__ void __launch_bounds__(kThreads) k_tree_mask(const float* __restrict__ vx, Geom g, const uint8_t* __restrict__ parent_recurse,
                                                         uint32_t parent_cols, float thr, int positive, uint8_t* __restrict__ leaf,
@@ -1771,22 +1836,37 @@ cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* m
   return cudaGetLastError();
 }
 
+// layout: class_hist[16] | ScanState
+constexpr size_t kClassHistBytes = 2 * kCostClasses * sizeof(uint32_t);
 size_t plan_scan_state_bytes(uint32_t nblocks) {
   const uint32_t tiles = (nblocks + kPlanTile - 1) / kPlanTile;
-  return sizeof(ScanState) + (size_t)tiles * sizeof(unsigned long long);
+  return kClassHistBytes + sizeof(ScanState) + (size_t)tiles * sizeof(unsigned long long);
 }
 
 cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
                         const LevelThresholds& thr, const uint8_t* mask, pxz_block_desc* descs, uint32_t* tabidx,
-                        uint64_t* total_bytes, void* scan_state, cudaStream_t s, uint64_t* launches) {
+                        uint64_t* total_bytes, void* scan_state, uint32_t* lists, uint32_t cap, cudaStream_t s, uint64_t* launches) {
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t tiles = (nblocks + kPlanTile - 1) / kPlanTile;
   cudaError_t e = cudaMemsetAsync(scan_state, 0, plan_scan_state_bytes(nblocks), s);
   if (e != cudaSuccess) return e;
   ++*launches;
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(scan_state);
   k_plan<<<tiles, kThreads, 0, s>>>(vx, vy, g, vm, minmax, thr, mask, descs, tabidx,
                                     reinterpret_cast<unsigned long long*>(total_bytes),
-                                    reinterpret_cast<ScanState*>(scan_state));
+                                    reinterpret_cast<ScanState*>(reinterpret_cast<uint8_t*>(scan_state) + kClassHistBytes), cursor,
+                                    lists, cap);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_class_lists(const pxz_block_desc* descs, const Geom& g, void* scan_state, uint32_t* lists, uint32_t cap,
+                               cudaStream_t s, uint64_t* launches) {
+  const uint32_t nblocks = g.cols * g.rows;
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(scan_state);
+  cudaError_t e = cudaMemsetAsync(cursor, 0, kClassHistBytes, s);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  k_class_lists<<<(nblocks + kThreads - 1) / kThreads, kThreads, 0, s>>>(descs, g, cursor, lists, cap);
   return cudaGetLastError();
 }
 
@@ -1800,7 +1880,8 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
                             uint8_t* scratch, size_t scratch_per_cta, int grid, bool fused, const uint8_t* opaque_flags,
-                            uint32_t* tile_counter, bool warp_tables, cudaStream_t s, int sm_count, uint64_t* launches) {
+                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, cudaStream_t s,
+                            int sm_count, uint64_t* launches) {
   cudaError_t e;
   ++*launches;
   // RGBA fast paths: tiles <= 64x64 with 16-byte aligned rows
@@ -1817,17 +1898,17 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
       if (fused) {
         e = set_smem(k_shrink_warp<true>, smem);
         if (e != cudaSuccess) return e;
-        k_shrink_warp<true><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+        k_shrink_warp<true><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
       } else {
         e = set_smem(k_shrink_warp<false>, smem);
         if (e != cudaSuccess) return e;
-        k_shrink_warp<false><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+        k_shrink_warp<false><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
       }
     } else {
       const size_t smem = (size_t)kWarpsPerCta * kExpandWarpBytes;
       const int wgrid = clamp_grid((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)sm_count * PXZ_EXPAND_WARP_CTAS);
-      if (fused) k_expand_warp<true><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
-      else k_expand_warp<false><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      if (fused) k_expand_warp<true><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      else k_expand_warp<false><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
     }
     return cudaGetLastError();
   }

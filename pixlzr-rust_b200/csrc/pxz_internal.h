@@ -84,7 +84,15 @@ cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* m
 // mask (may be NULL): blocks with mask[b] == 0 get an empty descriptor (w = h = 0) and are skipped by the resample
 cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
                         const LevelThresholds& thr, const uint8_t* mask, pxz_block_desc* descs, uint32_t* tabidx,
-                        uint64_t* total_bytes, void* scan_state, cudaStream_t s, uint64_t* launches);
+                        uint64_t* total_bytes, void* scan_state, uint32_t* lists, uint32_t cap, cudaStream_t s,
+                        uint64_t* launches);
+// Work order of the warp-per-tile resample kernels: lists[c * cap + i], c < 8, = the blocks of cost class c (0 = most
+// expensive), lists[8 * cap + c] = how many.  launch_plan fills them; this entry point does the same for descriptors
+// that came from the host.
+constexpr uint32_t kOrderClasses = 8;
+inline size_t order_list_words(size_t cap) { return (size_t)kOrderClasses * cap + kOrderClasses; }
+cudaError_t launch_class_lists(const pxz_block_desc* descs, const Geom& g, void* scan_state, uint32_t* lists, uint32_t cap,
+                               cudaStream_t s, uint64_t* launches);
 // quadtree level (process/tree.rs:47-77): leaf[b] = active && ((v >= thr) ^ positive), recurse[b] = active && !that,
 // where active = recurse flag of the parent block one level up (NULL parent = every block is active)
 cudaError_t launch_tree_mask(const float* vx, const Geom& g, const uint8_t* parent_recurse, uint32_t parent_cols, float thr,
@@ -95,7 +103,8 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
                             uint8_t* scratch, size_t scratch_per_cta, int grid_hint, bool fused, const uint8_t* opaque_flags,
-                            uint32_t* tile_counter, bool warp_tables, cudaStream_t s, int sm_count, uint64_t* launches);
+                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, cudaStream_t s,
+                            int sm_count, uint64_t* launches);
 size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
 int resample_grid(int sm_count, uint32_t nblocks);
 

@@ -39,6 +39,30 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// v-th block in cost order (lists: see launch_plan); nullptr = natural order
+struct TileOrder {
+  const uint32_t* lists;
+  uint32_t cap;
+  uint32_t end[8];  // running class totals
+  __device__ __forceinline__ void init(const uint32_t* l, uint32_t c) {
+    lists = l; cap = c;
+    uint32_t run = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      run += l ? __ldg(l + (size_t)8 * c + i) : 0u;
+      end[i] = run;
+    }
+  }
+  __device__ __forceinline__ uint32_t at(uint32_t v) const {
+    if (lists == nullptr) return v;
+    uint32_t c = 0, start = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+      if (v >= end[i]) { c = i + 1; start = end[i]; }
+    return __ldg(lists + (size_t)c * cap + (v - start));
+  }
+};
+
 // next tile of this warp (lane 0 asks, everybody gets the answer).  Every warp draws exactly one index >= ntiles; the
 // warp that draws the very last one puts the counter back to zero for the next launch on this stream.
 __device__ __forceinline__ uint32_t next_tile(uint32_t* counter, uint32_t ntiles, uint32_t total_warps) {
@@ -339,7 +363,8 @@ __device__ __forceinline__ void shrink_tile_warp(const uint8_t* __restrict__ img
 template <bool FUSED>
 __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shrink_warp(
     const uint8_t* __restrict__ img, size_t pitch, Geom g, const pxz_block_desc* __restrict__ descs,
-    const uint32_t* __restrict__ tabidx, const uint8_t* __restrict__ opaque_flags, uint8_t* __restrict__ payload,
+    const uint32_t* __restrict__ tabidx, const uint32_t* __restrict__ lists, uint32_t cap, const uint8_t* __restrict__ opaque_flags,
+    uint8_t* __restrict__ payload,
     const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool, uint32_t* counter, float rt_one, float rt_negzero) {
   extern __shared__ float4 s_warp[];
   float4* strip = s_warp + (threadIdx.x >> 5) * (kShrinkWarpBytes / 16);
@@ -349,14 +374,9 @@ __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shr
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kShrinkWarps;
   constexpr int F = FUSED ? 2 : 0;
-  // Tiles are handed out twice: the first sweep takes the expensive ones (8 or more output rows), the second the
-  // rest, so the kernel does not end on a few warps that drew a 20-microsecond tile last.
-  auto process = [&](uint32_t v, const pxz_block_desc& d, uint32_t ti) {
-    const uint32_t b = v < ntiles ? v : v - ntiles;
+  auto process = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti) {
     const Tile t = tile_of(g, b);
     if (d.w == 0 || d.h == 0) return;  // masked out (quadtree levels)
-    const bool heavy = d.h >= 8 && !(d.w == t.tw && d.h == t.th);
-    if (heavy != (v < ntiles)) return;
     if (d.w == t.tw && d.h == t.th) {
       // block.rs:279-281: clone.  The block is contiguous in the payload (4-byte aligned only).  Two rows per
       // instruction, 16 bytes per lane, 16 rows in flight.
@@ -387,35 +407,36 @@ __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shr
     if (opaque) shrink_tile_warp<F>(img, pitch, t, d, ht, ty, pool, strip, ring, payload, k);
     else shrink_tile_warp<F | 1>(img, pitch, t, d, ht, ty, pool, strip, ring, payload, k);
   };
-  // the next tile's index, descriptor and table indices are requested while the current tile is processed
-  const uint32_t nv = 2 * ntiles;
+  // Tiles are drawn in the order of the `order` list (most expensive first, so the kernel does not end on a few warps
+  // that drew a 20-microsecond tile last); the next tile's index, descriptor and table indices are requested while the
+  // current tile is processed.
 #ifdef PXZ_WARP_STATS
   const unsigned long long t_start = globaltimer_ns();
-  unsigned long long t_sweep2 = 0;
   uint32_t drawn = 0;
 #endif
-  uint32_t v = next_tile(counter, nv, total_warps);
+  TileOrder ord;
+  ord.init(lists, cap);
+  uint32_t v = next_tile(counter, ntiles, total_warps);
+  uint32_t b = 0, ti = 0;
   pxz_block_desc d{};
-  uint32_t ti = 0;
-  if (v < nv) { d = descs[v < ntiles ? v : v - ntiles]; ti = tabidx[v < ntiles ? v : v - ntiles]; }
-  while (v < nv) {
-    const uint32_t vn = next_tile(counter, nv, total_warps);
+  if (v < ntiles) { b = ord.at(v); d = descs[b]; ti = tabidx[b]; }
+  while (v < ntiles) {
+    const uint32_t vn = next_tile(counter, ntiles, total_warps);
+    uint32_t bn = 0, tin = 0;
     pxz_block_desc dn{};
-    uint32_t tin = 0;
-    if (vn < nv) { dn = descs[vn < ntiles ? vn : vn - ntiles]; tin = tabidx[vn < ntiles ? vn : vn - ntiles]; }
+    if (vn < ntiles) { bn = ord.at(vn); dn = descs[bn]; tin = tabidx[bn]; }
 #ifdef PXZ_WARP_STATS
-    if (v >= ntiles && t_sweep2 == 0) t_sweep2 = globaltimer_ns();
     ++drawn;
 #endif
-    process(v, d, ti);
-    v = vn; d = dn; ti = tin;
+    process(b, d, ti);
+    v = vn; b = bn; d = dn; ti = tin;
   }
 #ifdef PXZ_WARP_STATS
   if (lane == 0) {
     const uint32_t w = blockIdx.x * kShrinkWarps + (threadIdx.x >> 5);
     g_warp_stats[4 * w + 0] = t_start;
     g_warp_stats[4 * w + 1] = globaltimer_ns();
-    g_warp_stats[4 * w + 2] = t_sweep2;
+    g_warp_stats[4 * w + 2] = 0;
     g_warp_stats[4 * w + 3] = drawn;
   }
 #endif
@@ -588,7 +609,8 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
 template <bool FUSED>
 __global__ void __launch_bounds__(kWarpCtaThreads, PXZ_EXPAND_WARP_CTAS) k_expand_warp(
     uint8_t* __restrict__ img, size_t pitch, Geom g, const pxz_block_desc* __restrict__ descs,
-    const uint32_t* __restrict__ tabidx, const uint8_t* __restrict__ payload, const AxisTab* __restrict__ tabs,
+    const uint32_t* __restrict__ tabidx, const uint32_t* __restrict__ lists, uint32_t cap, const uint8_t* __restrict__ payload,
+    const AxisTab* __restrict__ tabs,
     const uint32_t* __restrict__ pool, uint32_t* counter, float rt_one, float rt_negzero) {
   extern __shared__ float4 s_warp[];
   float4* strip = s_warp + (threadIdx.x >> 5) * (kExpandWarpBytes / 16);
@@ -599,14 +621,10 @@ __global__ void __launch_bounds__(kWarpCtaThreads, PXZ_EXPAND_WARP_CTAS) k_expan
   __syncwarp();
   const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kWarpsPerCta;
   constexpr int F = FUSED ? 2 : 0;
-  // two sweeps over the tiles: resampled ones first, plain fills and copies last (short tail)
-  auto process = [&](uint32_t v, const pxz_block_desc& d, uint32_t ti) {
-    const uint32_t b = v < ntiles ? v : v - ntiles;
+  auto process = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti) {
     const Tile t = tile_of(g, b);
     const uint32_t sw = d.w, sh = d.h, dw = t.tw, dh = t.th;
     if (sw == 0 || sh == 0) return;  // masked out: the tile keeps what the output image already holds
-    const bool heavy = !(sw == dw && sh == dh) && !(sw == 1 && sh == 1);
-    if (heavy != (v < ntiles)) return;
     uint8_t* dst = img + (size_t)t.y0 * pitch + (size_t)t.x0 * 4;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(payload + d.offset);
     if (sw == dw && sh == dh) {
@@ -644,17 +662,21 @@ __global__ void __launch_bounds__(kWarpCtaThreads, PXZ_EXPAND_WARP_CTAS) k_expan
     if (opaque) expand_tile_warp<F>(img, pitch, t, d, tx, ty, pool, strip, payload, k);
     else expand_tile_warp<F | 1>(img, pitch, t, d, tx, ty, pool, strip, payload, k);
   };
-  const uint32_t nv = 2 * ntiles;
-  uint32_t v = next_tile(counter, nv, total_warps);
+  // Tiles are drawn in the order of the `order` list (most expensive first, so the kernel does not end on a few warps
+  // that drew a 20-microsecond tile last); the next tile's index, descriptor and table indices are requested while the
+  // current tile is processed.
+  TileOrder ord;
+  ord.init(lists, cap);
+  uint32_t v = next_tile(counter, ntiles, total_warps);
+  uint32_t b = 0, ti = 0;
   pxz_block_desc d{};
-  uint32_t ti = 0;
-  if (v < nv) { d = descs[v < ntiles ? v : v - ntiles]; ti = tabidx[v < ntiles ? v : v - ntiles]; }
-  while (v < nv) {
-    const uint32_t vn = next_tile(counter, nv, total_warps);
+  if (v < ntiles) { b = ord.at(v); d = descs[b]; ti = tabidx[b]; }
+  while (v < ntiles) {
+    const uint32_t vn = next_tile(counter, ntiles, total_warps);
+    uint32_t bn = 0, tin = 0;
     pxz_block_desc dn{};
-    uint32_t tin = 0;
-    if (vn < nv) { dn = descs[vn < ntiles ? vn : vn - ntiles]; tin = tabidx[vn < ntiles ? vn : vn - ntiles]; }
-    process(v, d, ti);
-    v = vn; d = dn; ti = tin;
+    if (vn < ntiles) { bn = ord.at(vn); dn = descs[bn]; tin = tabidx[bn]; }
+    process(b, d, ti);
+    v = vn; b = bn; d = dn; ti = tin;
   }
 }
