@@ -556,10 +556,23 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
         u64 a[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) a[c] = 0ull;
+        // blocks of at most 2 / 4 rows have at most that many taps (the table rows are +0 beyond them)
 #pragma unroll
-        for (int j = 0; j < 7; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int c = 0; c < NC; ++c) a[c] = mac2<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
+        if (sh > 2) {
+#pragma unroll
+          for (int j = 2; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a[c] = mac2<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
+          if (sh > 4) {
+#pragma unroll
+            for (int j = 4; j < 7; ++j)
+#pragma unroll
+              for (int c = 0; c < NC; ++c) a[c] = mac2<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
+          }
+        }
         if (vact) {
           float lo_[4] = {0.f, 0.f, 0.f, 0.f}, hi_[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll

@@ -460,3 +460,35 @@ def test_tree_process_edge_cases(ctx):
     # halved sizes that stop being exact are refused, not approximated
     with pytest.raises(N.PixlzrError):
         P.tree_process(img, 100, 0.01)
+
+
+# ---------------------------------------------------------------------------------------------
+# the CTA-per-tile resample kernels (selected with PXZ_RESAMPLE_KERNELS=cta when a context is created) stay bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cta_ctx():
+    old = os.environ.get("PXZ_RESAMPLE_KERNELS")
+    os.environ["PXZ_RESAMPLE_KERNELS"] = "cta"
+    try:
+        c = N.Context(0)
+    finally:
+        if old is None:
+            del os.environ["PXZ_RESAMPLE_KERNELS"]
+        else:
+            os.environ["PXZ_RESAMPLE_KERNELS"] = old
+    return c
+
+
+@pytest.mark.parametrize("shape,bs,fd,fu", [((520, 776), 64, O.LANCZOS3, O.LANCZOS3), ((300, 420), 32, O.CATMULLROM, O.TRIANGLE),
+                                            ((256, 256), 16, O.GAUSSIAN, O.NEAREST)])
+def test_cta_kernels_match_oracle(cta_ctx, shape, bs, fd, fu):
+    img = synth(shape[1], shape[0], 4, seed=11)
+    ref = O.shrink(img, bs, bs, 0, 1.0, fd)
+    d = cta_ctx.image_upload(img)
+    pl = d.shrink(bs, bs, 0, 1.0, fd, N.FLAG_EXACT_VALUES)
+    descs, px = pl.download()
+    assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+    assert np.array_equal(px, ref.payload)
+    assert np.array_equal(pl.expand(fu), O.expand(ref, fu))
+    pl.free()
+    d.free()
