@@ -83,7 +83,7 @@ struct pxz_ctx {
   size_t values_cap = 0;
   float* d_minmax = nullptr;
   uint32_t* d_tile_counter = nullptr;  // work counter of the warp-per-tile resample kernels (they leave it at 0)
-  bool warp_kernels = true;            // PXZ_RESAMPLE_KERNELS=cta selects the CTA-per-tile kernels instead
+  int resample_kernels = 0;            // 0 = by tile count, 1 = warp-per-tile, 2 = CTA-per-tile (PXZ_RESAMPLE_KERNELS=warp|cta)
   void* d_scan = nullptr;
   size_t scan_cap = 0;
   uint8_t* d_scratch = nullptr;
@@ -311,7 +311,8 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
                                 ts.ntabs, max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, opaque_flags,
-                                ctx->warp_kernels ? ctx->d_tile_counter : nullptr, p->d_order(), (uint32_t)p->nblocks_cap, ts.warp_ok, ctx->stream, ctx->sm_count,
+                                ctx->resample_kernels != 2 ? ctx->d_tile_counter : nullptr, p->d_order(), (uint32_t)p->nblocks_cap,
+                                ts.warp_ok, ctx->resample_kernels == 1, ctx->stream, ctx->sm_count,
                                 &ctx->launches));
   return PXZ_OK;
 }
@@ -373,7 +374,7 @@ pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx*
   ctx->band.abs_raw = 8.0e-6f; // fast arithmetic, absolute (SFU cube roots; measured <= 4e-6)
   if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
   if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
-  if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->warp_kernels = strcmp(e, "cta") != 0;
+  if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->resample_kernels = !strcmp(e, "warp") ? 1 : !strcmp(e, "cta") ? 2 : 0;
   if (cudaMalloc((void**)&ctx->d_minmax, 4 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_tile_counter, 64) != cudaSuccess || cudaMemset(ctx->d_tile_counter, 0, 64) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_total, 64) != cudaSuccess) {

@@ -1880,8 +1880,8 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
                             uint8_t* scratch, size_t scratch_per_cta, int grid, bool fused, const uint8_t* opaque_flags,
-                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, cudaStream_t s,
-                            int sm_count, uint64_t* launches) {
+                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, bool force_warp,
+                            cudaStream_t s, int sm_count, uint64_t* launches) {
   cudaError_t e;
   ++*launches;
   // RGBA fast paths: tiles <= 64x64 with 16-byte aligned rows
@@ -1889,9 +1889,10 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                     ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && max_src_px <= (uint32_t)kFastMaxPx && max_src_dim <= 64u &&
                     max_tmp_px <= (uint32_t)kFastMaxPx && max_tab_words <= (uint32_t)kFastMaxTabWords &&
                     ntabs <= (uint32_t)kFastMaxTabs && scratch == nullptr;
-  if (fast && warp_tables && tile_counter != nullptr) {
-    // warp-per-tile kernels (resample_warp.cuh)
-    const long long ntiles = (long long)g.cols * g.rows;
+  // warp-per-tile kernels (resample_warp.cuh) once there are enough tiles to keep every warp slot of the GPU busy for
+  // a few tiles; below that one tile's latency (15-40 us on one warp) decides and 8 warps per tile finish sooner
+  const long long ntiles = (long long)g.cols * g.rows;
+  if (fast && warp_tables && tile_counter != nullptr && (force_warp || ntiles >= (long long)sm_count * 16)) {
     if (direction == 0) {
       const size_t smem = (size_t)kShrinkWarps * kShrinkWarpBytes;
       const int wgrid = clamp_grid((ntiles + kShrinkWarps - 1) / kShrinkWarps, (long long)sm_count * PXZ_SHRINK_WARP_CTAS);

@@ -103,8 +103,8 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
                             uint8_t* scratch, size_t scratch_per_cta, int grid_hint, bool fused, const uint8_t* opaque_flags,
-                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, cudaStream_t s,
-                            int sm_count, uint64_t* launches);
+                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, bool force_warp,
+                            cudaStream_t s, int sm_count, uint64_t* launches);
 size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
 int resample_grid(int sm_count, uint32_t nblocks);
 

@@ -463,32 +463,51 @@ def test_tree_process_edge_cases(ctx):
 
 
 # ---------------------------------------------------------------------------------------------
-# the CTA-per-tile resample kernels (selected with PXZ_RESAMPLE_KERNELS=cta when a context is created) stay bit-exact
+# Both resample kernel families stay bit-exact.  By default the library picks by tile count (warp-per-tile from
+# 16 tiles per SM, CTA-per-tile below); PXZ_RESAMPLE_KERNELS=warp|cta, read when a context is created, forces one.
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(scope="module")
-def cta_ctx():
+def _forced_ctx(kind):
     old = os.environ.get("PXZ_RESAMPLE_KERNELS")
-    os.environ["PXZ_RESAMPLE_KERNELS"] = "cta"
+    os.environ["PXZ_RESAMPLE_KERNELS"] = kind
     try:
-        c = N.Context(0)
+        return N.Context(0)
     finally:
         if old is None:
             del os.environ["PXZ_RESAMPLE_KERNELS"]
         else:
             os.environ["PXZ_RESAMPLE_KERNELS"] = old
-    return c
 
 
-@pytest.mark.parametrize("shape,bs,fd,fu", [((520, 776), 64, O.LANCZOS3, O.LANCZOS3), ((300, 420), 32, O.CATMULLROM, O.TRIANGLE),
-                                            ((256, 256), 16, O.GAUSSIAN, O.NEAREST)])
-def test_cta_kernels_match_oracle(cta_ctx, shape, bs, fd, fu):
+@pytest.fixture(scope="module")
+def forced_ctx():
+    return {"cta": _forced_ctx("cta"), "warp": _forced_ctx("warp")}
+
+
+@pytest.mark.parametrize("kind", ["warp", "cta"])
+@pytest.mark.parametrize("shape,bs,metric,factor,fd,fu", [
+    ((520, 776), 64, 0, 1.0, O.LANCZOS3, O.LANCZOS3),      # trailing 8-px / 8-row tiles
+    ((300, 420), 32, 0, 1.0, O.CATMULLROM, O.TRIANGLE),
+    ((256, 256), 16, 0, 1.0, O.GAUSSIAN, O.NEAREST),
+    ((452, 648), 64, 0, 0.5, O.TRIANGLE, O.GAUSSIAN),      # trailing 4 / 8 px: irregular ratios (no slide table)
+    ((384, 512), 64, 1, 8.0, O.LANCZOS3, O.LANCZOS3),      # Sobel: the two axes get different levels
+    ((384, 512), 48, 1, 4.0, O.NEAREST, O.CATMULLROM),
+    ((200, 264), 40, 0, 2.0, O.LANCZOS3, O.CATMULLROM),    # 40-px tiles: 40 -> 20 -> 10 -> 5 -> 3 -> 2 -> 1
+])
+def test_resample_kernel_families_match_oracle(forced_ctx, kind, shape, bs, metric, factor, fd, fu):
+    ctx = forced_ctx[kind]
     img = synth(shape[1], shape[0], 4, seed=11)
-    ref = O.shrink(img, bs, bs, 0, 1.0, fd)
-    d = cta_ctx.image_upload(img)
-    pl = d.shrink(bs, bs, 0, 1.0, fd, N.FLAG_EXACT_VALUES)
+    img[: shape[0] // 3, : shape[1] // 2, 3] = (img[: shape[0] // 3, : shape[1] // 2, 0] // 2) + 60  # some translucent tiles
+    ref = O.shrink(img, bs, bs, metric, factor, fd)
+    d = ctx.image_upload(img)
+    pl = d.shrink(bs, bs, metric, factor, fd, N.FLAG_EXACT_VALUES)
     descs, px = pl.download()
     assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+    assert np.array_equal(descs["offset"], ref.descs["offset"])
     assert np.array_equal(px, ref.payload)
     assert np.array_equal(pl.expand(fu), O.expand(ref, fu))
+    # a payload that comes back from the host (pxz_payload_upload builds the work order itself)
+    pl2 = ctx.payload_upload(shape[1], shape[0], bs, bs, 4, descs, px)
+    assert np.array_equal(pl2.expand(fu), O.expand(ref, fu))
+    pl2.free()
     pl.free()
     d.free()
