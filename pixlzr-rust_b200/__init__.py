@@ -22,3 +22,4 @@ from .api import (  # noqa: F401
 )
 from . import _native as native  # noqa: F401
 from . import sharding  # noqa: F401
+from . import cli  # noqa: F401

@@ -10,3 +10,6 @@ _spec = importlib.util.spec_from_file_location(
 _mod = importlib.util.module_from_spec(_spec)
 sys.modules["pixlzr_b200"] = _mod
 _spec.loader.exec_module(_mod)
+
+if __name__ == "__main__":  # `python pixlzr_b200.py -i ... -o ...`: the reference CLI's arguments (src/bin/main.rs)
+    sys.exit(_mod.cli.main())

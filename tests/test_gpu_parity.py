@@ -511,3 +511,36 @@ def test_resample_kernel_families_match_oracle(forced_ctx, kind, shape, bs, metr
     pl2.free()
     pl.free()
     d.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# command-line driver (src/bin/main.rs:299-356 and the four conversions)
+# ---------------------------------------------------------------------------------------------
+def test_cli_conversions(tmp_path):
+    from PIL import Image
+    src = os.path.join(GOLDEN, "image.png")
+    img = load_png("image.png")
+    # test_image_to_image: no --force -> identity
+    out = str(tmp_path / "test_image.png")
+    assert P.cli.main(["-i", src, "-o", out, "-b", "8"]) == 0
+    assert np.array_equal(np.array(Image.open(out)), img)
+    # test_image_to_pix_to_image
+    pix, back = str(tmp_path / "image.pix"), str(tmp_path / "test_image_from_pix.png")
+    assert P.cli.main(["-i", src, "-o", pix, "-b", "64"]) == 0
+    assert P.cli.main(["-i", pix, "-o", back, "-b", "64"]) == 0
+    assert np.array_equal(np.array(Image.open(back)), img)
+    # --force shrinks: same bytes as the library calls, and as the oracle
+    big = os.path.join(GOLDEN, "Big-Ruscher.png")
+    out_pix = str(tmp_path / "big.pix")
+    assert P.cli.main(["-i", big, "-o", out_pix, "-b", "32", "-k", "1/8", "-f", "lanczos3", "--force"]) == 0
+    ref, _ = O.container_decode(open(os.path.join(GOLDEN, "Big-Ruscher.pix"), "rb").read())
+    got, _ = O.container_decode(open(out_pix, "rb").read())
+    assert np.array_equal(got.descs["w"], ref.descs["w"]) and np.array_equal(got.descs["h"], ref.descs["h"])
+    assert np.array_equal(got.payload, ref.payload)
+    # pix -> pix re-tiles the decoded image; pix -> image with another filter
+    out_pix2, out_png = str(tmp_path / "re.pixlzr"), str(tmp_path / "big.png")
+    assert P.cli.main(["-i", out_pix, "-o", out_pix2, "-b", "64", "-f", "nearest"]) == 0
+    assert P.cli.main(["-i", out_pix, "-o", out_png, "-f", "nearest"]) == 0
+    assert np.array_equal(np.array(Image.open(out_png)), load_png("Big-Ruscher.pix.png"))
+    assert np.array_equal(P.Pixlzr.open(out_pix2).to_image(P.FilterType.Nearest), load_png("Big-Ruscher.pix.png"))
+    assert P.cli.main(["-i", str(tmp_path / "missing.png"), "-o", out_png]) == 1

@@ -160,3 +160,21 @@ def test_resample_tables_match_oracle_bit_for_bit(filt):
         l1, c1, w1 = N.resample_table(n_in, n_out, filt)
         assert np.array_equal(l0, l1) and np.array_equal(c0, c1), (n_in, n_out)
         assert w0.shape == w1.shape and np.array_equal(w0.view(np.uint32), w1.view(np.uint32)), (n_in, n_out)
+
+
+def test_cli_arguments_and_operation_selection():
+    """src/bin/main.rs:7-114: flags, defaults, extension-based operation selection."""
+    import pixlzr_b200 as P
+    cli = P.cli
+    a = cli.parse_args(["-i", "a.png", "-o", "b.pix"])
+    assert (a.block_width, a.block_height, a.shrinking_factor, a.filter, a.direction_wise, a.force) == (64, None, "1", "lanczos3", None, False)
+    a = cli.parse_args(["-i", "a.png", "-o", "b.png", "-b", "32", "--block-height", "16", "-k", "-1/2", "-f", "catmull-rom",
+                                       "-d", "true", "--force"])
+    assert (a.block_width, a.block_height, a.shrinking_factor, a.filter, a.direction_wise, a.force) == (32, 16, "-1/2", "catmull-rom", True, True)
+    assert P.parse_shrinking_factor(a.shrinking_factor) == -0.5
+    assert cli.operation("x.png", "y.pix") == ("image", "pix")
+    assert cli.operation("x.PIXLZR", "y.jpg") == ("pix", "image")
+    assert cli.operation("x.pix", "y.PiX") == ("pix", "pix")
+    assert cli.operation("x", "y") == ("image", "pix")          # no extension: image in, container out (main.rs:100, 109)
+    assert cli.operation("x.webp", "y.png") == ("image", "image")
+    assert set(cli.FILTERS) == {"nearest", "triangle", "catmull-rom", "gaussian", "lanczos3"}
