@@ -1291,9 +1291,21 @@ struct Acc1 {
   }
 };
 
+// The same rounding with the clamp left to the pack instruction: 1.5 * 2^23 keeps the exponent fixed on both sides of
+// zero, so the bits of the sum are 0x4B400000 + n with n = floor(t + 0.5) for t >= 0 and some negative integer for
+// t < -0.5; cvt.pack.sat clamps n to [0, 255] and packs two channels per instruction (|t| < 2^22 here).
+__device__ __forceinline__ int32_t round_away_int(float t) {
+  return (int32_t)(__float_as_uint(__fadd_rz(__fadd_rz(t, 0.5f), 12582912.0f)) - 0x4B400000u);
+}
+__device__ __forceinline__ uint32_t pack_sat_u8x2(int32_t hi_byte, int32_t lo_byte, uint32_t upper16) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi_byte), "r"(lo_byte), "r"(upper16));
+  return d;
+}
 template <int MODE>
 __device__ __forceinline__ uint32_t pack_px(const float4& a) {
-  return pack_bits(to_u8_bits(a.x), to_u8_bits(a.y), to_u8_bits(a.z), (MODE & 1) ? to_u8_bits(a.w) : 0x000000FFu);
+  const uint32_t ba = pack_sat_u8x2((MODE & 1) ? round_away_int(a.w) : 255, round_away_int(a.z), 0u);  // {b, a, 0, 0}
+  return pack_sat_u8x2(round_away_int(a.y), round_away_int(a.x), ba);                                  // {r, g, b, a}
 }
 
 // ---- vertical_sample: src [sh][64] -> tmp [dh][ts] ---------------------------------------------------------------
