@@ -91,6 +91,32 @@ __device__ __forceinline__ float byte_to_float(uint32_t word) {
   return __uint_as_float(bits) - 8388608.0f;
 }
 
+// ---- packed f32x2 arithmetic (sm_100a FFMA2: two f32 lanes per issue slot) ---------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float lo2(u64 v) { float a, b; unpk2(v, a, b); return a; }
+__device__ __forceinline__ float hi2(u64 v) { float a, b; unpk2(v, a, b); return b; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // tile geometry of block index b
 struct Tile {
   uint32_t x0, y0, tw, th;
@@ -144,6 +170,20 @@ __device__ __forceinline__ OklabFast lms_fast_addr(uint32_t px, uint32_t lut_lan
   o.m = cbrt_fast(fmaf(M1_12, b, fmaf(M1_11, g, M1_10 * r)));
   o.s = cbrt_fast(fmaf(M1_22, b, fmaf(M1_21, g, M1_20 * r)));
   return o;
+}
+
+// two pixels at once: the 3x3 products run as f32x2 FMAs (each lane is the same IEEE fma as the scalar form, so the
+// values — and the guard band derived for them — do not change; only the issue slots halve)
+__device__ __forceinline__ void lms_fast_pair(uint32_t px0, uint32_t px1, uint32_t lut_lane_addr, OklabFast& o0, OklabFast& o1) {
+  const u64 r = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4440) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4440) << 7)));
+  const u64 g = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4441) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4441) << 7)));
+  const u64 b = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4442) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4442) << 7)));
+#define PXZ_ROW2(c0, c1, c2) fma2(pk2(c2, c2), b, fma2(pk2(c1, c1), g, mul2(pk2(c0, c0), r)))
+  const u64 l = PXZ_ROW2(M1_00, M1_01, M1_02), m = PXZ_ROW2(M1_10, M1_11, M1_12), q = PXZ_ROW2(M1_20, M1_21, M1_22);
+#undef PXZ_ROW2
+  o0.l = cbrt_fast(lo2(l)); o1.l = cbrt_fast(hi2(l));
+  o0.m = cbrt_fast(lo2(m)); o1.m = cbrt_fast(hi2(m));
+  o0.s = cbrt_fast(lo2(q)); o1.s = cbrt_fast(hi2(q));
 }
 
 #ifndef PXZ_MAD_MINBLOCKS
@@ -204,12 +244,16 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
       const bool inq = !MASK || (valid && QROW(j) < t.th && QCOL(j) < t.tw);
       const uint32_t w4[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        OklabFast o = lms_fast_addr(w4[k], lut_lane_addr);
-        if (MASK && !inq) { o.l = 0.f; o.m = 0.f; o.s = 0.f; }
-        c[j * 4 + k] = o;
-        sl += o.l; sm += o.m; ss += o.s;
+      for (int k = 0; k < 4; k += 2) {
+        OklabFast o0, o1;
+        lms_fast_pair(w4[k], w4[k + 1], lut_lane_addr, o0, o1);
+        if (MASK && !inq) { o0.l = 0.f; o0.m = 0.f; o0.s = 0.f; o1 = o0; }
+        c[j * 4 + k] = o0;
+        c[j * 4 + k + 1] = o1;
+        sl += o0.l; sm += o0.m; ss += o0.s;
+        sl += o1.l; sm += o1.m; ss += o1.s;
         asum = __dp4a(w4[k], 0x01000000u, asum);  // out-of-tile quads were loaded as zeros
+        asum = __dp4a(w4[k + 1], 0x01000000u, asum);
       }
 #ifdef PXZ_MAD_SCHED_FENCE
       asm volatile("" ::: "memory");  // keep the quads' LDS / MUFU bursts apart (MIO queue pressure)
@@ -244,18 +288,23 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
     const float nB = -(M2_20 * sl + M2_21 * sm + M2_22 * ss);
     float d = 0.f;
     float dp[4] = {0.f, 0.f, 0.f, 0.f};
+    const u64 nL2 = pk2(nL, nL), nA2 = pk2(nA, nA), nB2 = pk2(nB, nB);
 #pragma unroll
-    for (int i = 0; i < QPT * 4; ++i) {
-      const OklabFast o = c[i];
-      const float dL = fmaf(M2_02, o.s, fmaf(M2_01, o.m, fmaf(M2_00, o.l, nL)));
-      const float dA = fmaf(M2_12, o.s, fmaf(M2_11, o.m, fmaf(M2_10, o.l, nA)));
-      const float dB = fmaf(M2_22, o.s, fmaf(M2_21, o.m, fmaf(M2_20, o.l, nB)));
+    for (int i = 0; i < QPT * 4; i += 2) {
+      const u64 ol = pk2(c[i].l, c[i + 1].l), om = pk2(c[i].m, c[i + 1].m), os = pk2(c[i].s, c[i + 1].s);
+#define PXZ_ROW2(c0, c1, c2, bias) fma2(pk2(c2, c2), os, fma2(pk2(c1, c1), om, fma2(pk2(c0, c0), ol, bias)))
+      const u64 dL2 = PXZ_ROW2(M2_00, M2_01, M2_02, nL2), dA2 = PXZ_ROW2(M2_10, M2_11, M2_12, nA2), dB2 = PXZ_ROW2(M2_20, M2_21, M2_22, nB2);
+#undef PXZ_ROW2
+      const float e0 = (fabsf(lo2(dA2)) + fabsf(lo2(dB2))) + fabsf(lo2(dL2));
+      const float e1 = (fabsf(hi2(dA2)) + fabsf(hi2(dB2))) + fabsf(hi2(dL2));
       if (MASK) {
         const int j = i >> 2, k = i & 3;
-        const bool in = valid && QROW(j) < t.th && (QCOL(j) + k) < t.tw;
-        d += in ? (fabsf(dA) + fabsf(dB)) + fabsf(dL) : 0.f;
+        const bool rowin = valid && QROW(j) < t.th;
+        d += (rowin && (QCOL(j) + k) < t.tw) ? e0 : 0.f;
+        d += (rowin && (QCOL(j) + k + 1) < t.tw) ? e1 : 0.f;
       } else {
-        dp[i & 3] += (fabsf(dA) + fabsf(dB)) + fabsf(dL);
+        dp[i & 3] += e0;
+        dp[(i + 1) & 3] += e1;
       }
     }
     if (!MASK) d = (dp[0] + dp[1]) + (dp[2] + dp[3]);
@@ -1190,21 +1239,6 @@ __device__ __forceinline__ uint32_t to_u8_bits(float t) {
 }
 __device__ __forceinline__ uint32_t to_u8_fast(float t) { return to_u8_bits(t) & 0xFFu; }
 
-// ---- packed f32x2 arithmetic (sm_100a FFMA2: two f32 lanes per issue slot) ---------------------------------------
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ float lo2(u64 v) { float a, b; unpk2(v, a, b); return a; }
-__device__ __forceinline__ float hi2(u64 v) { float a, b; unpk2(v, a, b); return b; }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
 
 // 1.0 and -0.0 as *run-time* values (kernel arguments).  The reference rounds the product and the sum of a tap
 // separately (t += p * w without contraction); written as fma(p, w, -0) and fma(product, 1, t) those are two
