@@ -185,6 +185,33 @@ __device__ __forceinline__ void lms_fast_pair(uint32_t px0, uint32_t px1, uint32
   o0.m = cbrt_fast(lo2(m)); o1.m = cbrt_fast(hi2(m));
   o0.s = cbrt_fast(lo2(q)); o1.s = cbrt_fast(hi2(q));
 }
+// the same with the results left as pairs (l', m', s' of the two pixels)
+__device__ __forceinline__ u64 cbrt_fast2(u64 x) {
+  float a, b, la, lb;
+  unpk2(x, a, b);
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(la) : "f"(a));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lb) : "f"(b));
+  const u64 t = mul2(pk2(la, lb), pk2(0.333333343f, 0.333333343f));
+  unpk2(t, la, lb);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(la));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(lb));
+  return pk2(a, b);
+}
+struct OklabFast2 {
+  u64 l, m, s;
+};
+__device__ __forceinline__ OklabFast2 lms_fast_pair2(uint32_t px0, uint32_t px1, uint32_t lut_lane_addr) {
+  const u64 r = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4440) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4440) << 7)));
+  const u64 g = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4441) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4441) << 7)));
+  const u64 b = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4442) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4442) << 7)));
+#define PXZ_ROW2(c0, c1, c2) fma2(pk2(c2, c2), b, fma2(pk2(c1, c1), g, mul2(pk2(c0, c0), r)))
+  OklabFast2 o;
+  o.l = cbrt_fast2(PXZ_ROW2(M1_00, M1_01, M1_02));
+  o.m = cbrt_fast2(PXZ_ROW2(M1_10, M1_11, M1_12));
+  o.s = cbrt_fast2(PXZ_ROW2(M1_20, M1_21, M1_22));
+#undef PXZ_ROW2
+  return o;
+}
 
 #ifndef PXZ_MAD_MINBLOCKS
 #define PXZ_MAD_MINBLOCKS 3
@@ -236,8 +263,8 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
   auto process = [&](auto mask_tag, const Tile& t, bool valid, uint4(&cur)[QPT], uint4(&nxt)[QPT], uint32_t next_tile,
                      uint32_t tile, int buf) {
     constexpr bool MASK = decltype(mask_tag)::value;
-    OklabFast c[QPT * 4];
-    float sl = 0.f, sm = 0.f, ss = 0.f;
+    OklabFast2 c[QPT * 2];  // pixel pairs
+    u64 sl2 = 0ull, sm2 = 0ull, ss2 = 0ull;
     uint32_t asum = 0;  // integer sum of the alpha bytes (exact)
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
@@ -245,13 +272,10 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
       const uint32_t w4[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
       for (int k = 0; k < 4; k += 2) {
-        OklabFast o0, o1;
-        lms_fast_pair(w4[k], w4[k + 1], lut_lane_addr, o0, o1);
-        if (MASK && !inq) { o0.l = 0.f; o0.m = 0.f; o0.s = 0.f; o1 = o0; }
-        c[j * 4 + k] = o0;
-        c[j * 4 + k + 1] = o1;
-        sl += o0.l; sm += o0.m; ss += o0.s;
-        sl += o1.l; sm += o1.m; ss += o1.s;
+        OklabFast2 o = lms_fast_pair2(w4[k], w4[k + 1], lut_lane_addr);
+        if (MASK && !inq) { o.l = 0ull; o.m = 0ull; o.s = 0ull; }
+        c[j * 2 + (k >> 1)] = o;
+        sl2 = add2(sl2, o.l); sm2 = add2(sm2, o.m); ss2 = add2(ss2, o.s);
         asum = __dp4a(w4[k], 0x01000000u, asum);  // out-of-tile quads were loaded as zeros
         asum = __dp4a(w4[k + 1], 0x01000000u, asum);
       }
@@ -264,6 +288,7 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
     for (int j = 0; j < QPT; ++j) nxt[j] = make_uint4(0, 0, 0, 0);
     load_tile(next_tile, nxt);
     // ---- group reduction 1 ----
+    float sl = lo2(sl2) + hi2(sl2), sm = lo2(sm2) + hi2(sm2), ss = lo2(ss2) + hi2(ss2);
     float sa = (float)asum;
     sl = warp_sum(sl); sm = warp_sum(sm); ss = warp_sum(ss); sa = warp_sum(sa);
     if (WPG > 1) {
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
     const u64 nL2 = pk2(nL, nL), nA2 = pk2(nA, nA), nB2 = pk2(nB, nB);
 #pragma unroll
     for (int i = 0; i < QPT * 4; i += 2) {
-      const u64 ol = pk2(c[i].l, c[i + 1].l), om = pk2(c[i].m, c[i + 1].m), os = pk2(c[i].s, c[i + 1].s);
+      const u64 ol = c[i >> 1].l, om = c[i >> 1].m, os = c[i >> 1].s;
 #define PXZ_ROW2(c0, c1, c2, bias) fma2(pk2(c2, c2), os, fma2(pk2(c1, c1), om, fma2(pk2(c0, c0), ol, bias)))
       const u64 dL2 = PXZ_ROW2(M2_00, M2_01, M2_02, nL2), dA2 = PXZ_ROW2(M2_10, M2_11, M2_12, nA2), dB2 = PXZ_ROW2(M2_20, M2_21, M2_22, nB2);
 #undef PXZ_ROW2
