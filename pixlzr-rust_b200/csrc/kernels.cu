@@ -214,7 +214,7 @@ __device__ __forceinline__ OklabFast2 lms_fast_pair2(uint32_t px0, uint32_t px1,
 }
 
 #ifndef PXZ_MAD_MINBLOCKS
-#define PXZ_MAD_MINBLOCKS 3
+#define PXZ_MAD_MINBLOCKS 2
 #endif
 template <int G, int QPT>
 __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
@@ -1816,19 +1816,19 @@ cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom
     if (quads > 512) {
       e = set_smem(k_analyze_mad_rgba<256, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     } else if (quads > 256) {
       e = set_smem(k_analyze_mad_rgba<128, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     } else if (quads > 128) {
       e = set_smem(k_analyze_mad_rgba<64, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     } else {
       e = set_smem(k_analyze_mad_rgba<32, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
     }
   } else if (g.C == 4) {
     e = set_smem(k_analyze_mad_any<4>, smem);
