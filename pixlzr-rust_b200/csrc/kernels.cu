@@ -17,8 +17,6 @@
 #include <math.h>
 #include <stdint.h>
 
-#include <type_traits>
-
 #include "pxz_internal.h"
 
 namespace pxz {

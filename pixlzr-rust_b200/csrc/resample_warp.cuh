@@ -179,7 +179,7 @@ __device__ __forceinline__ void shrink_horizontal(const float4* strip, uint32_t 
 template <int MODE>
 struct ShrinkRun {
   static constexpr int NC = (MODE & 1) ? 4 : 3;
-  u64 acc[2][NC][3];             // [column][channel][slot pair]; tables with fewer slots use the first pairs
+  u64 acc[2][NC][3];  // [column][channel][slot pair]; tables with fewer slots use the first pairs
   const ulonglong2* wp;          // slide table row of source row r
   const uint32_t* dp;            // done[r]
   ulonglong2 wa_n;               // table row of source row r, requested one row ahead
@@ -191,8 +191,8 @@ struct ShrinkRun {
   uint32_t ob;                   // blocked fallback: next group of 4 output rows
 };
 
-template <int MODE, int NP, int S>
-__device__ __forceinline__ void take_slot3(u64 (&acc)[2][(MODE & 1) ? 4 : 3][3], float4& v0, float4& v1) {
+template <int MODE, int NPMAX, int S>
+__device__ __forceinline__ void take_slot3(u64 (&acc)[2][(MODE & 1) ? 4 : 3][NPMAX], float4& v0, float4& v1) {
   constexpr int NC = (MODE & 1) ? 4 : 3;
   constexpr int jp = S / 2;
   constexpr bool high = (S & 1) != 0;
@@ -225,12 +225,12 @@ __device__ __forceinline__ void shrink_vrun(ShrinkRun<MODE>& st, const uint8_t* 
     while (st.pend > 0 && st.o_next - st.batch0 < (uint32_t)kStripRows) {
       float4 v0, v1;
       switch (st.slot) {
-        case 0: take_slot3<MODE, NP, 0>(st.acc, v0, v1); break;
-        case 1: take_slot3<MODE, NP, 1>(st.acc, v0, v1); break;
-        case 2: if (A > 2) take_slot3<MODE, NP, (A > 2 ? 2 : 0)>(st.acc, v0, v1); break;
-        case 3: if (A > 2) take_slot3<MODE, NP, (A > 2 ? 3 : 0)>(st.acc, v0, v1); break;
-        case 4: if (A > 4) take_slot3<MODE, NP, (A > 4 ? 4 : 0)>(st.acc, v0, v1); break;
-        default: if (A > 4) take_slot3<MODE, NP, (A > 4 ? 5 : 0)>(st.acc, v0, v1); break;
+        case 0: take_slot3<MODE, 3, 0>(st.acc, v0, v1); break;
+        case 1: take_slot3<MODE, 3, 1>(st.acc, v0, v1); break;
+        case 2: if (A > 2) take_slot3<MODE, 3, (A > 2 ? 2 : 0)>(st.acc, v0, v1); break;
+        case 3: if (A > 2) take_slot3<MODE, 3, (A > 2 ? 3 : 0)>(st.acc, v0, v1); break;
+        case 4: if (A > 4) take_slot3<MODE, 3, (A > 4 ? 4 : 0)>(st.acc, v0, v1); break;
+        default: if (A > 4) take_slot3<MODE, 3, (A > 4 ? 5 : 0)>(st.acc, v0, v1); break;
       }
       float4* srow = strip + (st.o_next - st.batch0) * kStripStride + 2 * lane;
       srow[0] = v0;
@@ -276,6 +276,81 @@ __device__ __forceinline__ void shrink_vrun(ShrinkRun<MODE>& st, const uint8_t* 
       const uint32_t rn = ((st.r + 1) & ~1u) - 2 + kRingRows + crow;
       if (rn < sh && ccol) cp_async_16(ring + (rn & (kRingRows - 1)) * 64 + cchunk * 4, tile0 + (size_t)rn * pitch + cchunk * 16);
       cp_async_commit();
+    }
+  }
+}
+
+// Tiles whose output rows all fit the accumulator slots (n_out <= A: every output keeps its own slot for the whole walk,
+// nothing is emitted on the way): one plain loop over the source rows, then all rows go to the strip at once.  This is
+// every tile reduced to at most 4 rows — the state machine of shrink_vrun costs them twice the instructions.
+template <int MODE, int A>
+__device__ __forceinline__ void shrink_vsimple(const uint8_t* tile0, size_t pitch, uint32_t sw, uint32_t sh, uint32_t dh,
+                                               const AxisTab& ty, const uint32_t* __restrict__ pool, float4* strip, uint32_t* ring,
+                                               const TapK& k) {
+  constexpr int NC = (MODE & 1) ? 4 : 3;
+  constexpr int NP = A / 2;
+  constexpr int RING = kRingRows;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t crow = lane >> 4, cchunk = lane & 15u;
+  const bool ccol = cchunk * 4 < sw;
+  u64 acc[2][NC][NP];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < NP; ++j) acc[0][c][j] = acc[1][c][j] = 0ull;
+  auto issue = [&](uint32_t g) {
+    const uint32_t r = 2 * g + crow;
+    if (r < sh && ccol) cp_async_16(ring + (r & (RING - 1)) * 64 + cchunk * 4, tile0 + (size_t)r * pitch + cchunk * 16);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int g = 0; g < RING / 2; ++g) issue((uint32_t)g);
+  const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(pool + ty.soff);
+  ulonglong2 wn = __ldg(wp);  // slots 0..3 of source row 0 (A <= 4 here); the next row's are requested one row ahead
+  const uint32_t npairs = (sh + 1) >> 1;
+#pragma unroll 1
+  for (uint32_t g = 0; g < npairs; ++g) {
+    cp_async_wait<RING / 2 - 1>();
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t r = 2 * g + h;
+      if (r < sh) {
+        const uint2 px = *reinterpret_cast<const uint2*>(ring + (r & (RING - 1)) * 64 + 2 * lane);
+        u64 w[NP];
+        w[0] = wn.x;
+        if (NP > 1) w[NP > 1 ? 1 : 0] = wn.y;
+        wp += 2;
+        if (r + 1 < sh) wn = __ldg(wp);
+        const float4 pa = px_to_f4<MODE>(px.x), pb = px_to_f4<MODE>(px.y);
+        const float ca[4] = {pa.x, pa.y, pa.z, pa.w}, cb[4] = {pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const u64 ppa = pk2(ca[c], ca[c]), ppb = pk2(cb[c], cb[c]);
+#pragma unroll
+          for (int jp = 0; jp < NP; ++jp) {
+            acc[0][c][jp] = mac2<MODE>(acc[0][c][jp], ppa, w[jp], k);
+            acc[1][c][jp] = mac2<MODE>(acc[1][c][jp], ppb, w[jp], k);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    issue(g + RING / 2);
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int o = 0; o < A; ++o) {
+    if ((uint32_t)o < dh) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        a[c] = (o & 1) ? hi2(acc[0][c][o / 2]) : lo2(acc[0][c][o / 2]);
+        b[c] = (o & 1) ? hi2(acc[1][c][o / 2]) : lo2(acc[1][c][o / 2]);
+      }
+      float4* srow = strip + o * kStripStride + 2 * lane;
+      srow[0] = make_float4(a[0], a[1], a[2], a[3]);
+      srow[1] = make_float4(b[0], b[1], b[2], b[3]);
     }
   }
 }
@@ -332,7 +407,13 @@ __device__ __forceinline__ void shrink_tile_warp(const uint8_t* __restrict__ img
   st.r = 0; st.pend = 0; st.o_next = 0; st.slot = 0; st.batch0 = 0; st.ob = 0;
   st.wa_n = make_ulonglong2(0ull, 0ull); st.wb_n = 0ull; st.nd_n = 0;
   const uint32_t slots = ty.slots;
-  if (slots) {
+  // every output row keeps its own slot for the whole walk: plain loop, all rows to the strip at the end
+  const bool simple = (slots == 2 && dh <= 2) || (slots == 4 && dh <= 4);
+  if (simple) {
+    if (slots == 2) shrink_vsimple<MODE, 2>(tile0, pitch, sw, sh, dh, ty, pool, strip, ring, k);
+    else shrink_vsimple<MODE, 4>(tile0, pitch, sw, sh, dh, ty, pool, strip, ring, k);
+    st.o_next = dh;
+  } else if (slots) {
     // cp.async ring: pair g = source rows 2g, 2g+1 (lanes 0-15 / 16-31 copy 16 bytes each); 8 pairs in flight
     const uint32_t crow = lane >> 4, cchunk = lane & 15u;
 #pragma unroll
@@ -345,19 +426,21 @@ __device__ __forceinline__ void shrink_tile_warp(const uint8_t* __restrict__ img
     st.wb_n = slots > 4 ? __ldg(reinterpret_cast<const u64*>(st.wp + 1)) : 0ull;
     st.nd_n = __ldg(st.dp);
   }
-  while (st.o_next < dh) {
-    switch (slots) {
-      case 2: shrink_vrun<MODE, 2>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
-      case 4: shrink_vrun<MODE, 4>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
-      case 6: shrink_vrun<MODE, 6>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
-      default: shrink_vrun_blocked<MODE>(st, tile0, pitch, sw, dh, ty, pool, strip, k); break;
+  do {
+    if (!simple) {
+      switch (slots) {
+        case 2: shrink_vrun<MODE, 2>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
+        case 4: shrink_vrun<MODE, 4>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
+        case 6: shrink_vrun<MODE, 6>(st, tile0, pitch, sw, sh, dh, strip, ring, k); break;
+        default: shrink_vrun_blocked<MODE>(st, tile0, pitch, sw, dh, ty, pool, strip, k); break;
+      }
     }
     __syncwarp();
     shrink_horizontal<MODE>(strip, st.batch0, st.o_next - st.batch0, dw, ht, dst, k);
     __syncwarp();
     st.batch0 = st.o_next;
-  }
-  if (slots) cp_async_wait<0>();
+  } while (st.o_next < dh);
+  if (slots && !simple) cp_async_wait<0>();
 }
 
 template <bool FUSED>
