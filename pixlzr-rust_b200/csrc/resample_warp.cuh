@@ -620,19 +620,20 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
         for (int c = 0; c < NC; ++c) a[c] = mac1<MODE>(a[c], win[j][c], w[j]);
       if (vact) strip[soff + x] = make_float4(a[0], a[1], a[2], a[3]);
     };
-    // table rows of the next pair of output rows are requested before the horizontal pass of the current pair
-    ulonglong2 n01 = __ldg(gp), n23 = __ldg(gp + 1), n45 = __ldg(gp + 2), n67 = __ldg(gp + 3);
-    uint32_t nla = __ldg(gleft), nlb = dh > 1 ? __ldg(gleft + 1) : nla;
-    for (uint32_t oy0 = 0; oy0 < dh; oy0 += 2) {
-      const uint32_t nrows = min(2u, dh - oy0);
-      const uint32_t la = nla, lb = nlb;
-      const ulonglong2 w01 = n01, w23 = n23, w45 = n45, w67 = n67;
+    // The table rows of a pair of output rows are requested right after the vertical pass of the previous pair (into
+    // the same registers: they are dead by then), one horizontal pass before they are used.
+    ulonglong2 w01 = __ldg(gp), w23 = __ldg(gp + 1), w45 = __ldg(gp + 2), w67 = __ldg(gp + 3);
+    uint32_t la = __ldg(gleft), lb = dh > 1 ? __ldg(gleft + 1) : la;
+    auto request_next = [&](uint32_t oy0) {
       if (oy0 + 2 < dh) {
         const ulonglong2* wn = gp + 4 * ((oy0 >> 1) + 1);
-        n01 = __ldg(wn); n23 = __ldg(wn + 1); n45 = __ldg(wn + 2); n67 = __ldg(wn + 3);
-        nla = __ldg(gleft + oy0 + 2);
-        nlb = oy0 + 3 < dh ? __ldg(gleft + oy0 + 3) : nla;
+        w01 = __ldg(wn); w23 = __ldg(wn + 1); w45 = __ldg(wn + 2); w67 = __ldg(wn + 3);
+        la = __ldg(gleft + oy0 + 2);
+        lb = oy0 + 3 < dh ? __ldg(gleft + oy0 + 3) : la;
       }
+    };
+    for (uint32_t oy0 = 0; oy0 < dh; oy0 += 2) {
+      const uint32_t nrows = min(2u, dh - oy0);
       if (la == lb) {
         advance(la);
         const u64 w[7] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x};
@@ -667,6 +668,7 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
         vrow_solo(oy0, 0);
         vrow_solo(oy0 + 1, row1);
       }
+      request_next(oy0);
       __syncwarp();
       horizontal(oy0, nrows);
       __syncwarp();
