@@ -508,26 +508,36 @@ __device__ __forceinline__ uint32_t scaled_dim(uint32_t n, uint32_t k) {  // ope
   return d < 1 ? 1 : d;
 }
 
+// a * b as the reference's host computes it: a NaN operand comes back as it is (x86 returns the first NaN operand,
+// sign included), where the GPU would produce the canonical positive NaN.  The sign matters: the Sobel metric of a
+// block without interior pixels is 0/0 = the *negative* default NaN, which parse_value sends through `1 + v` to 0
+// (operations.rs:128-138), i.e. to a 1-pixel block, while a positive NaN keeps the block at full size.
+__device__ __forceinline__ float mul_host(float a, float b) {
+  if (a != a) return a;
+  if (b != b) return b;
+  return __fmul_rn(a, b);
+}
+
 __device__ __forceinline__ void map_values(const ValueMap& vm, const float* minmax, float rx, float ry, float& v0,
                                            float& v1) {
   if (vm.normalise) {
     // extension: v' = (v - min) / (max - min), 0 when the range is empty
     const float mnx = minmax[0], mxx = -minmax[1];
     const float rgx = __fsub_rn(mxx, mnx);
-    rx = (rgx > 0.f) ? __fdiv_rn(__fsub_rn(rx, mnx), rgx) : 0.f;
+    rx = (rgx > 0.f) ? (rx == rx ? __fdiv_rn(__fsub_rn(rx, mnx), rgx) : rx) : 0.f;  // a NaN value stays the NaN it is (host arithmetic)
     if (vm.mode == 2) {
       const float mny = minmax[2], mxy = -minmax[3];
       const float rgy = __fsub_rn(mxy, mny);
-      ry = (rgy > 0.f) ? __fdiv_rn(__fsub_rn(ry, mny), rgy) : 0.f;
+      ry = (rgy > 0.f) ? (ry == ry ? __fdiv_rn(__fsub_rn(ry, mny), rgy) : ry) : 0.f;
     }
   }
   if (vm.mode == 0) {
-    v0 = v1 = __fmul_rn(__fmul_rn(rx, vm.factor), 10.0f);  // pixlzr.rs:162
+    v0 = v1 = mul_host(mul_host(rx, vm.factor), 10.0f);  // pixlzr.rs:162
   } else if (vm.mode == 1) {
     v0 = v1 = rx;  // process/mod.rs:110
   } else {
-    v0 = __fmul_rn(rx, vm.factor);  // pixlzr.rs:199
-    v1 = __fmul_rn(ry, vm.factor);
+    v0 = mul_host(rx, vm.factor);  // pixlzr.rs:199
+    v1 = mul_host(ry, vm.factor);
   }
 }
 

@@ -544,3 +544,42 @@ def test_cli_conversions(tmp_path):
     assert np.array_equal(np.array(Image.open(out_png)), load_png("Big-Ruscher.pix.png"))
     assert np.array_equal(P.Pixlzr.open(out_pix2).to_image(P.FilterType.Nearest), load_png("Big-Ruscher.pix.png"))
     assert P.cli.main(["-i", str(tmp_path / "missing.png"), "-o", out_png]) == 1
+
+
+def test_random_shapes_seeded_warp_kernels(forced_ctx):
+    """The seeded sweep again, RGBA with 4-px aligned widths and blocks up to 64x64 (what the warp-per-tile kernels take), on a
+    context that forces them regardless of the tile count: ragged trailing tiles, odd heights, irregular ratios, Sobel."""
+    ctx = forced_ctx["warp"]
+    rng = np.random.default_rng(777)
+    for it in range(20):
+        bw, bh = int(rng.choice([8, 16, 24, 32, 40, 64])), int(rng.choice([8, 16, 24, 32, 48, 64]))
+        w, h = max(4, int(rng.integers(4, 420)) // 4 * 4), int(rng.integers(2, 300))
+        filt_d, filt_u = int(rng.choice(FILTERS)), int(rng.choice(FILTERS))
+        metric = int(rng.choice([O.METRIC_OKLAB_MAD, O.METRIC_OKLAB_MAD, O.METRIC_SOBEL_DIR]))
+        if metric == O.METRIC_SOBEL_DIR and (min(bh, h % bh or bh) < 2 or h < 2):
+            metric = O.METRIC_OKLAB_MAD
+        factor = float(rng.choice([0.2, 1.0, 3.0])) * (8.0 if metric == O.METRIC_SOBEL_DIR else 1.0)
+        img = synth(w, h, 4, seed=100 + it)
+        if it % 3 == 0:
+            img[: h // 2, :, 3] = img[: h // 2, :, 1]  # translucent half
+        ref = O.shrink(img, bw, bh, metric, factor, filt_d, nthreads=8)
+        descs, pixels, _ = gpu_shrink(ctx, img, bw, bh, metric, factor, filt_d)
+        assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"]), (it, w, h, bw, bh, metric)
+        assert np.array_equal(pixels, ref.payload), (it, w, h, bw, bh, metric, filt_d)
+        pl = ctx.payload_upload(w, h, bw, bh, 4, descs, pixels)
+        out = pl.expand(filt_u)
+        pl.free()
+        assert np.array_equal(out, O.expand(ref, filt_u, nthreads=8)), (it, w, h, bw, bh, metric, filt_u)
+
+
+def test_sobel_block_without_interior_pixels(ctx):
+    """A trailing block 2 rows high has no 3x3 window: the reference's metric is 0/0, the *negative* default NaN on its
+    host, which parse_value turns into a 1-pixel block (operations.rs:128-138, 253-254).  Also through the normalise
+    extension, whose min/max ignore NaNs."""
+    img = synth(136, 50, 4, seed=3)  # 50 = 6 * 8 + 2
+    for flags, norm in ((0, False), (N.FLAG_NORMALISE_GLOBAL, True)):
+        ref = O.shrink(img, 64, 8, O.METRIC_SOBEL_DIR, 8.0, O.LANCZOS3, normalise_global=norm)
+        descs, pixels, _ = gpu_shrink(ctx, img, 64, 8, N.METRIC_SOBEL_DIR, 8.0, O.LANCZOS3, flags)
+        assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+        assert (descs["w"][-3:] == 1).all() and (descs["h"][-3:] == 1).all()
+        assert np.array_equal(pixels, ref.payload)
