@@ -2,7 +2,7 @@
 throughput on the B200 (device-timed and end-to-end through the C ABI), the CPU oracle on 1 and all host
 cores, and the parity of the GPU result against the oracle (grid, dims, values, pixels, PSNR).
 
-    python tools/config_table.py > gpurun_out/config_table.md        (run under gpurun)
+    python tests/tools/config_table.py > gpurun_out/config_table.md        (run under gpurun)
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import oracle as O  # noqa: E402

@@ -1,12 +1,12 @@
 """Longer seeded fuzz of the whole encode / decode path against the oracle (run under gpurun; not part of the test suite):
 random image and block shapes, both channel counts, both metrics, every filter pair, flags, both resample kernel families.
-    python tools/fuzz_parity.py [iterations] [seed]"""
+    python tests/tools/fuzz_parity.py [iterations] [seed]"""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle as O
 import pixlzr_b200 as P
 
