@@ -457,6 +457,9 @@ __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shr
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kShrinkWarps;
   constexpr int F = FUSED ? 2 : 0;
+  uint32_t last_tx = 0xFFFFFFFFu, last_ty = 0xFFFFFFFFu;
+  AxisTab ty{};
+  HTab ht{};
   auto process = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti) {
     const Tile t = tile_of(g, b);
     if (d.w == 0 || d.h == 0) return;  // masked out (quadtree levels)
@@ -482,10 +485,17 @@ __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shr
       }
       return;
     }
-    const AxisTab ty = tabs[ti >> 16];
-    __syncwarp();  // the previous tile's horizontal pass is done with the table copy
-    const HTab ht = stage_htab(tabs[ti & 0xFFFFu], d.w, pool, htab_smem);
-    __syncwarp();
+    // tiles come in cost order, so a warp's consecutive tiles mostly share their tables: keep them
+    if ((ti >> 16) != last_ty) {
+      ty = tabs[ti >> 16];
+      last_ty = ti >> 16;
+    }
+    if ((ti & 0xFFFFu) != last_tx) {
+      __syncwarp();  // the previous tile's horizontal pass is done with the table copy
+      ht = stage_htab(tabs[ti & 0xFFFFu], d.w, pool, htab_smem);
+      __syncwarp();
+      last_tx = ti & 0xFFFFu;
+    }
     const bool opaque = opaque_flags != nullptr && opaque_flags[b] != 0;
     if (opaque) shrink_tile_warp<F>(img, pitch, t, d, ht, ty, pool, strip, ring, payload, k);
     else shrink_tile_warp<F | 1>(img, pitch, t, d, ht, ty, pool, strip, ring, payload, k);
