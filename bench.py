@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -79,6 +79,15 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout: float = 3.0):
+        """nvidia-smi needs a few hundred ms before its first line: do not start the timed region before it polls."""
+        t = time.time()
+        while self.proc is not None and not self.lines and time.time() - t < timeout:
+            time.sleep(0.01)
+
+    def samples_since(self, t0: float) -> int:
+        return sum(1 for (t, _) in self.lines if t >= t0)
 
     def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
@@ -237,7 +246,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
                                int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
         sampler.start()
-        time.sleep(0.25)
+        sampler.wait_first()
         launches0 = sum(c.launch_count() for c in ctxs)
         for c in ctxs:
             c.profile_enable(True)
@@ -266,7 +275,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 prof[name] = (a + ms, b + n)
             c.profile_enable(False)
         launches = sum(c.launch_count() for c in ctxs) - launches0
+        # the timed region is a few ms, nvidia-smi polls every >= 20 ms: the same steps keep running (untimed, outside the
+        # launch count) until at least two polls have seen the GPU under this load
+        t_keep = time.time()
+        while sampler.proc is not None and sampler.samples_since(t_wall0) < 2 and time.time() - t_keep < 1.0:
+            step_device()
+            torch.cuda.synchronize()
+        t_wall1 = time.time()
         clocks = sampler.stop(t_wall0, t_wall1)
+        clocks["window"] = "timed region + the same steps continued (untimed) until two nvidia-smi polls"
         # per-kernel durations without cross-stream contention: the same K steps again on the launching stream only
         prof_overlapped = prof
         if n_streams > 1:
