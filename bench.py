@@ -372,6 +372,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+    if world > 1:  # whole-job launch count
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     mp_per_step = world * batch * IMG_W * IMG_H / 1e6
     value = mp_per_step * args.steps / (elapsed_ms / 1e3)
     e2e_value = mp_per_step * e2e_steps / (e2e_ms / 1e3)
