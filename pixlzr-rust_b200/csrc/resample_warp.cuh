@@ -29,7 +29,8 @@ constexpr int kRingRows = PXZ_RING_ROWS;  // shrink: source rows in flight per w
 constexpr int kHTabWords = 512;       // shrink: per-warp copy of the tile's horizontal table (2 KB), else read via L1
 constexpr int kShrinkWarpBytes = kStripRows * kStripStride * 16 + kRingRows * 64 * 4 + kHTabWords * 4;
 constexpr int kExpandRow1 = 68;       // expand: second strip row starts at 64 + pad (pad chosen per tile, <= 4)
-constexpr int kExpandWarpBytes = (kExpandRow1 + 64 + 8) * 16;
+constexpr int kExpandPairPx = kExpandRow1 + 64 + 8;  // one pair of strip rows (second row at 64 + pad), + the walk's overrun
+constexpr int kExpandWarpBytes = 2 * kExpandPairPx * 16;  // two pairs: blocks at most 16 wide run two row pairs per vertical pass
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
@@ -572,14 +573,15 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
   ulonglong2 hwr[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) hwr[c] = (hact && (uint32_t)c < bpad) ? __ldg(hw + c) : make_ulonglong2(0ull, 0ull);
-  auto horizontal = [&](uint32_t oy0, uint32_t nrows) {
+  auto horizontal = [&](uint32_t oy0, uint32_t nrows, uint32_t sb) {
     if (hact && hr < nrows) {
+      const float4* tp = htp + sb;
       Acc4<MODE> acc;
-      if (bpad == 8) expand_walk<MODE, 8>(acc, htp, hwr, k);
-      else if (bpad == 4) expand_walk<MODE, 4>(acc, htp, hwr, k);
-      else if (bpad == 2) expand_walk<MODE, 2>(acc, htp, hwr, k);
+      if (bpad == 8) expand_walk<MODE, 8>(acc, tp, hwr, k);
+      else if (bpad == 4) expand_walk<MODE, 4>(acc, tp, hwr, k);
+      else if (bpad == 2) expand_walk<MODE, 2>(acc, tp, hwr, k);
       else
-        for (uint32_t c = 0; c < hn; ++c) acc.step(htp[c], __ldg(hw + c), k);
+        for (uint32_t c = 0; c < hn; ++c) acc.step(tp[c], __ldg(hw + c), k);
       uint32_t* o = reinterpret_cast<uint32_t*>(dst + (size_t)(oy0 + hr) * pitch) + hox;
       const uint32_t p0 = pack_px<MODE>(acc.out(0)), p1 = pack_px<MODE>(acc.out(1));
       const uint32_t p2 = pack_px<MODE>(acc.out(2)), p3 = pack_px<MODE>(acc.out(3));
@@ -595,8 +597,11 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
 
   if (sw <= 32) {
     // vertical: lane = source column; a 7-row window of converted samples lives in registers and moves down with the
-    // outputs' first tap.  Two output rows with the same first tap are the two lanes of one f32x2 accumulator.
-    const uint32_t x = lane;
+    // outputs' first tap.  Two output rows with the same first tap are the two lanes of one f32x2 accumulator.  Blocks
+    // at most 16 wide use the upper half warp for the next pair of rows (own window, own table rows): 4 rows per pass.
+    const uint32_t nh = sw <= 16 ? 2u : 1u;
+    const uint32_t half = nh == 2 ? lane >> 4 : 0u, x = nh == 2 ? (lane & 15u) : lane;
+    const uint32_t sb = half * kExpandPairPx;
     const bool vact = x < sw;
     float win[7][NC];
     auto conv = [&](uint32_t word, float(&o)[NC]) {
@@ -628,23 +633,26 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
       for (int j = 0; j < 7; ++j)
 #pragma unroll
         for (int c = 0; c < NC; ++c) a[c] = mac1<MODE>(a[c], win[j][c], w[j]);
-      if (vact) strip[soff + x] = make_float4(a[0], a[1], a[2], a[3]);
+      if (vact) strip[sb + soff + x] = make_float4(a[0], a[1], a[2], a[3]);
     };
     // The table rows of a pair of output rows are requested right after the vertical pass of the previous pair (into
     // the same registers: they are dead by then), one horizontal pass before they are used.
-    ulonglong2 w01 = __ldg(gp), w23 = __ldg(gp + 1), w45 = __ldg(gp + 2), w67 = __ldg(gp + 3);
-    uint32_t la = __ldg(gleft), lb = dh > 1 ? __ldg(gleft + 1) : la;
-    auto request_next = [&](uint32_t oy0) {
-      if (oy0 + 2 < dh) {
-        const ulonglong2* wn = gp + 4 * ((oy0 >> 1) + 1);
+    ulonglong2 w01 = make_ulonglong2(0ull, 0ull), w23 = w01, w45 = w01, w67 = w01;
+    uint32_t la = 0, lb = 0;
+    auto request = [&](uint32_t oy) {  // table rows of the pair (oy, oy + 1)
+      if (oy < dh) {
+        const ulonglong2* wn = gp + 4 * (oy >> 1);
         w01 = __ldg(wn); w23 = __ldg(wn + 1); w45 = __ldg(wn + 2); w67 = __ldg(wn + 3);
-        la = __ldg(gleft + oy0 + 2);
-        lb = oy0 + 3 < dh ? __ldg(gleft + oy0 + 3) : la;
+        la = __ldg(gleft + oy);
+        lb = oy + 1 < dh ? __ldg(gleft + oy + 1) : la;
       }
     };
-    for (uint32_t oy0 = 0; oy0 < dh; oy0 += 2) {
-      const uint32_t nrows = min(2u, dh - oy0);
-      if (la == lb) {
+    request(2 * half);
+    for (uint32_t oy0 = 0; oy0 < dh; oy0 += 2 * nh) {
+      const uint32_t my = oy0 + 2 * half;  // this lane's pair of output rows
+      if (my >= dh) {
+        // no rows left for the upper half warp
+      } else if (la == lb) {
         advance(la);
         const u64 w[7] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x};
         u64 a[NC];
@@ -671,16 +679,17 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
           float lo_[4] = {0.f, 0.f, 0.f, 0.f}, hi_[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < NC; ++c) unpk2(a[c], lo_[c], hi_[c]);
-          strip[x] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
-          strip[row1 + x] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
+          strip[sb + x] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
+          strip[sb + row1 + x] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
         }
       } else {
-        vrow_solo(oy0, 0);
-        vrow_solo(oy0 + 1, row1);
+        vrow_solo(my, 0);
+        vrow_solo(my + 1, row1);
       }
-      request_next(oy0);
+      request(my + 2 * nh);
       __syncwarp();
-      horizontal(oy0, nrows);
+      horizontal(oy0, min(2u, dh - oy0), 0u);
+      if (nh == 2 && oy0 + 2 < dh) horizontal(oy0 + 2, min(2u, dh - oy0 - 2), (uint32_t)kExpandPairPx);
       __syncwarp();
     }
   } else {
@@ -708,7 +717,7 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
         if (has1) strip[r * row1 + lane + 32] = make_float4(a1[0], a1[1], a1[2], a1[3]);
       }
       __syncwarp();
-      horizontal(oy0, nrows);
+      horizontal(oy0, nrows, 0u);
       __syncwarp();
     }
   }
