@@ -254,11 +254,12 @@ __device__ __forceinline__ void shrink_vrun(ShrinkRun<MODE>& st, const uint8_t* 
     st.pend = st.nd_n;
     st.wp += 2;
     ++st.dp;
-    if (r + 1 < sh) {  // the table row of the next source row is requested before this row's arithmetic
-      st.wa_n = __ldg(st.wp);
-      if (NP > 2) st.wb_n = __ldg(reinterpret_cast<const u64*>(st.wp + 1));
-      st.nd_n = __ldg(st.dp);
-    }
+    // the table row of the next source row is requested before this row's arithmetic — unconditionally (a predicated
+    // load makes ptxas copy the registers out and back): after the last row it reads the words behind the table, which
+    // the pool always has (build_axis_table pads it) and nobody uses
+    st.wa_n = __ldg(st.wp);
+    if (NP > 2) st.wb_n = __ldg(reinterpret_cast<const u64*>(st.wp + 1));
+    st.nd_n = __ldg(st.dp);
     const float4 pa = px_to_f4<MODE>(px.x), pb = px_to_f4<MODE>(px.y);
     const float ca[4] = {pa.x, pa.y, pa.z, pa.w}, cb[4] = {pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
@@ -322,7 +323,7 @@ __device__ __forceinline__ void shrink_vsimple(const uint8_t* tile0, size_t pitc
         w[0] = wn.x;
         if (NP > 1) w[NP > 1 ? 1 : 0] = wn.y;
         wp += 2;
-        if (r + 1 < sh) wn = __ldg(wp);
+        wn = __ldg(wp);  // unconditional, see shrink_vrun
         const float4 pa = px_to_f4<MODE>(px.x), pb = px_to_f4<MODE>(px.y);
         const float ca[4] = {pa.x, pa.y, pa.z, pa.w}, cb[4] = {pb.x, pb.y, pb.z, pb.w};
 #pragma unroll

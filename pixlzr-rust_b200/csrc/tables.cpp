@@ -211,6 +211,7 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
           (*pool)[sbase + (size_t)r * 8 + (o % slots)] = (*pool)[wbase + (size_t)o * stride + (r - lefts[o])];
         (*pool)[sbase + (size_t)n_in * 8 + (tr[o] - 1)] += 1u;
       }
+      pool->resize(pool->size() + 12, 0u);  // the kernels prefetch one table row (and one count) past the end
       tab->soff = (uint32_t)sbase;
       tab->slots = slots;
     }
