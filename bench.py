@@ -421,7 +421,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                         "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(algo[dom]), "avg_launch_us": kernels[dom]["us"],
                         "timing": ("CUDA events around every launch; single-stream pass of the same K steps right after the "
-                                   "timed region (in the 2-stream timed region kernels of different images overlap: see "
+                                   "timed region (in the multi-stream timed region kernels of different images overlap: see "
                                    "kernels[*].us_in_timed_region)") if n_streams > 1 else
                                   "CUDA events around every launch inside the timed region",
                         "single_stream_value_MPps": round(world * batch * IMG_W * IMG_H / 1e6 * args.steps / (solo_ms / 1e3), 1)}
@@ -461,7 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="8K images per rank per step")
-    ap.add_argument("--streams", type=int, default=2, help="contexts / CUDA streams of the device-resident leg")
+    ap.add_argument("--streams", type=int, default=4, help="contexts / CUDA streams of the device-resident leg")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads (contexts) of the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
