@@ -74,6 +74,9 @@ typedef struct {
 int pxz_abi_version(void);
 /* number of usable CUDA devices (0 if none / no driver) */
 int pxz_device_count(void);
+/* One context per host thread; it owns one CUDA stream and its scratch.  Environment read at creation (diagnostics only):
+ *   PXZ_RESAMPLE_KERNELS=warp|cta  force one of the two resample kernel families (default: by tile count),
+ *   PXZ_GUARD_REL / PXZ_GUARD_ABS  guard band of the fast Oklab-MAD path. */
 pxz_status pxz_ctx_create(int device, pxz_ctx** out);
 /* same, but work is ordered on an existing CUDA stream (cudaStream_t / CUstream passed as
  * void*), e.g. torch.cuda.current_stream().cuda_stream.  The stream must outlive the ctx. */
