@@ -224,6 +224,8 @@ pxz_status ensure_scratch(pxz_ctx* ctx, uint32_t nblocks) {
     ctx->scan_cap = 0;
     pxz_status st;
     if ((st = dev_alloc(ctx, &ctx->d_scan, need)) != PXZ_OK) return st;
+    // the plan / work-order kernels find this zeroed and leave it zeroed
+    PXZ_CUDA(ctx, cudaMemsetAsync(ctx->d_scan, 0, need, ctx->stream));
     ctx->scan_cap = need;
   }
   return PXZ_OK;
@@ -599,7 +601,8 @@ static pxz_status run_analysis(pxz_ctx* ctx, const pxz_image* img, const Geom& g
     } else {
       {
         ProfScope prof(ctx, K_MAD_FAST);
-        PXZ_CUDA(ctx, launch_analyze_mad_fast(img->d, img->pitch, g, ctx->d_vx, ctx->d_opaque, ctx->stream, ctx->sm_count, &ctx->launches));
+        PXZ_CUDA(ctx, launch_analyze_mad_fast(img->d, img->pitch, g, ctx->d_vx, ctx->d_opaque, ctx->d_list + nblocks, ctx->stream,
+                                              ctx->sm_count, &ctx->launches));
       }
       if (vm_for_band) {
         // recompute, in reference order, the tiles whose level could differ from the CPU result

@@ -216,7 +216,9 @@ __device__ __forceinline__ OklabFast2 lms_fast_pair2(uint32_t px0, uint32_t px1,
 #endif
 template <int G, int QPT>
 __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
-                                                                  float* __restrict__ vx, uint8_t* __restrict__ opaque) {
+                                                                  float* __restrict__ vx, uint8_t* __restrict__ opaque,
+                                                                  uint32_t* __restrict__ zero_word) {
+  if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;  // the guard-band list counter of the next kernel
   constexpr int TPC = kThreads / G;  // tiles per CTA iteration
   constexpr int WPG = G / 32;        // warps per group
   extern __shared__ float s_lut[];   // [256][32]
@@ -387,7 +389,9 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
 // 16 * 256 pixels recomputes the rest in pass 2.
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_analyze_mad_any(const uint8_t* __restrict__ img, size_t pitch, Geom g,
-                                                              float* __restrict__ vx, uint8_t* __restrict__ opaque) {
+                                                              float* __restrict__ vx, uint8_t* __restrict__ opaque,
+                                                              uint32_t* __restrict__ zero_word) {
+  if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;
   extern __shared__ float s_lut[];
   __shared__ float s_r1[kThreads / 32][4];
   __shared__ float s_r2[kThreads / 32];
@@ -918,9 +922,10 @@ __device__ __forceinline__ uint32_t cost_class(uint32_t w, uint32_t h, uint32_t 
 constexpr int kPlanItems = 1;
 constexpr int kPlanTile = kThreads * kPlanItems;
 
+// All of it is zero between launches: the CTA that finishes last puts it back (no memset per call).
 struct ScanState {
   unsigned int ticket;
-  unsigned int pad;
+  unsigned int done;             // CTAs that are through with the shared state
   unsigned long long status[1];  // [num_tiles]: flag << 62 | value ; flag 1 = aggregate, 2 = inclusive prefix
 };
 
@@ -1050,6 +1055,18 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
       lists[(size_t)cls[j] * cap + s_base[cls[j]] + rank[j]] = b;
       excl += sz[j];
     }
+  }
+  // the CTA that finishes last leaves ticket, status and cursors zeroed for the next launch on this stream
+  __shared__ bool s_last;
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(&st->done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (uint32_t i = tid; i < gridDim.x; i += kThreads) st->status[i] = 0ull;
+    if (tid < 2 * kCostClasses) cursor[tid] = 0u;
+    if (tid == 0) { st->ticket = 0u; st->done = 0u; }
   }
 }
 
@@ -1773,8 +1790,10 @@ __global__ void __launch_bounds__(kThreads) k_class_lists(const pxz_block_desc* 
   if (b < nblocks) lists[(size_t)cls * cap + s_base[cls] + rank] = b;
   if (tid == 0) {
     __threadfence();
-    if (atomicAdd(&cursor[kCostClasses], 1u) == gridDim.x - 1)
+    if (atomicAdd(&cursor[kCostClasses], 1u) == gridDim.x - 1) {
       for (int c = 0; c < kCostClasses; ++c) lists[(size_t)kCostClasses * cap + c] = atomicAdd(&cursor[c], 0u);
+      for (int c = 0; c <= kCostClasses; ++c) cursor[c] = 0u;  // zero again for the next launch (k_plan shares the words)
+    }
   }
 }
 
@@ -1811,7 +1830,7 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 }
 
 cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, uint8_t* opaque,
-                                    cudaStream_t s, int sm_count, uint64_t* launches) {
+                                    uint32_t* zero_word, cudaStream_t s, int sm_count, uint64_t* launches) {
   const uint32_t ntiles = g.cols * g.rows;
   const size_t smem = 256 * 32 * sizeof(float);
   const bool aligned = g.C == 4 && (g.bw % 4 == 0) && (g.W % 4 == 0) && (pitch % 16 == 0) &&
@@ -1824,28 +1843,28 @@ cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom
     if (quads > 512) {
       e = set_smem(k_analyze_mad_rgba<256, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
     } else if (quads > 256) {
       e = set_smem(k_analyze_mad_rgba<128, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
     } else if (quads > 128) {
       e = set_smem(k_analyze_mad_rgba<64, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
     } else {
       e = set_smem(k_analyze_mad_rgba<32, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
     }
   } else if (g.C == 4) {
     e = set_smem(k_analyze_mad_any<4>, smem);
     if (e != cudaSuccess) return e;
-    k_analyze_mad_any<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+    k_analyze_mad_any<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
   } else {
     e = set_smem(k_analyze_mad_any<3>, smem);
     if (e != cudaSuccess) return e;
-    k_analyze_mad_any<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque);
+    k_analyze_mad_any<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
   }
   return cudaGetLastError();
 }
@@ -1859,8 +1878,7 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
   cudaError_t e;
   const bool banded = vx_fast != nullptr;
   if (banded) {
-    e = cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
+    // *count was zeroed by the fast analysis kernel that produced vx_fast (launch_analyze_mad_fast's zero_word)
     ++*launches;
     k_band_list<<<(ntiles + kThreads - 1) / kThreads, kThreads, 0, s>>>(vx_fast, opaque, g, (int)g.C, *vm, *thr, *band, minmax,
                                                                        list, count);
@@ -1927,8 +1945,7 @@ cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const V
                         uint64_t* total_bytes, void* scan_state, uint32_t* lists, uint32_t cap, cudaStream_t s, uint64_t* launches) {
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t tiles = (nblocks + kPlanTile - 1) / kPlanTile;
-  cudaError_t e = cudaMemsetAsync(scan_state, 0, plan_scan_state_bytes(nblocks), s);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;  // scan_state is zero on entry and on exit (ensure_scratch clears it once)
   ++*launches;
   uint32_t* cursor = reinterpret_cast<uint32_t*>(scan_state);
   k_plan<<<tiles, kThreads, 0, s>>>(vx, vy, g, vm, minmax, thr, mask, descs, tabidx,
@@ -1941,9 +1958,7 @@ cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const V
 cudaError_t launch_class_lists(const pxz_block_desc* descs, const Geom& g, void* scan_state, uint32_t* lists, uint32_t cap,
                                cudaStream_t s, uint64_t* launches) {
   const uint32_t nblocks = g.cols * g.rows;
-  uint32_t* cursor = reinterpret_cast<uint32_t*>(scan_state);
-  cudaError_t e = cudaMemsetAsync(cursor, 0, kClassHistBytes, s);
-  if (e != cudaSuccess) return e;
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(scan_state);  // zero on entry and on exit
   ++*launches;
   k_class_lists<<<(nblocks + kThreads - 1) / kThreads, kThreads, 0, s>>>(descs, g, cursor, lists, cap);
   return cudaGetLastError();

@@ -71,8 +71,10 @@ struct GuardBand {
 
 // ---- kernel launchers (kernels.cu) ---------------------------------------------------------
 // All return cudaGetLastError() of the launch; *launches is incremented per kernel launched.
+// zero_word (may be NULL): a device word the kernel clears — the guard-band list counter launch_analyze_mad_exact
+// appends to next (saves a memset launch per image)
 cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, uint8_t* opaque,
-                                    cudaStream_t s, int sm_count, uint64_t* launches);
+                                    uint32_t* zero_word, cudaStream_t s, int sm_count, uint64_t* launches);
 cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
                                      const uint8_t* opaque, const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
                                      const float* minmax, uint32_t* list, uint32_t* count, cudaStream_t s, int sm_count,
