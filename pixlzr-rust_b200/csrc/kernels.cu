@@ -73,6 +73,14 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may become resident while the kernel before it
+// on the stream is still draining.  pdl_wait() blocks until that kernel has completed and its writes are visible —
+// every kernel calls it before it touches global memory that another kernel writes or reads — and pdl_trigger() lets
+// the kernel behind this one start being scheduled as soon as SM resources free up.  Without the launch attribute
+// both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // x >= 0.  cube root through the SFU: 2^(log2(x)/3); ~4e-7 relative error (fast path only).
 __device__ __forceinline__ float cbrt_fast(float x) {
   float l, r;
@@ -218,7 +226,6 @@ template <int G, int QPT>
 __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgba(const uint8_t* __restrict__ img, size_t pitch, Geom g,
                                                                   float* __restrict__ vx, uint8_t* __restrict__ opaque,
                                                                   uint32_t* __restrict__ zero_word) {
-  if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;  // the guard-band list counter of the next kernel
   constexpr int TPC = kThreads / G;  // tiles per CTA iteration
   constexpr int WPG = G / 32;        // warps per group
   extern __shared__ float s_lut[];   // [256][32]
@@ -248,6 +255,10 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
 #define QROW(j) (qrc[j] >> 16)
 #define QCOL(j) (qrc[j] & 0xFFFFu)
   const bool cta_all_in = __syncthreads_and(all_in) != 0;
+  // everything above (the 32 KB table, the quad mapping) may run while the previous kernel on the stream drains
+  pdl_wait();
+  pdl_trigger();
+  if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;  // the guard-band list counter of the next kernel
 
   auto load_tile = [&](uint32_t tile, uint4(&v)[QPT]) {
     if (tile < ntiles) {
@@ -391,6 +402,8 @@ template <int C>
 __global__ void __launch_bounds__(kThreads) k_analyze_mad_any(const uint8_t* __restrict__ img, size_t pitch, Geom g,
                                                               float* __restrict__ vx, uint8_t* __restrict__ opaque,
                                                               uint32_t* __restrict__ zero_word) {
+  pdl_wait();
+  pdl_trigger();
   if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;
   extern __shared__ float s_lut[];
   __shared__ float s_r1[kThreads / 32][4];
@@ -701,6 +714,8 @@ __global__ void __launch_bounds__(kThreads) k_band_list(const float* __restrict_
                                                         Geom g, int C, ValueMap vm, LevelThresholds thr, GuardBand band,
                                                         const float* minmax, uint32_t* __restrict__ list,
                                                         uint32_t* __restrict__ count) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t ntiles = g.cols * g.rows;
   const uint32_t tile = blockIdx.x * kThreads + threadIdx.x;
   if (tile >= ntiles) return;
@@ -717,9 +732,11 @@ __global__ void __launch_bounds__(kExactThreads) k_mad_exact(const uint8_t* __re
   float* s_val = s_dyn;  // 4 * kExactStride
   __shared__ float s_lut256[256];
   __shared__ float s_avg[4];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut256[i] = c_srgb_lut[i];
+  pdl_wait();
+  pdl_trigger();
   const uint32_t n = list ? *count : g.cols * g.rows;
   if (blockIdx.x >= n) return;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut256[i] = c_srgb_lut[i];
   __syncthreads();
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
     const uint32_t tile = list ? list[i] : i;
@@ -941,6 +958,8 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
   __shared__ unsigned long long s_warp[kThreads / 32];
   __shared__ unsigned long long s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  pdl_trigger();
   if (tid == 0) s_tile = atomicAdd(&st->ticket, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
@@ -1823,6 +1842,22 @@ __global__ void __launch_bounds__(kThreads) k_tree_mask(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 static inline int clamp_grid(long long want, long long cap) { return (int)(want < 1 ? 1 : (want > cap ? cap : want)); }
 
+// launch with programmatic stream serialization (see pdl_wait): the kernel may be scheduled while its predecessor drains
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -1843,28 +1878,28 @@ cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom
     if (quads > 512) {
       e = set_smem(k_analyze_mad_rgba<256, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<256, 4><<<clamp_grid(ntiles, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
+      e = launch_pdl(k_analyze_mad_rgba<256, 4>, clamp_grid(ntiles, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
     } else if (quads > 256) {
       e = set_smem(k_analyze_mad_rgba<128, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<128, 4><<<clamp_grid((ntiles + 1) / 2, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
+      e = launch_pdl(k_analyze_mad_rgba<128, 4>, clamp_grid((ntiles + 1) / 2, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
     } else if (quads > 128) {
       e = set_smem(k_analyze_mad_rgba<64, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<64, 4><<<clamp_grid((ntiles + 3) / 4, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
+      e = launch_pdl(k_analyze_mad_rgba<64, 4>, clamp_grid((ntiles + 3) / 4, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
     } else {
       e = set_smem(k_analyze_mad_rgba<32, 4>, smem);
       if (e != cudaSuccess) return e;
-      k_analyze_mad_rgba<32, 4><<<clamp_grid((ntiles + 7) / 8, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
+      e = launch_pdl(k_analyze_mad_rgba<32, 4>, clamp_grid((ntiles + 7) / 8, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
     }
   } else if (g.C == 4) {
     e = set_smem(k_analyze_mad_any<4>, smem);
     if (e != cudaSuccess) return e;
-    k_analyze_mad_any<4><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
+    e = launch_pdl(k_analyze_mad_any<4>, clamp_grid(ntiles, sm_count * 3), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
   } else {
     e = set_smem(k_analyze_mad_any<3>, smem);
     if (e != cudaSuccess) return e;
-    k_analyze_mad_any<3><<<clamp_grid(ntiles, sm_count * 3), kThreads, smem, s>>>(img, pitch, g, vx, opaque, zero_word);
+    e = launch_pdl(k_analyze_mad_any<3>, clamp_grid(ntiles, sm_count * 3), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
   }
   return cudaGetLastError();
 }
@@ -1880,7 +1915,7 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
   if (banded) {
     // *count was zeroed by the fast analysis kernel that produced vx_fast (launch_analyze_mad_fast's zero_word)
     ++*launches;
-    k_band_list<<<(ntiles + kThreads - 1) / kThreads, kThreads, 0, s>>>(vx_fast, opaque, g, (int)g.C, *vm, *thr, *band, minmax,
+    e = launch_pdl(k_band_list, (ntiles + kThreads - 1) / kThreads, kThreads, 0, s, vx_fast, opaque, g, (int)g.C, *vm, *thr, *band, minmax,
                                                                        list, count);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1892,11 +1927,11 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
   if (g.C == 4) {
     e = set_smem(k_mad_exact<4>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<4><<<grid, threads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
+    e = launch_pdl(k_mad_exact<4>, grid, threads, smem, s, img, pitch, g, vx, banded ? list : nullptr, count);
   } else {
     e = set_smem(k_mad_exact<3>, smem);
     if (e != cudaSuccess) return e;
-    k_mad_exact<3><<<grid, threads, smem, s>>>(img, pitch, g, vx, banded ? list : nullptr, count);
+    e = launch_pdl(k_mad_exact<3>, grid, threads, smem, s, img, pitch, g, vx, banded ? list : nullptr, count);
   }
   return cudaGetLastError();
 }
@@ -1948,11 +1983,11 @@ cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const V
   cudaError_t e = cudaSuccess;  // scan_state is zero on entry and on exit (ensure_scratch clears it once)
   ++*launches;
   uint32_t* cursor = reinterpret_cast<uint32_t*>(scan_state);
-  k_plan<<<tiles, kThreads, 0, s>>>(vx, vy, g, vm, minmax, thr, mask, descs, tabidx,
+  e = launch_pdl(k_plan, tiles, kThreads, 0, s, vx, vy, g, vm, minmax, thr, mask, descs, tabidx,
                                     reinterpret_cast<unsigned long long*>(total_bytes),
                                     reinterpret_cast<ScanState*>(reinterpret_cast<uint8_t*>(scan_state) + kClassHistBytes), cursor,
                                     lists, cap);
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_class_lists(const pxz_block_desc* descs, const Geom& g, void* scan_state, uint32_t* lists, uint32_t cap,
@@ -1993,17 +2028,17 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
       if (fused) {
         e = set_smem(k_shrink_warp<true>, smem);
         if (e != cudaSuccess) return e;
-        k_shrink_warp<true><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+        e = launch_pdl(k_shrink_warp<true>, wgrid, kShrinkCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
       } else {
         e = set_smem(k_shrink_warp<false>, smem);
         if (e != cudaSuccess) return e;
-        k_shrink_warp<false><<<wgrid, kShrinkCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+        e = launch_pdl(k_shrink_warp<false>, wgrid, kShrinkCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
       }
     } else {
       const size_t smem = (size_t)kWarpsPerCta * kExpandWarpBytes;
       const int wgrid = clamp_grid((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)sm_count * PXZ_EXPAND_WARP_CTAS);
-      if (fused) k_expand_warp<true><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
-      else k_expand_warp<false><<<wgrid, kWarpCtaThreads, smem, s>>>(img, pitch, g, descs, tabidx, lists, cap, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      if (fused) e = launch_pdl(k_expand_warp<true>, wgrid, kWarpCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+      else e = launch_pdl(k_expand_warp<false>, wgrid, kWarpCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
     }
     return cudaGetLastError();
   }

@@ -456,6 +456,8 @@ __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shr
   uint32_t* ring = reinterpret_cast<uint32_t*>(strip + kStripRows * kStripStride);
   uint32_t* htab_smem = ring + kRingRows * 64;
   const TapK k = make_tapk(rt_one, rt_negzero);
+  pdl_wait();
+  pdl_trigger();
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kShrinkWarps;
   constexpr int F = FUSED ? 2 : 0;
@@ -737,6 +739,8 @@ __global__ void __launch_bounds__(kWarpCtaThreads, PXZ_EXPAND_WARP_CTAS) k_expan
   // the fixed-length walks read up to 7 strip entries past a group's own window: keep them finite (w = +0 there)
   for (uint32_t i = lane; i < kExpandWarpBytes / 16; i += 32) strip[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
+  pdl_wait();
+  pdl_trigger();
   const uint32_t ntiles = g.cols * g.rows, total_warps = gridDim.x * kWarpsPerCta;
   constexpr int F = FUSED ? 2 : 0;
   auto process = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti) {
