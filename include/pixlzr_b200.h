@@ -90,6 +90,26 @@ uint64_t pxz_launch_count(const pxz_ctx* ctx);
  * contraction — resampled pixels are bit-identical to the CPU result.  1: fused multiply-add on the RGBA fast paths;
  * faster, dims / offsets / values unchanged, pixels within +-1 LSB of the reference (the bar BASELINE.json states). */
 pxz_status pxz_ctx_set_fast_resample(pxz_ctx* ctx, int on);
+/* ---- per-block filter pairs ("strategy") --------------------------------------------------
+ * The reference's author measured, per bucket of width 1/64 of the value that enters the level quantiser, which
+ * (down, up) filter pair reproduces a block best (strategies.txt:1-118, summarised in strategies_by_level.txt:1-12),
+ * but the crate never uses the result: `shrink_*` / `expand` take one filter per call.  With a strategy installed,
+ * pxz_shrink / pxz_expand* / pxz_payload_upload of this context ignore their filter argument and pick, per block,
+ * down[b] / up[b] with b = pxz_strategy_bucket(block value).  The bucket is a function of the value STORED with the
+ * block (pxz_block_desc.value = hypot(p0, p1), operations.rs:154; it travels in the container), so a decoder finds the
+ * same filter: b = floor(64 * value / sqrt(2)) clamped to [0, 64]; NaN and negatives give 0.  value / sqrt(2) is the
+ * quantiser's input p for Oklab-MAD (both axes share it) and the root mean square of (p0, p1) for the Sobel metric.
+ * pxz_tree_process keeps its two explicit filters.  NULL removes the strategy.  No reference run exists for this
+ * mode: parity is against the oracle's restatement of the same rule on top of the pinned per-block resize. */
+#define PXZ_STRATEGY_BUCKETS 65
+typedef struct pxz_strategy {
+  uint8_t down[PXZ_STRATEGY_BUCKETS]; /* pxz_filter per bucket, used by pxz_shrink        */
+  uint8_t up[PXZ_STRATEGY_BUCKETS];   /* pxz_filter per bucket, used by the expand calls  */
+} pxz_strategy;
+uint32_t pxz_strategy_bucket(float block_value);
+/* the table the reference's log arrives at (strategies_by_level.txt:1-12) */
+pxz_status pxz_strategy_by_level(pxz_strategy* out);
+pxz_status pxz_ctx_set_strategy(pxz_ctx* ctx, const pxz_strategy* strategy);
 /* Per-kernel device timing (CUDA events recorded on the context's stream around every kernel
  * launch while enabled).  pxz_profile_read synchronises the stream, returns the accumulated
  * duration and launch count of kernel `kernel_id` since profiling was enabled.  Kernel ids are

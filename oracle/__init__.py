@@ -71,6 +71,13 @@ def lib():
         L.pxo_shrink.restype = C.c_int64
         L.pxo_expand.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.pxo_strategy_bucket.argtypes = [C.c_float]
+        L.pxo_strategy_bucket.restype = C.c_uint32
+        L.pxo_shrink_strategy.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_size_t, C.c_uint32, C.c_uint32,
+                                          C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.pxo_shrink_strategy.restype = C.c_int64
+        L.pxo_expand_strategy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         L.pxo_tree_process.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32,
                                        C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.pxo_qoi_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]
@@ -214,6 +221,53 @@ def expand(s: Shrunk, filter_up: int, nthreads: int = 1) -> np.ndarray:
                           s.channels, filter_up, _ptr(out), out.strides[0], nthreads)
     if rc != 0:
         raise ValueError("pxo_expand failed")
+    return out
+
+
+STRATEGY_BUCKETS = 65
+
+
+def strategy_bucket(value: float) -> int:
+    """EXTENSION: bucket of a block's stored value, floor(64 * value / sqrt(2)) clamped to [0, 64] (strategies.txt's levels)."""
+    return int(lib().pxo_strategy_bucket(float(value)))
+
+
+def strategy_by_level():
+    """(down, up) filter ids per bucket as strategies_by_level.txt:1-12 lists them."""
+    down = np.full(STRATEGY_BUCKETS, LANCZOS3, np.uint8)
+    up = np.full(STRATEGY_BUCKETS, LANCZOS3, np.uint8)
+    down[0], up[0] = NEAREST, NEAREST          # v < 0.015625
+    down[1], up[1] = TRIANGLE, NEAREST         # [0.015625; 0.03125)
+    down[2], up[2] = CATMULLROM, LANCZOS3      # [0.03125; 0.046875)
+    down[3], up[3] = LANCZOS3, CATMULLROM      # [0.046875; 0.0625)
+    down[45:], up[45:] = NEAREST, NEAREST      # v >= 0.703125
+    return down, up
+
+
+def shrink_strategy(img: np.ndarray, bw: int, bh: int, metric: int, factor: float, down_by_bucket: np.ndarray,
+                    use_factor: bool = True, normalise_global: bool = False, nthreads: int = 1) -> Shrunk:
+    """shrink() with the down filter of every block taken from `down_by_bucket[strategy_bucket(block value)]`."""
+    w, h, c, pitch = _check_img(img)
+    cols, rows = grid(w, h, bw, bh)
+    descs = np.zeros(cols * rows, DESC_DTYPE)
+    payload = np.zeros(w * h * c, np.uint8)
+    lut = np.ascontiguousarray(down_by_bucket, np.uint8)
+    assert lut.size == STRATEGY_BUCKETS
+    n = lib().pxo_shrink_strategy(_ptr(img), w, h, c, pitch, bw, bh, metric, factor, int(use_factor), _ptr(lut),
+                                  int(normalise_global), _ptr(descs), _ptr(payload), nthreads)
+    if n < 0:
+        raise ValueError(f"pxo_shrink_strategy failed ({n})")
+    return Shrunk(w, h, bw, bh, c, descs, payload[:n].copy())
+
+
+def expand_strategy(s: Shrunk, up_by_bucket: np.ndarray, nthreads: int = 1) -> np.ndarray:
+    out = np.zeros((s.height, s.width, s.channels), np.uint8)
+    lut = np.ascontiguousarray(up_by_bucket, np.uint8)
+    assert lut.size == STRATEGY_BUCKETS
+    rc = lib().pxo_expand_strategy(_ptr(s.descs), _ptr(s.payload), s.width, s.height, s.block_width, s.block_height,
+                                   s.channels, _ptr(lut), _ptr(out), out.strides[0], nthreads)
+    if rc != 0:
+        raise ValueError("pxo_expand_strategy failed")
     return out
 
 

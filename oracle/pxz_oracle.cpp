@@ -548,9 +548,18 @@ int pxo_analyze(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pitch,
   return err ? -5 : 0;
 }
 
-int64_t pxo_shrink(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pitch, uint32_t bw, uint32_t bh,
-                   int metric, float factor, int use_factor, int filter_down, int normalise_global,
-                   pxo_block_desc* descs, uint8_t* payload, int nthreads) {
+/* EXTENSION (include/pixlzr_b200.h "strategy"; the reference only logged the experiment, strategies.txt:1-118):
+   bucket of a block = floor(64 * stored value / sqrt(2)), one f32 multiply, clamped to [0, 64]. */
+uint32_t pxo_strategy_bucket(float value) {
+  const float t = value * 45.25483322143555f;
+  if (!(t > 0.0f)) return 0;
+  if (t >= 64.0f) return 64;
+  return (uint32_t)t;
+}
+
+static int64_t shrink_impl(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pitch, uint32_t bw, uint32_t bh,
+                           int metric, float factor, int use_factor, int filter_down, const uint8_t* down_by_bucket,
+                           int normalise_global, pxo_block_desc* descs, uint8_t* payload, int nthreads) {
   if (!descs || !payload) return -1;
   const uint32_t cols = ceil_div_f64(w, bw), rows = ceil_div_f64(h, bh);
   const int64_t nb = (int64_t)cols * rows;
@@ -605,7 +614,8 @@ int64_t pxo_shrink(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pit
     std::vector<uint8_t> blk((size_t)tw[bi] * th[bi] * C);
     for (uint32_t y = 0; y < th[bi]; ++y)
       memcpy(&blk[(size_t)y * tw[bi] * C], img + (size_t)(by * bh + y) * pitch + (size_t)bx * bw * C, (size_t)tw[bi] * C);
-    if (resize_image_rs(blk.data(), tw[bi], th[bi], C, payload + descs[bi].offset, ow[bi], oh[bi], filter_down) != 0) {
+    const int filt = down_by_bucket ? down_by_bucket[pxo_strategy_bucket(descs[bi].value)] : filter_down;
+    if (resize_image_rs(blk.data(), tw[bi], th[bi], C, payload + descs[bi].offset, ow[bi], oh[bi], filt) != 0) {
 #ifdef _OPENMP
 #pragma omp atomic write
 #endif
@@ -615,8 +625,23 @@ int64_t pxo_shrink(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pit
   return err ? -1 : (int64_t)off;
 }
 
-int pxo_expand(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh,
-               int C, int filter_up, uint8_t* out, size_t out_pitch, int nthreads) {
+int64_t pxo_shrink(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pitch, uint32_t bw, uint32_t bh,
+                   int metric, float factor, int use_factor, int filter_down, int normalise_global,
+                   pxo_block_desc* descs, uint8_t* payload, int nthreads) {
+  return shrink_impl(img, w, h, C, pitch, bw, bh, metric, factor, use_factor, filter_down, nullptr, normalise_global, descs,
+                     payload, nthreads);
+}
+
+int64_t pxo_shrink_strategy(const uint8_t* img, uint32_t w, uint32_t h, int C, size_t pitch, uint32_t bw, uint32_t bh,
+                            int metric, float factor, int use_factor, const uint8_t* down_by_bucket, int normalise_global,
+                            pxo_block_desc* descs, uint8_t* payload, int nthreads) {
+  if (!down_by_bucket) return -1;
+  return shrink_impl(img, w, h, C, pitch, bw, bh, metric, factor, use_factor, 0, down_by_bucket, normalise_global, descs,
+                     payload, nthreads);
+}
+
+static int expand_impl(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh,
+                       int C, int filter_up, const uint8_t* up_by_bucket, uint8_t* out, size_t out_pitch, int nthreads) {
   /* block grid in f32 as Pixlzr::block_grid_width/height do (pixlzr.rs:37-42) */
   const uint32_t cols = (uint32_t)ceilf((float)w / (float)bw), rows = (uint32_t)ceilf((float)h / (float)bh);
   const int64_t nb = (int64_t)cols * rows;
@@ -630,7 +655,8 @@ int pxo_expand(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, 
     const uint32_t nw = (bx == cols - 1 && trail_w > 0) ? trail_w : bw; /* :103-107 */
     const uint32_t nh = (by == rows - 1 && trail_h > 0) ? trail_h : bh; /* :92-96 */
     std::vector<uint8_t> blk((size_t)nw * nh * C);
-    if (resize_image_rs(payload + descs[bi].offset, descs[bi].w, descs[bi].h, C, blk.data(), nw, nh, filter_up) != 0) {
+    const int filt = up_by_bucket ? up_by_bucket[pxo_strategy_bucket(descs[bi].value)] : filter_up;
+    if (resize_image_rs(payload + descs[bi].offset, descs[bi].w, descs[bi].h, C, blk.data(), nw, nh, filt) != 0) {
 #ifdef _OPENMP
 #pragma omp atomic write
 #endif
@@ -642,6 +668,17 @@ int pxo_expand(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, 
       memcpy(out + (size_t)(by * bh + y) * out_pitch + (size_t)bx * bw * C, &blk[(size_t)y * nw * C], (size_t)nw * C);
   }
   return err ? -1 : 0;
+}
+
+int pxo_expand(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh,
+               int C, int filter_up, uint8_t* out, size_t out_pitch, int nthreads) {
+  return expand_impl(descs, payload, w, h, bw, bh, C, filter_up, nullptr, out, out_pitch, nthreads);
+}
+
+int pxo_expand_strategy(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, uint32_t h, uint32_t bw,
+                        uint32_t bh, int C, const uint8_t* up_by_bucket, uint8_t* out, size_t out_pitch, int nthreads) {
+  if (!up_by_bucket) return -1;
+  return expand_impl(descs, payload, w, h, bw, bh, C, 0, up_by_bucket, out, out_pitch, nthreads);
 }
 
 /* process/tree.rs:23-83, literally: `img` is the (sub-)image of this recursion level, tightly packed. */

@@ -78,6 +78,18 @@ int pxo_expand(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, 
                uint32_t bw, uint32_t bh, int channels, int filter_up, uint8_t* out,
                size_t out_pitch, int nthreads);
 
+/* EXTENSION — per-block filter pairs (include/pixlzr_b200.h "strategy").  The reference only logged the experiment
+   (strategies.txt:1-118, strategies_by_level.txt:1-12); there is no reference run to pin these against, so they are
+   "parity unpinned" beyond the per-block resize they are built from (which is pinned).  *_by_bucket: 65 filter ids,
+   indexed by pxo_strategy_bucket(stored block value) = floor(64 * value / sqrt(2)) clamped to [0, 64]. */
+uint32_t pxo_strategy_bucket(float value);
+int64_t pxo_shrink_strategy(const uint8_t* img, uint32_t w, uint32_t h, int channels, size_t pitch, uint32_t bw,
+                            uint32_t bh, int metric, float factor, int use_factor, const uint8_t* down_by_bucket,
+                            int normalise_global, pxo_block_desc* descs, uint8_t* payload, int nthreads);
+int pxo_expand_strategy(const pxo_block_desc* descs, const uint8_t* payload, uint32_t w, uint32_t h, uint32_t bw,
+                        uint32_t bh, int channels, const uint8_t* up_by_bucket, uint8_t* out, size_t out_pitch,
+                        int nthreads);
+
 /* tree::process_custom (process/tree.rs:23-83) with before = |x-avg|, after = identity: quadtree of blocks, a block
    whose value is below the threshold is reduced + re-expanded, the others are split again with halved block size
    until the size reaches max(min, 4).  Output has the input's channel count (the reference pastes into an RGBA8

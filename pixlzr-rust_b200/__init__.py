@@ -11,10 +11,12 @@ from .api import (  # noqa: F401
     FilterType,
     Pixlzr,
     PixlzrBlock,
+    Strategy,
     get_block_variance,
     get_block_variance_directionally,
     parse_shrinking_factor,
     process,
+    process_by_strategy,
     process_custom,
     reduce_image_section,
     tree_process,

@@ -36,6 +36,9 @@ SYMBOLS = {
     "pxz_synchronize": (_i, [_vp]),
     "pxz_launch_count": (_u64, [_vp]),
     "pxz_ctx_set_fast_resample": (_i, [_vp, _i]),
+    "pxz_strategy_bucket": (_u32, [C.c_float]),
+    "pxz_strategy_by_level": (_i, [_vp]),
+    "pxz_ctx_set_strategy": (_i, [_vp, _vp]),
     "pxz_profile_enable": (_i, [_vp, _i]),
     "pxz_profile_kernel_name": (C.c_char_p, [_i]),
     "pxz_profile_read": (_i, [_vp, _i, _P(C.c_double), _P(_u64)]),
@@ -105,6 +108,22 @@ def ptr(a):
     return a
 
 
+STRATEGY_BUCKETS = 65
+
+
+def strategy_bucket(value: float) -> int:
+    return int(lib().pxz_strategy_bucket(float(value)))
+
+
+def strategy_by_level():
+    """(down, up) uint8[65]: the table of strategies_by_level.txt (pxz_strategy_by_level)."""
+    buf = np.zeros(2 * STRATEGY_BUCKETS, np.uint8)
+    rc = lib().pxz_strategy_by_level(buf.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"pxz_strategy_by_level failed ({rc})")
+    return buf[:STRATEGY_BUCKETS].copy(), buf[STRATEGY_BUCKETS:].copy()
+
+
 class Context:
     """One device + one stream (pxz_ctx).  Not thread-safe; use one per thread."""
 
@@ -138,6 +157,17 @@ class Context:
     def set_fast_resample(self, on: bool = True):
         """Fused multiply-add in the RGBA resample kernels: pixels within +-1 LSB instead of bit-exact."""
         self.check(lib().pxz_ctx_set_fast_resample(self._h, int(on)))
+
+    def set_strategy(self, down=None, up=None):
+        """Per-block filter pairs (pxz_ctx_set_strategy): `down` / `up` are 65 filter ids indexed by
+        strategy_bucket(block value); None removes the strategy."""
+        if down is None or up is None:
+            self.check(lib().pxz_ctx_set_strategy(self._h, None))
+            return
+        buf = np.concatenate([np.asarray(down, np.uint8).reshape(-1), np.asarray(up, np.uint8).reshape(-1)])
+        if buf.size != 2 * STRATEGY_BUCKETS:
+            raise ValueError(f"a strategy has {STRATEGY_BUCKETS} entries per direction")
+        self.check(lib().pxz_ctx_set_strategy(self._h, buf.ctypes.data_as(C.c_void_p)))
 
     def profile_enable(self, on: bool = True):
         self.check(lib().pxz_profile_enable(self._h, int(on)))

@@ -109,6 +109,27 @@ def _check_image(image: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(image)
 
 
+@dataclass
+class Strategy:
+    """(down, up) filter per value bucket of width 1/64 (pxz_strategy, include/pixlzr_b200.h).  The bucket of a block
+    is `Strategy.bucket(block_value)` = floor(64 * value / sqrt(2)) clamped to [0, 64]."""
+    down: np.ndarray
+    up: np.ndarray
+
+    @classmethod
+    def by_level(cls) -> "Strategy":
+        """The table the reference's log arrives at (strategies_by_level.txt:1-12)."""
+        return cls(*N.strategy_by_level())
+
+    @classmethod
+    def uniform(cls, down: FilterType, up: FilterType) -> "Strategy":
+        return cls(np.full(N.STRATEGY_BUCKETS, int(down), np.uint8), np.full(N.STRATEGY_BUCKETS, int(up), np.uint8))
+
+    @staticmethod
+    def bucket(value: float) -> int:
+        return N.strategy_bucket(value)
+
+
 class Pixlzr:
     """struct Pixlzr (pixlzr.rs:17-25).  Holds either the source image (blocks = tiles, no values) or
     a packed block payload (descriptor table + pixels), both on the host; the GPU does the work."""
@@ -224,6 +245,30 @@ class Pixlzr:
     def shrink_directionally(self, filter_downscale: FilterType, factor: float):
         """Pixlzr::shrink_directionally (pixlzr.rs:187-205)."""
         self._shrink(N.METRIC_SOBEL_DIR, filter_downscale, factor, 0)
+
+    def shrink_by_strategy(self, strategy: "Strategy", factor: float):
+        """EXTENSION: shrink_by with the down filter of every block taken from the strategy table
+        (strategies.txt / strategies_by_level.txt: the experiment the reference logged but never wired in)."""
+        if self._image is None and self._values_present:
+            return
+        ctx = self._ctx()
+        ctx.set_strategy(strategy.down, strategy.up)
+        try:
+            self._shrink(N.METRIC_OKLAB_MAD, FilterType.Lanczos3, factor, 0)
+        finally:
+            ctx.set_strategy(None, None)
+
+    def to_image_by_strategy(self, strategy: "Strategy") -> np.ndarray:
+        """EXTENSION: to_image with the up filter of every block taken from the strategy table; the bucket comes from
+        the value stored with the block, so it also works on a decoded container."""
+        if self._image is not None:
+            return self._image.copy()
+        ctx = self._ctx()
+        ctx.set_strategy(strategy.down, strategy.up)
+        try:
+            return self.to_image(FilterType.Lanczos3)
+        finally:
+            ctx.set_strategy(None, None)
 
     def shrink(self, filter_downscale: FilterType, before_average, after_average):
         """Pixlzr::shrink (pixlzr.rs:124-152) takes arbitrary closures; only the two closure pairs the
@@ -342,6 +387,19 @@ def process_custom(image: np.ndarray, block_width: int, block_height: int, filte
     if out.shape[2] == 3:
         out = np.concatenate([out, np.full(out.shape[:2] + (1,), 255, np.uint8)], axis=2)
     return out
+
+
+def process_by_strategy(image: np.ndarray, block_size: int, strategy: Optional[Strategy] = None,
+                        ctx: Optional[N.Context] = None) -> np.ndarray:
+    """EXTENSION: `process` with a per-block (down, up) filter pair instead of Lanczos3 / Nearest (the experiment of
+    strategies.txt; default table: strategies_by_level.txt)."""
+    ctx = ctx or default_context()
+    strategy = strategy or Strategy.by_level()
+    ctx.set_strategy(strategy.down, strategy.up)
+    try:
+        return process_custom(image, block_size, block_size, FilterType.Lanczos3, FilterType.Lanczos3, ctx)
+    finally:
+        ctx.set_strategy(None, None)
 
 
 def process(image: np.ndarray, block_size: int, ctx: Optional[N.Context] = None) -> np.ndarray:

@@ -74,6 +74,7 @@ struct pxz_ctx {
   std::string err;
   uint64_t launches = 0;
   LevelThresholds thr{};
+  StrategyLut strategy{};  // on = 0 unless pxz_ctx_set_strategy installed a table
   GuardBand band{};
   // scratch, grown on demand
   float* d_vx = nullptr;
@@ -118,6 +119,9 @@ struct pxz_payload {
   pxz_block_desc* d_descs = nullptr;
   uint32_t* d_tabidx = nullptr;  // [nblocks_cap] table indices, then the work-order lists (launch_plan) of capacity nblocks_cap
   uint32_t* d_order() const { return d_tabidx + nblocks_cap; }
+  uint32_t* d_up() const { return d_order() + order_list_words(nblocks_cap); }  // [nblocks_cap] expand-side indices (strategy)
+  // 0: one filter per call | 1: per-block filters, expand indices in d_up() (pxz_shrink) | 2: ... in d_tabidx (upload)
+  int strategy = 0;
   uint8_t* d_pixels = nullptr;
   uint64_t capacity = 0;
   uint64_t* d_total = nullptr;
@@ -255,19 +259,26 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
     *out = it->second;
     return PXZ_OK;
   }
-  std::vector<AxisTab> tabs(spec.n_small.size());
+  // filter < 0: the tables of all five filters one after the other (index = filter * spec size + i), for payloads
+  // whose blocks carry their own filter (pxz_ctx_set_strategy)
+  const size_t per_filter = spec.n_small.size();
+  const int f0 = filter < 0 ? 0 : filter, f1 = filter < 0 ? 4 : filter;
+  std::vector<AxisTab> tabs(per_filter * (size_t)(f1 - f0 + 1));
   std::vector<uint32_t> pool;
-  std::map<std::pair<uint32_t, uint32_t>, AxisTab> seen;
-  for (size_t i = 0; i < tabs.size(); ++i) {
-    const uint32_t n_in = direction == 0 ? spec.n_tile[i] : spec.n_small[i];
-    const uint32_t n_out = direction == 0 ? spec.n_small[i] : spec.n_tile[i];
-    auto s = seen.find({n_in, n_out});
-    if (s != seen.end()) {
-      tabs[i] = s->second;
-      continue;
+  for (int f = f0; f <= f1; ++f) {
+    std::map<std::pair<uint32_t, uint32_t>, AxisTab> seen;
+    for (size_t i = 0; i < per_filter; ++i) {
+      AxisTab& t = tabs[(size_t)(f - f0) * per_filter + i];
+      const uint32_t n_in = direction == 0 ? spec.n_tile[i] : spec.n_small[i];
+      const uint32_t n_out = direction == 0 ? spec.n_small[i] : spec.n_tile[i];
+      auto s = seen.find({n_in, n_out});
+      if (s != seen.end()) {
+        t = s->second;
+        continue;
+      }
+      if (!build_axis_table(n_in, n_out, f, &pool, &t)) return fail(ctx, PXZ_E_ARG, "bad resample table request");
+      seen[{n_in, n_out}] = t;
     }
-    if (!build_axis_table(n_in, n_out, filter, &pool, &tabs[i])) return fail(ctx, PXZ_E_ARG, "bad resample table request");
-    seen[{n_in, n_out}] = tabs[i];
   }
   TabSet ts;
   ts.ntabs = (uint32_t)tabs.size();
@@ -311,7 +322,8 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
     scratch = ctx->d_scratch;
   }
   ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
-  PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, p->d_tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
+  const uint32_t* tabidx = (direction == 1 && p->strategy == 1) ? p->d_up() : p->d_tabidx;
+  PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
                                 ts.ntabs, max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, opaque_flags,
                                 ctx->resample_kernels != 2 ? ctx->d_tile_counter : nullptr, p->d_order(), (uint32_t)p->nblocks_cap,
                                 ts.warp_ok, ctx->resample_kernels == 1, ctx->stream, ctx->sm_count,
@@ -454,6 +466,40 @@ uint64_t pxz_launch_count(const pxz_ctx* ctx) { return ctx ? ctx->launches : 0; 
 pxz_status pxz_ctx_set_fast_resample(pxz_ctx* ctx, int on) {
   if (!ctx) return PXZ_E_ARG;
   ctx->fast_resample = on != 0;
+  return PXZ_OK;
+}
+
+// ---- per-block filter pairs (strategies.txt / strategies_by_level.txt) ----------------------------------------
+uint32_t pxz_strategy_bucket(float block_value) { return strategy_bucket(block_value); }
+
+pxz_status pxz_strategy_by_level(pxz_strategy* out) {
+  if (!out) return PXZ_E_ARG;
+  // strategies_by_level.txt:1-12 (= strategies.txt, one line per bucket of width 1/64)
+  for (int b = 0; b < PXZ_STRATEGY_BUCKETS; ++b) {
+    pxz_filter down = PXZ_LANCZOS3, up = PXZ_LANCZOS3;  // v in [0.0625; 0.703125)
+    if (b == 0) { down = PXZ_NEAREST; up = PXZ_NEAREST; }            // v < 0.015625
+    else if (b == 1) { down = PXZ_TRIANGLE; up = PXZ_NEAREST; }      // [0.015625; 0.03125)
+    else if (b == 2) { down = PXZ_CATMULLROM; up = PXZ_LANCZOS3; }   // [0.03125; 0.046875)
+    else if (b == 3) { down = PXZ_LANCZOS3; up = PXZ_CATMULLROM; }   // [0.046875; 0.0625)
+    else if (b >= 45) { down = PXZ_NEAREST; up = PXZ_NEAREST; }      // v >= 0.703125
+    out->down[b] = (uint8_t)down;
+    out->up[b] = (uint8_t)up;
+  }
+  return PXZ_OK;
+}
+
+pxz_status pxz_ctx_set_strategy(pxz_ctx* ctx, const pxz_strategy* strategy) {
+  if (!ctx) return PXZ_E_ARG;
+  if (!strategy) {
+    ctx->strategy.on = 0;
+    return PXZ_OK;
+  }
+  for (int b = 0; b < PXZ_STRATEGY_BUCKETS; ++b)
+    if (strategy->down[b] > 4 || strategy->up[b] > 4) return fail(ctx, PXZ_E_ARG, "unknown filter in the strategy table");
+  static_assert(PXZ_STRATEGY_BUCKETS == kStrategyBuckets, "bucket count");
+  memcpy(ctx->strategy.down, strategy->down, PXZ_STRATEGY_BUCKETS);
+  memcpy(ctx->strategy.up, strategy->up, PXZ_STRATEGY_BUCKETS);
+  ctx->strategy.on = 1;
   return PXZ_OK;
 }
 
@@ -670,7 +716,7 @@ static pxz_status payload_new(pxz_ctx* ctx, const Geom& g, uint64_t capacity, px
   p->nblocks_cap = nblocks;
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&p->d_descs, nblocks * sizeof(pxz_block_desc))) != PXZ_OK ||
-      (st = dev_alloc(ctx, (void**)&p->d_tabidx, (nblocks + order_list_words(nblocks)) * 4)) != PXZ_OK ||  // table indices | work order lists
+      (st = dev_alloc(ctx, (void**)&p->d_tabidx, (2 * nblocks + order_list_words(nblocks)) * 4)) != PXZ_OK ||  // table indices | work order lists | expand-side indices
       (st = dev_alloc(ctx, (void**)&p->d_pixels, capacity)) != PXZ_OK ||
       (st = dev_alloc(ctx, (void**)&p->d_total, 8)) != PXZ_OK) {
     // partial allocations must not enter the cache
@@ -700,6 +746,10 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   vm.mode = (metric == PXZ_METRIC_SOBEL_DIR) ? 2 : ((flags & PXZ_FLAG_AFTER_IDENTITY) ? 1 : 0);
   vm.normalise = normalise ? 1 : 0;
   vm.extra_thr = NAN;
+  if (ctx->strategy.on)
+    for (int k = 1; k < kStrategyBuckets; ++k)
+      if (ctx->strategy.down[k] != ctx->strategy.down[k - 1] || ctx->strategy.up[k] != ctx->strategy.up[k - 1])
+        vm.bucket_edges |= 1ull << (k - 1);
 
   // with global normalisation every value depends on the exact min and max, so the Oklab path
   // runs in reference order for all blocks
@@ -740,15 +790,19 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   cudaError_t e;
   {
     ProfScope prof(ctx, K_PLAN);
+    StrategyLut lut = ctx->strategy;
+    lut.stride = (uint32_t)p->spec->n_small.size();
+    p->strategy = lut.on ? 1 : 0;
     e = launch_plan(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, g, vm, ctx->d_minmax, ctx->thr, nullptr,
-                    p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, p->d_order(), (uint32_t)p->nblocks_cap, ctx->stream, &ctx->launches);
+                    p->d_descs, p->d_tabidx, p->d_total, ctx->d_scan, p->d_order(), (uint32_t)p->nblocks_cap, ctx->stream, &ctx->launches,
+                    &lut, p->d_up());
   }
   if (e != cudaSuccess) {
     payload_release(p);
     return fail(ctx, PXZ_E_CUDA, std::string("plan: ") + cudaGetErrorString(e));
   }
   TabSet ts;
-  st = get_tabset(ctx, *p->spec, (int)filter_down, 0, &ts);
+  st = get_tabset(ctx, *p->spec, p->strategy ? -1 : (int)filter_down, 0, &ts);
   // the fast Oklab-MAD pass also told which tiles are fully opaque: their alpha channel needs no arithmetic
   const uint8_t* opaque_flags = (metric == PXZ_METRIC_OKLAB_MAD && !exact_all) ? ctx->d_opaque : nullptr;
   if (st == PXZ_OK)
@@ -866,6 +920,7 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
   auto spec = std::make_shared<TabSpec>();
   std::map<std::pair<uint32_t, uint32_t>, uint32_t> index;
   std::vector<uint32_t> tabidx(nblocks);
+  std::vector<uint8_t> filt(ctx->strategy.on ? nblocks : 0);  // per-block expand filter (pxz_ctx_set_strategy)
   uint32_t max_small = 1, max_tmp_up = 1, max_tmp_down = 1, max_dim = 1;
   auto pad8 = [](uint32_t v) { return (v + 7u) & ~7u; };
   auto idx_of = [&](uint32_t small, uint32_t tile) -> uint32_t {
@@ -890,6 +945,7 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
     const uint32_t ix = idx_of(d.w, tw), iy = idx_of(d.h, th);
     if (ix > 0xFFFFu || iy > 0xFFFFu) return fail(ctx, PXZ_E_UNSUPPORTED, "more than 65536 distinct block sizes");
     tabidx[b] = ix | (iy << 16);
+    if (ctx->strategy.on) filt[b] = ctx->strategy.up[strategy_bucket(d.value)];
     max_small = std::max(max_small, (uint32_t)d.w * d.h);
     max_dim = std::max(max_dim, (uint32_t)std::max(d.w, d.h));
     max_tmp_up = std::max(max_tmp_up, th * pad8(d.w));
@@ -899,6 +955,15 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
   st = payload_new(ctx, g, bytes, &p);
   if (st != PXZ_OK) return st;
   p->spec = spec;
+  if (ctx->strategy.on) {
+    const uint32_t per_filter = (uint32_t)spec->n_small.size();
+    if (per_filter * 5u > 0x10000u) {
+      payload_release(p);
+      return fail(ctx, PXZ_E_UNSUPPORTED, "too many distinct block sizes for per-block filters");
+    }
+    for (size_t b = 0; b < nblocks; ++b) tabidx[b] += (filt[b] * per_filter) * 0x10001u;
+    p->strategy = 2;
+  }
   p->max_small_px = max_small;
   p->max_small_dim = max_dim;
   p->max_tmp_up = max_tmp_up;
@@ -931,7 +996,7 @@ pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter fi
   if ((int)filter_up < 0 || (int)filter_up > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
   if (out->w != p->g.W || out->h != p->g.H || out->c != p->g.C) return fail(ctx, PXZ_E_ARG, "output image geometry mismatch");
   TabSet ts;
-  pxz_status st = get_tabset(ctx, *p->spec, (int)filter_up, 1, &ts);
+  pxz_status st = get_tabset(ctx, *p->spec, p->strategy ? -1 : (int)filter_up, 1, &ts);
   if (st != PXZ_OK) return st;
   return run_resample(ctx, 1, out->d, out->pitch, p, ts, p->max_small_px, p->max_small_dim, p->max_tmp_up);
 }

@@ -705,6 +705,12 @@ __device__ __forceinline__ bool in_guard_band(float raw, bool opaque, int C, con
     if (fabsf(pv - thr.thr[k]) <= tol) return true;
   }
   if (vm.extra_thr == vm.extra_thr && fabsf(v0 - vm.extra_thr) <= tol) return true;  // quadtree split decision
+  if (vm.bucket_edges != 0ull) {  // filter strategy: the bucket of sqrt(2) * pv / sqrt(2) changes at pv = k / 64
+    const float kq = rintf(pv * 64.0f);
+    if (kq >= 1.0f && kq <= 64.0f && ((vm.bucket_edges >> ((int)kq - 1)) & 1ull) &&
+        fabsf(pv - kq * 0.015625f) <= tol + 2e-6f * pv)  // + the roundings of hypot and of the bucket product
+      return true;
+  }
   // the kink of parse_value at v = -1 (1 + v = 0) maps to 1 px on both sides
   return false;
 }
@@ -946,12 +952,14 @@ struct ScanState {
   unsigned long long status[1];  // [num_tiles]: flag << 62 | value ; flag 1 = aggregate, 2 = inclusive prefix
 };
 
+template <bool STRATEGY>
 __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx, const float* __restrict__ vy, Geom g,
                                                    ValueMap vm, const float* __restrict__ minmax, LevelThresholds thr,
                                                    const uint8_t* __restrict__ mask, pxz_block_desc* __restrict__ descs,
                                                    uint32_t* __restrict__ tabidx,
                                                    unsigned long long* __restrict__ total, ScanState* st,
-                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ lists, uint32_t cap) {
+                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ lists, uint32_t cap,
+                                                   StrategyLut strat, uint32_t* __restrict__ tabidx_up) {
   __shared__ unsigned int s_tile;
   __shared__ uint32_t s_hist[kCostClasses], s_base[kCostClasses];
   if (threadIdx.x < kCostClasses) s_hist[threadIdx.x] = 0;
@@ -966,7 +974,7 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t first = tile * kPlanTile + tid * kPlanItems;
 
-  uint32_t dw[kPlanItems], dh[kPlanItems], tix[kPlanItems];
+  uint32_t dw[kPlanItems], dh[kPlanItems], tix[kPlanItems], tix_up[kPlanItems];
   float val[kPlanItems];
   unsigned long long sz[kPlanItems];
   unsigned long long tsum = 0;
@@ -990,6 +998,12 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
       const uint32_t ix = (0u * 2u + cx) * kLevelsPerClass + min(k0, (uint32_t)kMaxLevel);
       const uint32_t iy = (1u * 2u + cy) * kLevelsPerClass + min(k1, (uint32_t)kMaxLevel);
       tix[j] = ix | (iy << 16);
+      if (STRATEGY) {  // the block's filter pair: the same tables, `stride` entries further per filter
+        const uint32_t bucket = strategy_bucket(val[j]);
+        const uint32_t fd = strat.down[bucket] * strat.stride, fu = strat.up[bucket] * strat.stride;
+        tix_up[j] = (ix + fu) | ((iy + fu) << 16);
+        tix[j] = (ix + fd) | ((iy + fd) << 16);
+      }
       if (mask != nullptr && mask[b] == 0) { dw[j] = 0; dh[j] = 0; }  // not a leaf of this quadtree level
       sz[j] = (unsigned long long)dw[j] * dh[j] * g.C;
       tsum += sz[j];
@@ -1071,6 +1085,7 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
       d.h = (uint16_t)dh[j];
       descs[b] = d;
       tabidx[b] = tix[j];
+      if (STRATEGY) tabidx_up[b] = tix_up[j];
       lists[(size_t)cls[j] * cap + s_base[cls[j]] + rank[j]] = b;
       excl += sz[j];
     }
@@ -1977,16 +1992,20 @@ size_t plan_scan_state_bytes(uint32_t nblocks) {
 
 cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
                         const LevelThresholds& thr, const uint8_t* mask, pxz_block_desc* descs, uint32_t* tabidx,
-                        uint64_t* total_bytes, void* scan_state, uint32_t* lists, uint32_t cap, cudaStream_t s, uint64_t* launches) {
+                        uint64_t* total_bytes, void* scan_state, uint32_t* lists, uint32_t cap, cudaStream_t s, uint64_t* launches,
+                        const StrategyLut* strategy, uint32_t* tabidx_up) {
   const uint32_t nblocks = g.cols * g.rows;
   const uint32_t tiles = (nblocks + kPlanTile - 1) / kPlanTile;
+  const bool adaptive = strategy != nullptr && strategy->on != 0 && tabidx_up != nullptr;
+  StrategyLut lut = {};
+  if (adaptive) lut = *strategy;
   cudaError_t e = cudaSuccess;  // scan_state is zero on entry and on exit (ensure_scratch clears it once)
   ++*launches;
   uint32_t* cursor = reinterpret_cast<uint32_t*>(scan_state);
-  e = launch_pdl(k_plan, tiles, kThreads, 0, s, vx, vy, g, vm, minmax, thr, mask, descs, tabidx,
-                                    reinterpret_cast<unsigned long long*>(total_bytes),
-                                    reinterpret_cast<ScanState*>(reinterpret_cast<uint8_t*>(scan_state) + kClassHistBytes), cursor,
-                                    lists, cap);
+  ScanState* st = reinterpret_cast<ScanState*>(reinterpret_cast<uint8_t*>(scan_state) + kClassHistBytes);
+  unsigned long long* total = reinterpret_cast<unsigned long long*>(total_bytes);
+  if (adaptive) e = launch_pdl(k_plan<true>, tiles, kThreads, 0, s, vx, vy, g, vm, minmax, thr, mask, descs, tabidx, total, st, cursor, lists, cap, lut, tabidx_up);
+  else e = launch_pdl(k_plan<false>, tiles, kThreads, 0, s, vx, vy, g, vm, minmax, thr, mask, descs, tabidx, total, st, cursor, lists, cap, lut, tabidx_up);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -55,11 +55,35 @@ struct ValueMap {
   int mode;       // 0: MAD * factor * 10 | 1: MAD identity | 2: Sobel (hz,vr) * factor
   int normalise;  // 0/1; minmax = {min_x, -max_x, min_y, -max_y} on device
   float extra_thr;  // tree processing: an additional decision threshold on the value (NaN = none), process/tree.rs:56
+  // per-block filter strategy: bit k-1 set = the buckets k-1 and k (edge at p = k/64) name different filters, so the
+  // fast Oklab-MAD path must resolve that edge exactly as well (guard band)
+  unsigned long long bucket_edges = 0;
 };
 
 struct LevelThresholds {
   float thr[kThresholds];
 };
+
+// Per-block filter pair chosen by the block value (include/pixlzr_b200.h, pxz_strategy; reference: the experiment
+// logged in strategies.txt / strategies_by_level.txt).  The bucket is a function of the value STORED with the block
+// (sqrt(p0^2 + p1^2), operations.rs:154), so a decoder finds the same filter again: value / sqrt(2) is the quantiser's
+// input p when both axes share it (Oklab-MAD), and its root mean square otherwise.
+constexpr int kStrategyBuckets = 65;
+struct StrategyLut {
+  uint32_t on;      // 0: one filter for all blocks
+  uint32_t stride;  // tables per filter in the combined table set
+  uint8_t down[kStrategyBuckets + 3];
+  uint8_t up[kStrategyBuckets + 3];
+};
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t strategy_bucket(float value) {
+  const float t = value * 45.25483322143555f;  // 64 / sqrt(2), one f32 multiply
+  if (!(t > 0.0f)) return 0;                   // zero, negative, NaN
+  if (t >= 64.0f) return 64;
+  return (uint32_t)t;
+}
 
 // Guard band of the fast Oklab-MAD path (DESIGN.md "guard band"): a block is recomputed in reference
 // order when its fast value is within the bound of |v_ref - v_fast| of a level threshold.  The bound's
@@ -87,7 +111,7 @@ cudaError_t launch_minmax(const float* vx, const float* vy, uint32_t n, float* m
 cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const ValueMap& vm, const float* minmax,
                         const LevelThresholds& thr, const uint8_t* mask, pxz_block_desc* descs, uint32_t* tabidx,
                         uint64_t* total_bytes, void* scan_state, uint32_t* lists, uint32_t cap, cudaStream_t s,
-                        uint64_t* launches);
+                        uint64_t* launches, const StrategyLut* strategy = nullptr, uint32_t* tabidx_up = nullptr);
 // Work order of the warp-per-tile resample kernels: lists[c * cap + i], c < 8, = the blocks of cost class c (0 = most
 // expensive), lists[8 * cap + c] = how many.  launch_plan fills them; this entry point does the same for descriptors
 // that came from the host.

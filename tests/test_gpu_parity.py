@@ -583,3 +583,112 @@ def test_sobel_block_without_interior_pixels(ctx):
         assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
         assert (descs["w"][-3:] == 1).all() and (descs["h"][-3:] == 1).all()
         assert np.array_equal(pixels, ref.payload)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-block filter pairs (pxz_ctx_set_strategy): the reference logged which (down, up) pair suits
+# each value bucket (strategies.txt) but never used it; the oracle restates the rule on top of the pinned resize.
+# ---------------------------------------------------------------------------------------------
+def _rainbow_strategy(seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 5, 65).astype(np.uint8), rng.integers(0, 5, 65).astype(np.uint8)
+
+
+def _spread_image(w, h, c, bs, seed):
+    """Noise whose amplitude is log-uniform per block (2^-9 .. 1 of full scale): block values over three decades."""
+    rng = np.random.default_rng(seed)
+    rows, cols = (h + bs - 1) // bs, (w + bs - 1) // bs
+    amp = 128.0 * 2.0 ** (-9.0 * rng.random((rows, cols)))
+    amp = np.kron(amp, np.ones((bs, bs)))[:h, :w, None]
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([128 + 60 * np.sin(xx / 97.0), 128 + 60 * np.cos(yy / 131.0), 128 + 40 * np.sin((xx + yy) / 61.0)], -1)
+    img = np.clip(base + (rng.random((h, w, 3)) - 0.5) * 2 * amp, 0, 255).astype(np.uint8)
+    if c == 4:
+        a = np.where(rng.random((h, w, 1)) < 0.5, 255, rng.integers(0, 256, (h, w, 1))).astype(np.uint8)
+        a[: h // 2] = 255
+        img = np.concatenate([img, a], -1)
+    return np.ascontiguousarray(img)
+
+
+@pytest.mark.parametrize("kind", ["warp", "cta"])
+@pytest.mark.parametrize("shape,bs,metric,factor,table", [
+    ((520, 776), 64, 0, 0.3, "by_level"),      # trailing 8-px tiles
+    ((520, 776), 64, 0, 0.3, "rainbow"),       # every filter in both directions
+    ((300, 420), 32, 0, 0.2, "rainbow"),
+    ((384, 512), 48, 1, 4.0, "rainbow"),       # Sobel: bucket from hypot(p0, p1) / sqrt(2)
+    ((200, 264), 40, 0, 0.1, "by_level"),
+    ((97, 131), 16, 0, 0.2, "rainbow"),        # RGB: generic kernels
+])
+def test_strategy_matches_oracle(forced_ctx, kind, shape, bs, metric, factor, table):
+    ctx = forced_ctx[kind]
+    channels = 3 if shape == (97, 131) else 4
+    img = _spread_image(shape[1], shape[0], channels, bs, seed=5)
+    down, up = O.strategy_by_level() if table == "by_level" else _rainbow_strategy(bs + metric)
+    ref = O.shrink_strategy(img, bs, bs, metric, factor, down)
+    want = O.expand_strategy(ref, up)
+    buckets = {O.strategy_bucket(v) for v in ref.descs["value"]}
+    assert len(buckets) >= 8 and len({(down[b], up[b]) for b in buckets}) >= 3, "the test image must reach several filter pairs"
+    ctx.set_strategy(down, up)
+    try:
+        d = ctx.image_upload(img)
+        pl = d.shrink(bs, bs, metric, factor, O.GAUSSIAN, N.FLAG_EXACT_VALUES)  # the filter argument is ignored
+        descs, px = pl.download()
+        assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+        assert np.array_equal(descs["value"].view("<u4"), ref.descs["value"].view("<u4"))
+        assert np.array_equal(px, ref.payload)
+        assert np.array_equal(pl.expand(O.GAUSSIAN), want)
+        # decoder side: descriptors + pixels from the host; the bucket comes from the stored value
+        pl2 = ctx.payload_upload(shape[1], shape[0], bs, bs, channels, descs, px)
+        assert np.array_equal(pl2.expand(O.TRIANGLE), want)
+        pl2.free()
+        pl.free()
+        d.free()
+    finally:
+        ctx.set_strategy(None, None)
+    # strategy removed: one filter per call again
+    ref1 = O.shrink(img, bs, bs, metric, factor, O.CATMULLROM)
+    d = ctx.image_upload(img)
+    pl = d.shrink(bs, bs, metric, factor, O.CATMULLROM, N.FLAG_EXACT_VALUES)
+    assert np.array_equal(pl.download()[1], ref1.payload)
+    assert np.array_equal(pl.expand(O.NEAREST), O.expand(ref1, O.NEAREST))
+    pl.free()
+    d.free()
+
+
+def test_strategy_uniform_table_equals_plain_filters(ctx):
+    """A table with the same pair in every bucket is the ordinary two-filter path."""
+    img = synth(400, 300, 4, seed=8)
+    ref = O.shrink(img, 32, 32, 0, 0.5, O.CATMULLROM)
+    ctx.set_strategy(np.full(65, O.CATMULLROM, np.uint8), np.full(65, O.TRIANGLE, np.uint8))
+    try:
+        d = ctx.image_upload(img)
+        pl = d.shrink(32, 32, 0, 0.5, O.NEAREST, N.FLAG_EXACT_VALUES)
+        assert np.array_equal(pl.download()[1], ref.payload)
+        assert np.array_equal(pl.expand(O.NEAREST), O.expand(ref, O.TRIANGLE))
+        pl.free()
+        d.free()
+    finally:
+        ctx.set_strategy(None, None)
+    with pytest.raises(RuntimeError):
+        ctx.set_strategy(np.full(65, 7, np.uint8), np.zeros(65, np.uint8))  # unknown filter id
+
+
+def test_strategy_api_and_container_roundtrip():
+    """Pixlzr.shrink_by_strategy -> container -> decode -> to_image_by_strategy, and process_by_strategy."""
+    img = load_png(os.path.join(GOLDEN, "Big-Ruscher.png"))
+    st = P.Strategy.by_level()
+    ref = O.shrink_strategy(img, 32, 32, 0, 0.5, st.down)  # shrink_by: value * factor * 10 is the oracle's default
+    want = O.expand_strategy(ref, st.up)
+    pix = P.Pixlzr.from_image(img, 32, 32)
+    pix.shrink_by_strategy(st, 0.5)
+    back = P.Pixlzr.decode_from_vec(pix.encode_to_vec())
+    got = back.to_image_by_strategy(st)
+    # fast analysis: the guard band also covers the bucket edges where the table changes filters
+    assert np.array_equal(got, want)
+    assert np.array_equal(back.to_image(P.FilterType.Nearest), O.expand(ref, O.NEAREST))  # and the plain path still works
+    ref2 = O.shrink_strategy(img, 64, 64, 0, 1.0, st.down, use_factor=False)
+    out = P.process_by_strategy(img, 64)
+    want2 = O.expand_strategy(ref2, st.up)
+    if want2.shape[2] == 3:
+        want2 = np.concatenate([want2, np.full(want2.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    assert np.array_equal(out, want2)

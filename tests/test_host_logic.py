@@ -178,3 +178,42 @@ def test_cli_arguments_and_operation_selection():
     assert cli.operation("x", "y") == ("image", "pix")          # no extension: image in, container out (main.rs:100, 109)
     assert cli.operation("x.webp", "y.png") == ("image", "image")
     assert set(cli.FILTERS) == {"nearest", "triangle", "catmull-rom", "gaussian", "lanczos3"}
+
+
+# ---------------------------------------------------------------------------------------------
+# per-block filter pairs: the table of the reference's experiment log
+# ---------------------------------------------------------------------------------------------
+def test_strategy_table_matches_reference_log():
+    """pxz_strategy_by_level (host function, no GPU) and the oracle's table against tests/golden/strategies.json, which
+    tests/golden/make_strategy_fixture.py parsed from strategies.txt / strategies_by_level.txt."""
+    import json
+    with open(os.path.join(GOLDEN, "strategies.json")) as f:
+        fx = json.load(f)
+    down, up = P.native.strategy_by_level()
+    odown, oup = O.strategy_by_level()
+    assert down.size == up.size == P.native.STRATEGY_BUCKETS == O.STRATEGY_BUCKETS == 65
+    assert np.array_equal(down, odown) and np.array_equal(up, oup)
+    for b, (d, u) in fx["per_bucket"].items():  # every bucket the author measured
+        b = min(int(b), 64)  # the log goes beyond v = 1; all of those are (Nearest, Nearest) like bucket 64
+        assert (down[b], up[b]) == (d, u), b
+    for r in fx["ranges"]:  # the summary: ranges of v
+        lo = int(round(r["lo"] * 64))
+        hi = 65 if r["hi"] is None else int(round(r["hi"] * 64))
+        assert (down[lo:hi] == r["down"]).all() and (up[lo:hi] == r["up"]).all(), r
+
+
+def test_strategy_bucket_rule():
+    """bucket = floor(64 * value / sqrt(2)) in f32, clamped; the library and the oracle agree on every edge."""
+    f32 = np.float32
+    vals = [0.0, -0.0, -1.0, float("nan"), float("inf"), 1e-30, 0.0221, 0.5, 0.99436, 1.0, 1.4142135, 1.4142137, 5.0]
+    vals += list(np.nextafter(f32(k / 64 * 2 ** 0.5), f32(s)) for k in range(1, 65) for s in (0, 4))
+    rng = np.random.default_rng(3)
+    vals += list(rng.random(2000, dtype=np.float32) * 1.6)
+    for v in vals:
+        b = P.native.strategy_bucket(v)
+        assert b == O.strategy_bucket(v)
+        t = f32(v) * f32(45.25483322143555)
+        want = 0 if not (t > 0) else (64 if t >= 64 else int(t))
+        assert b == want, (v, b, want)
+    with pytest.raises(ValueError):
+        P.native.Context.set_strategy(None, np.zeros(3, np.uint8), np.zeros(65, np.uint8))
