@@ -95,4 +95,56 @@ for it in range(iters // 5):
     if not ok:
         tbad += 1
         print("TREE MISMATCH", dict(it=it, c=c, w=w, h=h, bw=bw, bh=bh, mw=mw, mh=mh, fd=fd, fu=fu, thr=thr), flush=True)
-print(f"{iters} cases, {bad} mismatches; {iters // 5} tree cases, {tbad} mismatches")
+# per-block filter pairs (pxz_ctx_set_strategy) on a third as many cases: random tables, continuous factors (bucket edges),
+# fast and exact analysis, the expand both from the device payload and from descriptors that went through the host
+sbad = 0
+for it in range(iters // 3):
+    c = int(rng.choice([3, 4]))
+    bw, bh = int(rng.choice([8, 16, 24, 32, 40, 64, 128])), int(rng.choice([8, 16, 20, 32, 64, 80]))
+    w, h = int(rng.integers(8, 500)), int(rng.integers(8, 400))
+    if c == 4 and rng.random() < 0.7:
+        w = max(4, w // 4 * 4)
+    metric = int(rng.choice([0, 0, 0, 1]))
+    tw_min, th_min = (w % bw) or min(bw, w), (h % bh) or min(bh, h)
+    if metric == 1 and (min(bw, w, tw_min) < 2 or min(bh, h, th_min) < 2):
+        metric = 0
+    factor = float(np.exp(rng.uniform(np.log(0.01), np.log(0.6)))) * (20.0 if metric == 1 else 1.0)
+    flags = int(rng.choice([0, 0, N.FLAG_EXACT_VALUES, N.FLAG_AFTER_IDENTITY])) if metric == 0 else 0
+    kind = str(rng.choice(["auto", "warp", "cta"]))
+    if rng.random() < 0.5:
+        down, up = rng.integers(0, 5, 65).astype(np.uint8), rng.integers(0, 5, 65).astype(np.uint8)
+    else:  # a few ranges
+        edges = np.sort(rng.integers(1, 65, 4))
+        down, up = np.zeros(65, np.uint8), np.zeros(65, np.uint8)
+        for lo, hi in zip(np.r_[0, edges], np.r_[edges, 65]):
+            down[lo:hi], up[lo:hi] = rng.integers(0, 5), rng.integers(0, 5)
+    amp = 128.0 * 2.0 ** (-9.0 * rng.random(((h + bh - 1) // bh, (w + bw - 1) // bw)))
+    amp = np.kron(amp, np.ones((bh, bw)))[:h, :w, None]
+    xx = np.mgrid[0:h, 0:w][1]
+    img = np.clip(np.rint(128 + 60 * np.sin(xx / 41.0 + it)[..., None] * np.ones(c) + (rng.random((h, w, c)) - 0.5) * 2 * amp), 0, 255).astype(np.uint8)
+    if c == 4 and rng.random() < 0.5:
+        img[..., 3] = 255
+    img = np.ascontiguousarray(img)
+    ctx = ctxs[kind]
+    try:
+        ref = O.shrink_strategy(img, bw, bh, metric, factor, down, use_factor=0 if flags == N.FLAG_AFTER_IDENTITY else 1, nthreads=8)
+        want = O.expand_strategy(ref, up, nthreads=8)
+        ctx.set_strategy(down, up)
+        d = ctx.image_upload(img)
+        pl = d.shrink(bw, bh, metric, factor, 3, flags)
+        descs, px = pl.download()
+        out = pl.expand(3)
+        pl2 = ctx.payload_upload(w, h, bw, bh, c, descs, px)
+        out2 = pl2.expand(1)
+        pl2.free(); pl.free(); d.free()
+        ok = (np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"]) and np.array_equal(px, ref.payload)
+              and np.array_equal(out, want) and np.array_equal(out2, want))
+    except Exception as e:  # noqa: BLE001
+        ok = False
+        print("EXC", repr(e)[:200])
+    finally:
+        ctx.set_strategy(None, None)
+    if not ok:
+        sbad += 1
+        print("STRATEGY MISMATCH", dict(it=it, c=c, w=w, h=h, bw=bw, bh=bh, metric=metric, factor=factor, flags=flags, kind=kind), flush=True)
+print(f"{iters} cases, {bad} mismatches; {iters // 5} tree cases, {tbad} mismatches; {iters // 3} strategy cases, {sbad} mismatches")
