@@ -1045,31 +1045,50 @@ __global__ void __launch_bounds__(kThreads) k_plan(const float* __restrict__ vx,
   }
   unsigned long long excl = wbase + inc - tsum;
 
-  if (tid == 0) {
+  if (warp == 0) {
+    // decoupled look-back, one window of 32 predecessors per step: every lane waits for its own predecessor's status,
+    // the window is summed back to the nearest inclusive prefix (tiles are ticket-ordered, so predecessors always arrive)
+    constexpr unsigned long long kValue = (1ull << 62) - 1;
     unsigned long long prefix = 0;
     volatile unsigned long long* status = st->status;
     if (tile == 0) {
-      __threadfence();
-      status[0] = (2ull << 62) | agg;
-    } else {
-      status[tile] = (1ull << 62) | agg;
-      __threadfence();
-      int p = (int)tile - 1;
-      while (true) {
-        unsigned long long s;
-        do { s = status[p]; } while ((s >> 62) == 0ull);
-        prefix += s & ((1ull << 62) - 1);
-        if ((s >> 62) == 2ull) break;
-        --p;
+      if (lane == 0) {
+        __threadfence();
+        status[0] = (2ull << 62) | agg;
       }
-      __threadfence();
-      status[tile] = (2ull << 62) | (prefix + agg);
+    } else {
+      if (lane == 0) {
+        status[tile] = (1ull << 62) | agg;
+        __threadfence();
+      }
+      int base = (int)tile - 1;
+      while (true) {
+        const int idx = base - lane;
+        unsigned long long sv = 2ull << 62;  // before tile 0: an inclusive prefix of zero
+        if (idx >= 0) {
+          do { sv = status[idx]; } while ((sv >> 62) == 0ull);
+        }
+        const unsigned incl = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
+        const int stop = incl ? __ffs((int)incl) - 1 : 31;  // nearest inclusive prefix in this window
+        unsigned long long v = lane <= stop ? (sv & kValue) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        prefix += v;
+        if (incl) break;
+        base -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        status[tile] = (2ull << 62) | (prefix + agg);
+      }
     }
-    s_prefix = prefix;
+    if (lane == 0) s_prefix = prefix;
     if ((tile + 1) * (uint32_t)kPlanTile >= nblocks) {
-      *total = prefix + agg;
+      if (lane == 0) *total = prefix + agg;
       // every other CTA has published its status, hence reserved its slots: the cursors are final
-      for (int c = 0; c < kCostClasses; ++c) lists[(size_t)kCostClasses * cap + c] = atomicAdd(&cursor[c], 0u);
+      __syncwarp();
+      __threadfence();
+      if (lane < kCostClasses) lists[(size_t)kCostClasses * cap + lane] = atomicAdd(&cursor[lane], 0u);
     }
   }
   __syncthreads();
