@@ -566,7 +566,14 @@ __device__ __forceinline__ void map_values(const ValueMap& vm, const float* minm
 __device__ __forceinline__ float cbrtf_ref(float x) {  // x >= 0, finite
   if (x == 0.0f) return 0.0f;
   int xe;
-  const float xm = frexpf(x, &xe);
+  float xm;
+  const uint32_t xb = __float_as_uint(x);
+  if (xb >= 0x00800000u && xb < 0x7F800000u) {  // normal: frexp is a field split (mantissa in [0.5, 1))
+    xe = (int)(xb >> 23) - 126;
+    xm = __uint_as_float((xb & 0x007FFFFFu) | 0x3F000000u);
+  } else {
+    xm = frexpf(x, &xe);
+  }
   const double dxm = (double)xm;
   const float u = __double2float_rn(__dadd_rn(
       0.492659620528969547, __dmul_rn(__dsub_rn(0.697570460207922770, __dmul_rn(0.191502161678719066, dxm)), dxm)));
@@ -581,7 +588,8 @@ __device__ __forceinline__ float cbrtf_ref(float x) {  // x >= 0, finite
   const double num = __dmul_rn((double)u, __dadd_rn(dt2, __dmul_rn(2.0, dxm)));
   const double den = __dadd_rn(__dmul_rn(2.0, dt2), dxm);
   const float ym = __double2float_rn(__dmul_rn(__ddiv_rn(num, den), factor));
-  return ldexpf(ym, xe / 3);
+  // ldexpf(ym, xe / 3): ym is in [0.5, 2) and |xe / 3| <= 50, so the product with the power of two is exact
+  return __fmul_rn(ym, __uint_as_float((uint32_t)(xe / 3 + 127) << 23));
 }
 
 __device__ __forceinline__ void oklab_ref(const float* lut, uint32_t r8, uint32_t g8, uint32_t b8, float& L, float& A,
@@ -600,6 +608,64 @@ __device__ __forceinline__ void oklab_ref(const float* lut, uint32_t r8, uint32_
 constexpr int kExactChunk = 4096;             // pixels staged per pass
 constexpr int kExactStride = kExactChunk + 4; // +4 floats: 16-byte aligned rows, and the 4 channel lanes hit different banks
 
+// the sequential f32 sum of the reference over p[0..n), continuing from s; p is 16-byte aligned.  Loads run one batch
+// of 16 ahead of the dependent adds.
+__device__ __forceinline__ float chain_sum(const float* __restrict__ p, uint32_t n, float s) {
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  const uint32_t nb = n >> 4;
+#define PXZ_ADD16(q0, q1, q2, q3)                                                                       \
+  s = __fadd_rn(s, q0.x); s = __fadd_rn(s, q0.y); s = __fadd_rn(s, q0.z); s = __fadd_rn(s, q0.w);        \
+  s = __fadd_rn(s, q1.x); s = __fadd_rn(s, q1.y); s = __fadd_rn(s, q1.z); s = __fadd_rn(s, q1.w);        \
+  s = __fadd_rn(s, q2.x); s = __fadd_rn(s, q2.y); s = __fadd_rn(s, q2.z); s = __fadd_rn(s, q2.w);        \
+  s = __fadd_rn(s, q3.x); s = __fadd_rn(s, q3.y); s = __fadd_rn(s, q3.z); s = __fadd_rn(s, q3.w);
+  if (nb) {
+    float4 a0 = p4[0], a1 = p4[1], a2 = p4[2], a3 = p4[3];
+    for (uint32_t bi = 1; bi < nb; ++bi) {
+      const float4 c0 = p4[4 * bi], c1 = p4[4 * bi + 1], c2 = p4[4 * bi + 2], c3 = p4[4 * bi + 3];
+      PXZ_ADD16(a0, a1, a2, a3)
+      a0 = c0; a1 = c1; a2 = c2; a3 = c3;
+    }
+    PXZ_ADD16(a0, a1, a2, a3)
+  }
+#undef PXZ_ADD16
+  for (uint32_t i = nb << 4; i < n; ++i) s = __fadd_rn(s, p[i]);
+  return s;
+}
+
+template <int C>
+__device__ __forceinline__ void stage_exact_px(const uint8_t* __restrict__ base, size_t pitch, const Tile& t, uint32_t idx, uint32_t slot,
+                                               float* s_val, const float* s_lut256) {
+  const uint32_t y = idx / t.tw, x = idx - y * t.tw;
+  const uint8_t* p = base + (size_t)y * pitch + (size_t)x * C;
+  float L, A, B;
+  oklab_ref(s_lut256, p[0], p[1], p[2], L, A, B);
+  s_val[0 * kExactStride + slot] = A;
+  s_val[1 * kExactStride + slot] = B;
+  s_val[2 * kExactStride + slot] = L;
+  if (C == 4) s_val[3 * kExactStride + slot] = __fmul_rn((float)p[3], kInv255);
+}
+
+template <int C>
+__device__ __forceinline__ void stage_exact_px2(const uint8_t* __restrict__ base, size_t pitch, const Tile& t, uint32_t idx0, uint32_t idx1,
+                                                uint32_t slot0, uint32_t slot1, float* s_val, const float* s_lut256) {
+  const uint32_t y0 = idx0 / t.tw, x0 = idx0 - y0 * t.tw, y1 = idx1 / t.tw, x1 = idx1 - y1 * t.tw;
+  const uint8_t* p0 = base + (size_t)y0 * pitch + (size_t)x0 * C;
+  const uint8_t* p1 = base + (size_t)y1 * pitch + (size_t)x1 * C;
+  float L0, A0, B0, L1, A1, B1;
+  oklab_ref(s_lut256, p0[0], p0[1], p0[2], L0, A0, B0);
+  oklab_ref(s_lut256, p1[0], p1[1], p1[2], L1, A1, B1);
+  s_val[0 * kExactStride + slot0] = A0;
+  s_val[1 * kExactStride + slot0] = B0;
+  s_val[2 * kExactStride + slot0] = L0;
+  s_val[0 * kExactStride + slot1] = A1;
+  s_val[1 * kExactStride + slot1] = B1;
+  s_val[2 * kExactStride + slot1] = L1;
+  if (C == 4) {
+    s_val[3 * kExactStride + slot0] = __fmul_rn((float)p0[3], kInv255);
+    s_val[3 * kExactStride + slot1] = __fmul_rn((float)p1[3], kInv255);
+  }
+}
+
 template <int C>
 __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, const Tile& t, float* s_val /*[4][stride]*/,
                                 const float* s_lut256, float* s_avg /*[4]*/) {
@@ -614,17 +680,11 @@ __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, c
       const uint32_t n = min((uint32_t)kExactChunk, npx - c0);
       // stage the chunk (skipped in pass 2 when the whole tile is still resident)
       if (pass == 0 || npx > (uint32_t)kExactChunk) {
-        for (uint32_t i = tid; i < n; i += blockDim.x) {
-          const uint32_t idx = c0 + i;
-          const uint32_t y = idx / t.tw, x = idx - y * t.tw;
-          const uint8_t* p = base + (size_t)y * pitch + (size_t)x * C;
-          float L, A, B;
-          oklab_ref(s_lut256, p[0], p[1], p[2], L, A, B);
-          s_val[0 * kExactStride + i] = A;
-          s_val[1 * kExactStride + i] = B;
-          s_val[2 * kExactStride + i] = L;
-          if (C == 4) s_val[3 * kExactStride + i] = __fmul_rn((float)p[3], kInv255);
-        }
+        // two pixels per iteration: the conversion is a long dependent chain (double-precision divide), so a thread
+        // keeps six cube roots in flight instead of three
+        uint32_t i = tid;
+        for (; i + blockDim.x < n; i += 2 * blockDim.x) stage_exact_px2<C>(base, pitch, t, c0 + i, c0 + i + blockDim.x, i, i + blockDim.x, s_val, s_lut256);
+        if (i < n) stage_exact_px<C>(base, pitch, t, c0 + i, i, s_val, s_lut256);
         __syncthreads();
       }
       if (pass == 1) {
@@ -634,30 +694,7 @@ __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, c
         }
         __syncthreads();
       }
-      if (warp == 0 && lane < C) {
-        // the sequential f32 sum of the reference; loads run one batch of 16 ahead of the dependent adds
-        const float4* p4 = reinterpret_cast<const float4*>(s_val + lane * kExactStride);
-        float s = run;
-        const uint32_t nb = n >> 4;
-#define PXZ_ADD16(q0, q1, q2, q3)                                                                       \
-  s = __fadd_rn(s, q0.x); s = __fadd_rn(s, q0.y); s = __fadd_rn(s, q0.z); s = __fadd_rn(s, q0.w);        \
-  s = __fadd_rn(s, q1.x); s = __fadd_rn(s, q1.y); s = __fadd_rn(s, q1.z); s = __fadd_rn(s, q1.w);        \
-  s = __fadd_rn(s, q2.x); s = __fadd_rn(s, q2.y); s = __fadd_rn(s, q2.z); s = __fadd_rn(s, q2.w);        \
-  s = __fadd_rn(s, q3.x); s = __fadd_rn(s, q3.y); s = __fadd_rn(s, q3.z); s = __fadd_rn(s, q3.w);
-        if (nb) {
-          float4 a0 = p4[0], a1 = p4[1], a2 = p4[2], a3 = p4[3];
-          for (uint32_t bi = 1; bi < nb; ++bi) {
-            const float4 c0 = p4[4 * bi], c1 = p4[4 * bi + 1], c2 = p4[4 * bi + 2], c3 = p4[4 * bi + 3];
-            PXZ_ADD16(a0, a1, a2, a3)
-            a0 = c0; a1 = c1; a2 = c2; a3 = c3;
-          }
-          PXZ_ADD16(a0, a1, a2, a3)
-        }
-#undef PXZ_ADD16
-        const float* p = s_val + lane * kExactStride;
-        for (uint32_t i = nb << 4; i < n; ++i) s = __fadd_rn(s, p[i]);
-        run = s;
-      }
+      if (warp == 0 && lane < C) run = chain_sum(s_val + lane * kExactStride, n, run);
       __syncthreads();
     }
     if (pass == 0) {
