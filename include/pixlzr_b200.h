@@ -209,6 +209,16 @@ pxz_status pxz_container_decode(const uint8_t* data, size_t len, uint32_t* w, ui
                                 int32_t* filter_byte /* -1 if absent */, uint32_t* channels, uint64_t* payload_bytes,
                                 pxz_block_desc* descs, uint8_t* pixels);
 
+/* The same stage on the device: the per-block QOI streams are written from / decoded into the
+ * device-resident payload, so only the compressed file crosses PCIe.  Output and accepted input are byte-identical to
+ * pxz_container_encode / pxz_container_decode (= Pixlzr::encode_to_vec / decode_from_vec, src/encoding/mod.rs:40-165).
+ * values_present = 0 writes every block value as 0.0 (block_value == None, :173-178).  host_out: capacity from
+ * pxz_container_bound(); *bytes_out = size of the file.  pxz_payload_from_container returns a payload ready for
+ * pxz_expand*; *filter_byte as pxz_container_decode. */
+pxz_status pxz_payload_to_container(pxz_ctx* ctx, const pxz_payload* p, uint32_t filter_byte, int values_present, uint8_t* host_out,
+                                    size_t cap, uint64_t* bytes_out);
+pxz_status pxz_payload_from_container(pxz_ctx* ctx, const uint8_t* data, size_t len, int32_t* filter_byte, pxz_payload** out);
+
 #ifdef __cplusplus
 }
 #endif

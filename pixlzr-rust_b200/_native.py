@@ -67,6 +67,8 @@ SYMBOLS = {
     "pxz_comm_destroy": (None, [_vp]),
     "pxz_container_bound": (C.c_int64, [_u32, _u32, _u32, _u32, _u32, _u64]),
     "pxz_container_encode": (C.c_int64, [_u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _sz, _i]),
+    "pxz_payload_to_container": (_i, [_vp, _vp, _u32, _i, _vp, _sz, _P(_u64)]),
+    "pxz_payload_from_container": (_i, [_vp, _vp, _sz, _P(C.c_int32), _P(_vp)]),
     "pxz_container_decode": (_i, [_vp, _sz, _P(_u32), _P(_u32), _P(_u32), _P(_u32), _P(C.c_int32), _P(_u32),
                                   _P(_u64), _vp, _vp]),
 }
@@ -231,6 +233,14 @@ class Context:
         return Payload(self, hd)
 
 
+    def payload_from_container(self, data: bytes):
+        """(Payload, filter byte or -1): a .pxlzr file decoded on the device (pxz_payload_from_container)."""
+        buf = np.frombuffer(data, np.uint8)
+        hd, filt = C.c_void_p(), C.c_int32(-1)
+        self.check(lib().pxz_payload_from_container(self._h, ptr(buf), len(data), C.byref(filt), C.byref(hd)))
+        return Payload(self, hd), int(filt.value)
+
+
 class Image:
     def __init__(self, ctx: Context, handle, w, h, c):
         self.ctx, self._h, self.w, self.h, self.c = ctx, handle, w, h, c
@@ -286,6 +296,18 @@ class Payload:
     @property
     def handle(self):
         return self._h
+
+    def to_container(self, filter_byte: int = 0, values_present: bool = True) -> bytes:
+        """The .pxlzr file of this payload, QOI streams written on the device (pxz_payload_to_container)."""
+        i = self.info()
+        cap = lib().pxz_container_bound(i["w"], i["h"], i["bw"], i["bh"], i["channels"], i["bytes"])
+        if cap < 0:
+            raise PixlzrError(int(cap), "pxz_container_bound")
+        out = np.empty(cap, np.uint8)
+        n = C.c_uint64()
+        self.ctx.check(lib().pxz_payload_to_container(self.ctx.handle, self._h, int(filter_byte), int(values_present), ptr(out), cap,
+                                                      C.byref(n)))
+        return out[:n.value].tobytes()
 
     def info(self):
         v = [C.c_uint32() for _ in range(7)]

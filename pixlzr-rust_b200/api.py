@@ -316,6 +316,35 @@ class Pixlzr:
         p._values_present = True  # decode_block sets Some(value) (encoding/mod.rs:240)
         return p
 
+    # ---- container stage on the device: only the compressed file crosses PCIe ---------------------------
+    @staticmethod
+    def encode_image_to_vec(image: np.ndarray, block_width: int, block_height: int, filter_downscale: FilterType, factor: float,
+                            directionally: bool = False, ctx: Optional[N.Context] = None) -> bytes:
+        """from_image + shrink_by (or shrink_directionally) + encode_to_vec in one pass on the device: the per-block QOI
+        streams are written by the GPU from the resident payload (pxz_payload_to_container).  Same bytes as the three calls."""
+        image = _check_image(image)
+        ctx = ctx or default_context()
+        img = ctx.image_upload(image)
+        try:
+            pl = img.shrink(block_width, block_height, N.METRIC_SOBEL_DIR if directionally else N.METRIC_OKLAB_MAD, factor,
+                            int(filter_downscale), 0)
+            try:
+                return pl.to_container(0, True)  # from_image leaves `filter` unset: byte 0
+            finally:
+                pl.free()
+        finally:
+            img.free()
+
+    @staticmethod
+    def decode_vec_to_image(data: bytes, filter: FilterType, ctx: Optional[N.Context] = None) -> np.ndarray:
+        """decode_from_vec + to_image with the QOI streams decoded on the device (pxz_payload_from_container)."""
+        ctx = ctx or default_context()
+        pl, _ = ctx.payload_from_container(data)
+        try:
+            return pl.expand(int(filter))
+        finally:
+            pl.free()
+
     @classmethod
     def open(cls, path) -> "Pixlzr":
         with open(path, "rb") as f:

@@ -93,6 +93,15 @@ def run(args) -> None:
     filt = FILTERS[args.filter]
     shrink_by = api.parse_shrinking_factor(args.shrinking_factor)
     src, dst = operation(args.input, args.output)
+    # the two plain conversions run with the container stage on the device (same bytes / pixels as the general path)
+    if src == "image" and dst == "pix" and args.force:
+        with open(args.output, "wb") as f:
+            f.write(api.Pixlzr.encode_image_to_vec(_open_image(args.input), bw, bh, filt, shrink_by, bool(args.direction_wise)))
+        return
+    if src == "pix" and dst == "image":  # --force leaves a decoded file alone: every block carries a value (pixlzr.rs:168-170)
+        with open(args.input, "rb") as f:
+            _save_image(args.output, api.Pixlzr.decode_vec_to_image(f.read(), filt))
+        return
     if src == "image":                                   # image_to_pix / image_to_image (main.rs:142-214)
         pix = api.Pixlzr.from_image(_open_image(args.input), bw, bh)
     elif dst == "image":                                 # pix_to_image (main.rs:216-240)

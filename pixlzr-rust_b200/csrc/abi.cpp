@@ -906,9 +906,10 @@ pxz_status pxz_payload_download(pxz_ctx* ctx, const pxz_payload* p, pxz_block_de
   return PXZ_OK;
 }
 
-pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t channels,
-                              const pxz_block_desc* descs, const uint8_t* pixels, uint64_t bytes, pxz_payload** out) {
-  if (!ctx || !descs || (!pixels && bytes) || !out) return PXZ_E_ARG;
+// pixels == NULL with copy_pixels == false: the caller fills p->d_pixels on the device (pxz_payload_from_container)
+static pxz_status payload_from_descs(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t channels,
+                                     const pxz_block_desc* descs, const uint8_t* pixels, bool copy_pixels, uint64_t bytes,
+                                     pxz_payload** out) {
   *out = nullptr;
   cudaSetDevice(ctx->device);
   Geom g;
@@ -972,7 +973,7 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
   p->bytes_known = true;
   cudaError_t e = cudaMemcpyAsync(p->d_descs, descs, nblocks * sizeof(pxz_block_desc), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_tabidx, tabidx.data(), nblocks * 4, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(p->d_pixels, pixels, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && bytes && copy_pixels) e = cudaMemcpyAsync(p->d_pixels, pixels, bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_total, &p->bytes, 8, cudaMemcpyHostToDevice, ctx->stream);
   // work order of the expand kernel (blocks by cost class)
   if (e == cudaSuccess && ensure_scratch(ctx, (uint32_t)nblocks) != PXZ_OK) e = cudaErrorMemoryAllocation;
@@ -983,6 +984,112 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
     payload_release(p);
     return fail(ctx, PXZ_E_CUDA, std::string("payload upload: ") + cudaGetErrorString(e));
   }
+  *out = p;
+  return PXZ_OK;
+}
+
+pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t channels,
+                              const pxz_block_desc* descs, const uint8_t* pixels, uint64_t bytes, pxz_payload** out) {
+  if (!ctx || !descs || (!pixels && bytes) || !out) return PXZ_E_ARG;
+  return payload_from_descs(ctx, w, h, bw, bh, channels, descs, pixels, true, bytes, out);
+}
+
+// ---- container stage on the device (qoi_device.cu) ------------------------------------------------------------
+pxz_status pxz_payload_to_container(pxz_ctx* ctx, const pxz_payload* p, uint32_t filter_byte, int values_present, uint8_t* host_out,
+                                    size_t cap, uint64_t* bytes_out) {
+  if (!ctx || !p || !host_out || !bytes_out) return PXZ_E_ARG;
+  cudaSetDevice(ctx->device);
+  uint64_t bytes = 0;
+  pxz_status st = payload_bytes(ctx, p, &bytes);
+  if (st != PXZ_OK) return st;
+  const Geom& g = p->g;
+  const uint32_t nblocks = g.cols * g.rows;
+  const size_t arena_bytes = qoi_arena_bytes(nblocks, bytes, g.C);
+  const size_t out_cap = 26 + (size_t)4 * g.rows + arena_bytes;
+  uint8_t *d_arena = nullptr, *d_out = nullptr;
+  uint32_t* d_len = nullptr;
+  unsigned long long *d_off = nullptr, *d_total = nullptr;
+  auto release = [&]() { dev_free(ctx, d_arena); dev_free(ctx, d_out); dev_free(ctx, d_len); dev_free(ctx, d_off); dev_free(ctx, d_total); };
+  if ((st = dev_alloc(ctx, (void**)&d_arena, arena_bytes)) != PXZ_OK || (st = dev_alloc(ctx, (void**)&d_out, out_cap)) != PXZ_OK ||
+      (st = dev_alloc(ctx, (void**)&d_len, (size_t)nblocks * 4)) != PXZ_OK || (st = dev_alloc(ctx, (void**)&d_off, (size_t)nblocks * 8)) != PXZ_OK ||
+      (st = dev_alloc(ctx, (void**)&d_total, 8)) != PXZ_OK) {
+    release();
+    return st;
+  }
+  cudaError_t e = launch_qoi_encode(p->d_descs, p->d_pixels, g, values_present, filter_byte, d_arena, d_len, d_off, d_out, d_total,
+                                    ctx->stream, &ctx->launches);
+  unsigned long long total = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && total <= cap) {
+    e = cudaMemcpyAsync(host_out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  release();
+  if (e != cudaSuccess) return fail(ctx, PXZ_E_CUDA, std::string("container encode: ") + cudaGetErrorString(e));
+  *bytes_out = total;
+  if (total > cap) return fail(ctx, PXZ_E_ARG, "output buffer too small (size it with pxz_container_bound)");
+  return PXZ_OK;
+}
+
+pxz_status pxz_payload_from_container(pxz_ctx* ctx, const uint8_t* data, size_t len, int32_t* filter_byte, pxz_payload** out) {
+  if (!ctx || !data || !out) return PXZ_E_ARG;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  uint32_t w, h, bw, bh, ch;
+  int32_t filt = -1;
+  uint64_t bytes = 0;
+  // the host walks the headers (a few bytes per block); the streams themselves are decoded on the device
+  pxz_status st = pxz_container_decode(data, len, &w, &h, &bw, &bh, &filt, &ch, &bytes, nullptr, nullptr);
+  if (st != PXZ_OK) return fail(ctx, st, "malformed .pxlzr container");
+  Geom g;
+  if ((st = make_geom(ctx, w, h, ch, bw, bh, &g)) != PXZ_OK) return st;
+  const size_t nblocks = (size_t)g.cols * g.rows;
+  std::vector<pxz_block_desc> descs(nblocks);
+  st = pxz_container_decode(data, len, &w, &h, &bw, &bh, &filt, &ch, &bytes, descs.data(), nullptr);
+  if (st != PXZ_OK) return fail(ctx, st, "malformed .pxlzr container");
+  std::vector<unsigned long long> in_off(nblocks);
+  std::vector<uint32_t> qlen(nblocks);
+  {
+    size_t q = 26 + (size_t)4 * g.rows;  // constants.rs:19-20 + the line table; validated by the walk above
+    for (size_t b = 0; b < nblocks; ++b) {
+      const uint8_t* hd = data + q + 9;
+      qlen[b] = (uint32_t)hd[0] << 24 | (uint32_t)hd[1] << 16 | (uint32_t)hd[2] << 8 | hd[3];
+      in_off[b] = q + 13;
+      q += 13 + (size_t)qlen[b];
+    }
+  }
+  for (size_t b = 0; b < nblocks; ++b)
+    if (ch == 4 && (descs[b].offset & 3u)) return fail(ctx, PXZ_E_UNSUPPORTED, "unaligned RGBA block");  // cannot happen: w*h*4
+  pxz_payload* p = nullptr;
+  st = payload_from_descs(ctx, w, h, bw, bh, ch, descs.data(), nullptr, false, bytes, &p);
+  if (st != PXZ_OK) return st;
+  uint8_t* d_in = nullptr;
+  unsigned long long* d_off = nullptr;
+  uint32_t* d_len = nullptr;
+  int* d_err = nullptr;
+  auto release = [&]() { dev_free(ctx, d_in); dev_free(ctx, d_off); dev_free(ctx, d_len); dev_free(ctx, d_err); };
+  if ((st = dev_alloc(ctx, (void**)&d_in, len)) != PXZ_OK || (st = dev_alloc(ctx, (void**)&d_off, nblocks * 8)) != PXZ_OK ||
+      (st = dev_alloc(ctx, (void**)&d_len, nblocks * 4)) != PXZ_OK || (st = dev_alloc(ctx, (void**)&d_err, 4)) != PXZ_OK) {
+    release();
+    payload_release(p);
+    return st;
+  }
+  int err = 0;
+  cudaError_t e = cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, in_off.data(), nblocks * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, qlen.data(), nblocks * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, 4, ctx->stream);
+  if (e == cudaSuccess) e = launch_qoi_decode(d_in, d_off, d_len, p->d_descs, g, p->d_pixels, d_err, ctx->stream, &ctx->launches);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  release();
+  if (e != cudaSuccess || err) {
+    payload_release(p);
+    return e != cudaSuccess ? fail(ctx, PXZ_E_CUDA, std::string("container decode: ") + cudaGetErrorString(e))
+                            : fail(ctx, PXZ_E_FORMAT, "truncated QOI stream");
+  }
+  if (filter_byte) *filter_byte = filt;
   *out = p;
   return PXZ_OK;
 }

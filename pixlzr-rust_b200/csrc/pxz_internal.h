@@ -124,6 +124,14 @@ cudaError_t launch_class_lists(const pxz_block_desc* descs, const Geom& g, void*
 cudaError_t launch_tree_mask(const float* vx, const Geom& g, const uint8_t* parent_recurse, uint32_t parent_cols, float thr,
                              int positive, uint8_t* leaf, uint8_t* recurse, cudaStream_t s, uint64_t* launches);
 size_t plan_scan_state_bytes(uint32_t nblocks);
+// container stage on the device (qoi_device.cu): per-block QOI streams written from / decoded into the packed payload.
+// arena: qoi_arena_bytes(); out: 26 + 4 * rows + arena bytes; *total = bytes of the finished file
+size_t qoi_arena_bytes(uint32_t nblocks, uint64_t payload_bytes, uint32_t C);
+cudaError_t launch_qoi_encode(const pxz_block_desc* descs, const uint8_t* pixels, const Geom& g, int values_present,
+                              uint32_t filter_byte, uint8_t* arena, uint32_t* enc_len, unsigned long long* out_off, uint8_t* out,
+                              unsigned long long* total, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_qoi_decode(const uint8_t* in, const unsigned long long* in_off, const uint32_t* qlen, const pxz_block_desc* descs,
+                              const Geom& g, uint8_t* pixels, int* err, cudaStream_t s, uint64_t* launches);
 // direction 0: image tiles -> payload (shrink); 1: payload -> image tiles (expand)
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,

@@ -692,3 +692,78 @@ def test_strategy_api_and_container_roundtrip():
     if want2.shape[2] == 3:
         want2 = np.concatenate([want2, np.full(want2.shape[:2] + (1,), 255, np.uint8)], axis=2)
     assert np.array_equal(out, want2)
+
+
+# ---------------------------------------------------------------------------------------------
+# container stage on the device (second half): per-block QOI written / read by the GPU,
+# byte-identical to the host stage and to the reference's own files
+# ---------------------------------------------------------------------------------------------
+def test_device_container_reproduces_reference_files(ctx):
+    """The committed .pix / .pixlzr fixtures: decoded on the device = decoded on the host; re-encoded on the device =
+    the file itself (Big-Ruscher.pix is RGB with a shrunk payload, base.pixlzr RGBA at full size with trailing blocks)."""
+    for name in ("Big-Ruscher.pix", "base.pixlzr"):
+        with open(os.path.join(GOLDEN, name), "rb") as f:
+            data = f.read()
+        hdr, descs, pixels = N.container_decode(data)
+        pl, filt = ctx.payload_from_container(data)
+        d2, p2 = pl.download()
+        assert filt == hdr["filter"]
+        for k in ("w", "h", "offset"):
+            assert np.array_equal(d2[k], descs[k]), (name, k)
+        assert np.array_equal(d2["value"].view("<u4"), descs["value"].view("<u4"))
+        assert np.array_equal(p2, pixels), name
+        assert pl.to_container(max(filt, 0)) == data, name
+        assert np.array_equal(pl.expand(O.NEAREST), O.expand(O.Shrunk(hdr["w"], hdr["h"], hdr["bw"], hdr["bh"], hdr["channels"], descs, pixels), O.NEAREST))
+        pl.free()
+
+
+@pytest.mark.parametrize("shape,c,bs,metric,factor", [
+    ((300, 420), 4, 32, 0, 0.3),
+    ((97, 131), 3, 16, 0, 0.2),
+    ((384, 512), 4, 48, 1, 4.0),
+    ((64, 64), 4, 64, 0, 1.0),       # one block
+    ((250, 333), 3, 40, 0, 0.05),    # mostly tiny blocks
+])
+def test_device_container_matches_host_stage(ctx, shape, c, bs, metric, factor):
+    img = _spread_image(shape[1], shape[0], c, bs, seed=9)
+    img[: shape[0] // 2, : shape[1] // 2, :3] = (40, 90, 200)  # flat region: runs, index hits
+    d = ctx.image_upload(img)
+    pl = d.shrink(bs, bs, metric, factor, O.LANCZOS3, N.FLAG_EXACT_VALUES)
+    descs, px = pl.download()
+    for vp in (True, False):
+        host = N.container_encode(shape[1], shape[0], bs, bs, 4, c, descs, px, None if vp else np.zeros(len(descs), np.uint8))
+        dev = pl.to_container(4, vp)
+        assert dev == host, "device container differs from the host stage"
+    ref = O.shrink(img, bs, bs, metric, factor, O.LANCZOS3)
+    assert pl.to_container(4, True) == O.container_encode(ref, 4), "device container differs from the oracle"
+    back, filt = ctx.payload_from_container(host)
+    d2, p2 = back.download()
+    assert filt == 4 and np.array_equal(p2, px) and np.array_equal(d2["w"], descs["w"]) and np.array_equal(d2["h"], descs["h"])
+    assert (d2["value"] == 0).all()  # written with values_present = False
+    assert np.array_equal(back.expand(O.CATMULLROM), O.expand(ref, O.CATMULLROM))
+    back.free()
+    pl.free()
+    d.free()
+
+
+def test_device_container_rejects_garbage(ctx):
+    with open(os.path.join(GOLDEN, "base.pixlzr"), "rb") as f:
+        data = f.read()
+    for bad in (b"", b"PIXLZR", data[:100], b"X" + data[1:], data[:-7]):
+        with pytest.raises(RuntimeError):
+            ctx.payload_from_container(bad)
+    pl, _ = ctx.payload_from_container(data)  # the context is still usable afterwards
+    pl.free()
+
+
+def test_device_container_api_equals_three_calls():
+    img = load_png("Big-Ruscher.png")
+    pix = P.Pixlzr.from_image(img, 32, 32)
+    pix.shrink_by(P.FilterType.Lanczos3, 0.125)
+    data = pix.encode_to_vec()
+    assert P.Pixlzr.encode_image_to_vec(img, 32, 32, P.FilterType.Lanczos3, 0.125) == data
+    assert np.array_equal(P.Pixlzr.decode_vec_to_image(data, P.FilterType.CatmullRom),
+                          P.Pixlzr.decode_from_vec(data).to_image(P.FilterType.CatmullRom))
+    pix = P.Pixlzr.from_image(img, 48, 24)
+    pix.shrink_directionally(P.FilterType.Triangle, 2.0)
+    assert P.Pixlzr.encode_image_to_vec(img, 48, 24, P.FilterType.Triangle, 2.0, directionally=True) == pix.encode_to_vec()
