@@ -297,6 +297,14 @@ class Payload:
     def handle(self):
         return self._h
 
+    def to_container_into(self, out: np.ndarray, filter_byte: int = 0, values_present: bool = True) -> int:
+        """to_container into a caller-owned uint8 buffer (pinned memory makes the copy run at PCIe speed); returns the size."""
+        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        n = C.c_uint64()
+        self.ctx.check(lib().pxz_payload_to_container(self.ctx.handle, self._h, int(filter_byte), int(values_present), ptr(out), out.size,
+                                                      C.byref(n)))
+        return int(n.value)
+
     def to_container(self, filter_byte: int = 0, values_present: bool = True) -> bytes:
         """The .pxlzr file of this payload, QOI streams written on the device (pxz_payload_to_container)."""
         i = self.info()

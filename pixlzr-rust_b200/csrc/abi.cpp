@@ -44,9 +44,10 @@ struct TabSet {  // device copy of the axis tables of one (spec, filter, directi
 
 using TabKey = std::tuple<std::vector<uint32_t>, std::vector<uint32_t>, int, int>;
 
-enum KernelId { K_MAD_FAST = 0, K_MAD_EXACT, K_SOBEL, K_MINMAX, K_PLAN, K_RESAMPLE_DOWN, K_RESAMPLE_UP, K_COUNT };
+enum KernelId { K_MAD_FAST = 0, K_MAD_EXACT, K_SOBEL, K_MINMAX, K_PLAN, K_RESAMPLE_DOWN, K_RESAMPLE_UP, K_QOI_ENCODE, K_QOI_DECODE, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"analyze_mad_fast", "mad_exact",     "analyze_sobel", "minmax",
-                                           "plan",             "resample_down", "resample_up"};
+                                           "plan",             "resample_down", "resample_up",   "qoi_encode",
+                                           "qoi_decode"};
 struct ProfRec {
   int id;
   cudaEvent_t a, b;
@@ -1016,8 +1017,12 @@ pxz_status pxz_payload_to_container(pxz_ctx* ctx, const pxz_payload* p, uint32_t
     release();
     return st;
   }
-  cudaError_t e = launch_qoi_encode(p->d_descs, p->d_pixels, g, values_present, filter_byte, d_arena, d_len, d_off, d_out, d_total,
-                                    ctx->stream, &ctx->launches);
+  cudaError_t e;
+  {
+    ProfScope prof(ctx, K_QOI_ENCODE);
+    e = launch_qoi_encode(p->d_descs, p->d_pixels, g, values_present, filter_byte, d_arena, d_len, d_off, d_out, d_total, ctx->stream,
+                          &ctx->launches);
+  }
   unsigned long long total = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1080,7 +1085,10 @@ pxz_status pxz_payload_from_container(pxz_ctx* ctx, const uint8_t* data, size_t 
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, in_off.data(), nblocks * 8, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, qlen.data(), nblocks * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, 4, ctx->stream);
-  if (e == cudaSuccess) e = launch_qoi_decode(d_in, d_off, d_len, p->d_descs, g, p->d_pixels, d_err, ctx->stream, &ctx->launches);
+  if (e == cudaSuccess) {
+    ProfScope prof(ctx, K_QOI_DECODE);
+    e = launch_qoi_decode(d_in, d_off, d_len, p->d_descs, g, p->d_pixels, d_err, ctx->stream, &ctx->launches);
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   release();

@@ -56,6 +56,14 @@ for it in range(iters):
         pl = d.shrink(bw, bh, metric, factor, fd, flags)
         descs, px = pl.download()
         out = pl.expand(fu)
+        if it % 4 == 0:  # container stage on the device: same bytes as the oracle's writer, and back
+            file_bytes = pl.to_container(fd, True)
+            back, _ = ctx.payload_from_container(file_bytes)
+            bd, bp = back.download()
+            back.free()
+            if file_bytes != O.container_encode(ref, fd) and flags in (N.FLAG_EXACT_VALUES, N.FLAG_NORMALISE_GLOBAL) or not np.array_equal(bp, px) \
+                    or not np.array_equal(bd["w"], descs["w"]):
+                raise RuntimeError("device container mismatch")
         pl.free(); d.free()
         ok = (np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"]) and np.array_equal(descs["offset"], ref.descs["offset"])
               and np.array_equal(px, ref.payload) and np.array_equal(out, O.expand(ref, fu, nthreads=8)))
