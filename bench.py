@@ -257,6 +257,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             st.wait_event(ev0)           # ... and every other stream starts after it
         for _ in range(args.steps):
             step_device()
+        t_launched = time.time()         # host time to issue the K steps (launch-bound when close to the device time)
         for st in streams[1:]:
             e = torch.cuda.Event()
             e.record(st)
@@ -391,10 +392,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                              f"{[round(wk.busy_s * 1e3, 1) for wk in workers]} ms\n")
 
     # ---- reduce over ranks: max time -------------------------------------------------------------------
-    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3, (t_launched - t_wall0) * 1e3], dtype=torch.float64, device=dev)
+    per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
+        gathered = [torch.zeros_like(times) for _ in range(world)]
+        dist.all_gather(gathered, times)
+        per_rank_ms = [float(t[0]) / args.steps for t in gathered]  # diagnostic: which rank sets the max
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+    elapsed_ms, e2e_ms, host_issue_ms = float(times[0]), float(times[1]), float(times[2])
     if world > 1:  # whole-job launch count
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
@@ -465,6 +470,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "host_threads": n_workers,
                     "path": "pxz_image_upload -> pxz_shrink -> pxz_payload_download -> pxz_payload_upload -> pxz_expand, pinned host buffers"},
             "gpu_launches": int(launches),
+            # host wall time to issue one step's launches (max over ranks): the step is launch-bound when this nears ms_per_step
+            "host_issue_ms_per_step": round(host_issue_ms / args.steps, 4),
+            "ms_per_step_per_rank": [round(x, 4) for x in per_rank_ms],
             "fused_resample_mode": fused_info,
             "roofline": roofline,
             "kernels": kernels,
