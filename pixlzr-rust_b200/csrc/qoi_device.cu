@@ -72,10 +72,22 @@ __global__ void __launch_bounds__(kQoiThreads) k_qoi_encode(const pxz_block_desc
   bool seen_literal = false;
   const uint32_t npx = (uint32_t)d.w * d.h;
   const uint8_t* p = pixels + d.offset;
+  // pixels are fetched eight at a time: the loop body is one long dependent chain, a load per iteration would add its
+  // full latency to every pixel
+  constexpr uint32_t kBatch = 8;
+  uint32_t buf[kBatch];
   for (uint32_t i = 0; i < npx; ++i) {
-    uint32_t cur;
-    if (C == 4) cur = reinterpret_cast<const uint32_t*>(p)[i];
-    else cur = (uint32_t)p[3 * i] | ((uint32_t)p[3 * i + 1] << 8) | ((uint32_t)p[3 * i + 2] << 16) | 0xFF000000u;
+    if ((i & (kBatch - 1)) == 0) {
+#pragma unroll
+      for (uint32_t j = 0; j < kBatch; ++j) {
+        const uint32_t k = min(i + j, npx - 1);
+        if (C == 4) buf[j] = reinterpret_cast<const uint32_t*>(p)[k];
+        else buf[j] = (uint32_t)p[3 * k] | ((uint32_t)p[3 * k + 1] << 8) | ((uint32_t)p[3 * k + 2] << 16) | 0xFF000000u;
+      }
+    }
+    uint32_t cur = buf[0];
+#pragma unroll
+    for (uint32_t j = 0; j < kBatch - 1; ++j) buf[j] = buf[j + 1];  // register shift: no dynamic indexing
     if (cur == last) {
       if (++run == 62u || i + 1u == npx) {
         w.put(OP_RUN | (run - 1u));
