@@ -60,6 +60,38 @@ def merge_shards(parts: Sequence[Tuple[np.ndarray, np.ndarray]]) -> Tuple[np.nda
             np.concatenate(pixels_out) if pixels_out else np.zeros(0, np.uint8))
 
 
+def merge_shard_containers(files: Sequence[bytes], width: int, height: int) -> bytes:
+    """One .pxlzr file from the files of the block-row shards, in rank order.  Each rank can write its shard's file on
+    its own GPU (Payload.to_container): a file is header | one length per block row | the rows' blocks, and a shard is a
+    run of whole block rows, so the image's file is the image header, the length tables one after the other and the
+    block bytes one after the other.  Empty shards (more ranks than block rows) are passed as b""."""
+    tables, bodies, first = [], [], None
+    rows_total, prev_partial = 0, False
+    for f in files:
+        if not f:
+            continue
+        if len(f) < 26 or f[:6] != b"PIXLZR" or f[6:9] != b"\x00\x00\x02":
+            raise ValueError("not a version 0.0.2 .pxlzr shard")
+        w, h, bw, bh = (int.from_bytes(f[10 + 4 * i:14 + 4 * i], "big") for i in range(4))
+        if first is None:
+            first = (f[9], bw, bh)
+        if w != width or (f[9], bw, bh) != first:
+            raise ValueError("shards disagree on width, block size or filter")
+        rows = -(-h // bh)
+        if prev_partial:
+            raise ValueError("only the last shard may end in a partial block row")
+        prev_partial = h % bh != 0
+        tables.append(f[26:26 + 4 * rows])
+        bodies.append(f[26 + 4 * rows:])
+        rows_total += rows
+    if first is None:
+        raise ValueError("no shard holds any block row")
+    if rows_total != -(-height // first[2]):
+        raise ValueError("the shards do not cover the image's block rows")
+    head = b"PIXLZR\x00\x00\x02" + bytes([first[0]]) + b"".join(int(v).to_bytes(4, "big") for v in (width, height, first[1], first[2]))
+    return head + b"".join(tables) + b"".join(bodies)
+
+
 def share_comm_id(dist, make_id, rank: int, device=None) -> bytes:
     """Rank 0 creates the 128-byte NCCL unique id (make_id()), everyone receives it through a
     torch.distributed broadcast (any backend)."""

@@ -767,3 +767,27 @@ def test_device_container_api_equals_three_calls():
     pix = P.Pixlzr.from_image(img, 48, 24)
     pix.shrink_directionally(P.FilterType.Triangle, 2.0)
     assert P.Pixlzr.encode_image_to_vec(img, 48, 24, P.FilterType.Triangle, 2.0, directionally=True) == pix.encode_to_vec()
+
+
+def test_device_container_of_block_row_shards_stitches_to_the_whole_file(ctx):
+    """§8(e): every rank writes the file of its own block rows on its GPU; the host stitches them (here: 3 shards, one GPU)."""
+    S = P.sharding
+    w, h, bs = 333, 407, 32   # 13 block rows, the last one partial
+    img = _spread_image(w, h, 4, bs, seed=21)
+    d = ctx.image_upload(img)
+    pl = d.shrink(bs, bs, 0, 0.3, O.LANCZOS3, N.FLAG_EXACT_VALUES)
+    whole = pl.to_container(4, True)
+    pl.free()
+    d.free()
+    files = []
+    for rank in range(3):
+        y0, y1 = S.shard_pixel_rows(h, bs, 3, rank)
+        ds = ctx.image_upload(np.ascontiguousarray(img[y0:y1]))
+        ps = ds.shrink(bs, bs, 0, 0.3, O.LANCZOS3, N.FLAG_EXACT_VALUES)
+        files.append(ps.to_container(4, True))
+        ps.free()
+        ds.free()
+    assert S.merge_shard_containers(files, w, h) == whole
+    assert S.merge_shard_containers(files[:2] + [b""] + files[2:], w, h) == whole  # an empty shard is skipped
+    with pytest.raises(ValueError):
+        S.merge_shard_containers(files[:2], w, h)

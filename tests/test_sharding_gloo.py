@@ -94,6 +94,11 @@ def _worker(rank, world, port, out_dir):
             # and the merged payload goes through the product's host container stage unchanged
             a = P.native.container_encode(w, h, bs, bs, 4, 3, descs, pixels, None, nthreads=2)
             assert a == O.container_encode(whole, 4)
+            # each rank writes its own shard's file (on its GPU in production: Payload.to_container); stitched = the whole file
+            mine_file = O.container_encode(local, 4) if y1 > y0 else b""
+            files = [None] * world
+            dist.all_gather_object(files, mine_file)
+            assert S.merge_shard_containers(files, w, h) == a
 
     # 3. batch round-robin: every image is processed by exactly one rank
     mine_idx = S.round_robin(7, world, rank)
