@@ -126,8 +126,34 @@ def strategy_by_level():
     return buf[:STRATEGY_BUCKETS].copy(), buf[STRATEGY_BUCKETS:].copy()
 
 
+class PinnedBuffer:
+    """Page-locked host bytes (pxz_host_alloc) as a numpy uint8 array; freed with the object."""
+
+    def __init__(self, nbytes: int):
+        self._p = C.c_void_p()
+        st = lib().pxz_host_alloc(max(1, int(nbytes)), C.byref(self._p))
+        if st != OK:
+            self._p = C.c_void_p()
+            raise PixlzrError(st, "pxz_host_alloc")
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(1, int(nbytes)),))
+
+    def __del__(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self.array = None
+            lib().pxz_host_free(self._p)
+            self._p = C.c_void_p()
+
+
 class Context:
     """One device + one stream (pxz_ctx).  Not thread-safe; use one per thread."""
+    _staging: "PinnedBuffer | None" = None
+
+    def staging(self, nbytes: int) -> np.ndarray:
+        """A pinned scratch array of at least `nbytes` owned by the context (grows, never shrinks)."""
+        if self._staging is None or self._staging.array.size < nbytes:
+            self._staging = None
+            self._staging = PinnedBuffer(nbytes)
+        return self._staging.array
 
     def __init__(self, device: int = 0, cuda_stream: int | None = None):
         self._h = C.c_void_p()
@@ -311,9 +337,9 @@ class Payload:
         cap = lib().pxz_container_bound(i["w"], i["h"], i["bw"], i["bh"], i["channels"], i["bytes"])
         if cap < 0:
             raise PixlzrError(int(cap), "pxz_container_bound")
-        out = np.empty(cap, np.uint8)
+        out = self.ctx.staging(cap) if cap <= (1 << 30) else np.empty(cap, np.uint8)  # pinned: the file comes back at PCIe speed
         n = C.c_uint64()
-        self.ctx.check(lib().pxz_payload_to_container(self.ctx.handle, self._h, int(filter_byte), int(values_present), ptr(out), cap,
+        self.ctx.check(lib().pxz_payload_to_container(self.ctx.handle, self._h, int(filter_byte), int(values_present), ptr(out), out.size,
                                                       C.byref(n)))
         return out[:n.value].tobytes()
 
