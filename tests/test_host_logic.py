@@ -217,3 +217,28 @@ def test_strategy_bucket_rule():
         assert b == want, (v, b, want)
     with pytest.raises(ValueError):
         P.native.Context.set_strategy(None, np.zeros(3, np.uint8), np.zeros(65, np.uint8))
+
+
+def test_merge_shard_containers_host():
+    """Block-row shard files stitch to the image's file (host stage only; the device path is tested under -m gpu)."""
+    S = P.sharding
+    rng = np.random.default_rng(4)
+    w, h, bs = 150, 210, 32  # 7 block rows, the last one partial
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[40:120, 10:90] = (9, 200, 77)
+    whole = O.container_encode(O.shrink(img, bs, bs, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3), 4)
+    for world in (1, 2, 3, 7, 9):  # 9 ranks: two of them hold no block row
+        files = []
+        for rank in range(world):
+            y0, y1 = S.shard_pixel_rows(h, bs, world, rank)
+            files.append(O.container_encode(O.shrink(np.ascontiguousarray(img[y0:y1]), bs, bs, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3), 4)
+                         if y1 > y0 else b"")
+        assert S.merge_shard_containers(files, w, h) == whole, world
+    with pytest.raises(ValueError):
+        S.merge_shard_containers([files[0]], w, h)          # rows missing
+    with pytest.raises(ValueError):
+        S.merge_shard_containers([b"garbage" * 5], w, h)
+    with pytest.raises(ValueError):
+        S.merge_shard_containers([b"", b""], w, h)
+    with pytest.raises(ValueError):
+        S.merge_shard_containers(files[::-1], w, h)         # the partial row must come last
