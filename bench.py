@@ -392,13 +392,27 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                              f"{[round(wk.busy_s * 1e3, 1) for wk in workers]} ms\n")
 
     # ---- reduce over ranks: max time -------------------------------------------------------------------
-    times = torch.tensor([elapsed_ms, e2e_s * 1e3, (t_launched - t_wall0) * 1e3], dtype=torch.float64, device=dev)
+    reason_names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reason_bits = sum(1 << i for i, n in enumerate(reason_names) if n in (clocks.get("reasons") or []))
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3, (t_launched - t_wall0) * 1e3, clocks.get("sm_mhz") or -1.0, float(reason_bits)],
+                         dtype=torch.float64, device=dev)
     per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
         gathered = [torch.zeros_like(times) for _ in range(world)]
         dist.all_gather(gathered, times)
         per_rank_ms = [float(t[0]) / args.steps for t in gathered]  # diagnostic: which rank sets the max
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        # clocks of every rank's GPU: the line reports the slowest one and the union of the throttle reasons
+        mhz = [float(t[3]) for t in gathered]
+        bits = 0
+        for t in gathered:
+            bits |= int(t[4])
+        clocks["sm_mhz_per_rank"] = mhz
+        if all(m > 0 for m in mhz):
+            clocks["sm_mhz"] = min(mhz)
+        clocks["reasons"] = sorted(set(clocks.get("reasons") or []) | {n for i, n in enumerate(reason_names) if bits >> i & 1})
+        head = times[:3].clone()
+        dist.all_reduce(head, op=dist.ReduceOp.MAX)
+        times[:3] = head
     elapsed_ms, e2e_ms, host_issue_ms = float(times[0]), float(times[1]), float(times[2])
     if world > 1:  # whole-job launch count
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
