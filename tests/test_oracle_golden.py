@@ -152,3 +152,32 @@ def test_qoi_roundtrip_random():
         for shape in [(1, 1), (5, 7), (64, 64)]:
             img = rng.integers(0, 4, size=shape + (c,), dtype=np.uint8) * 60
             assert np.array_equal(O.qoi_decode(O.qoi_encode(img)), img)
+
+
+def test_oracle_strategy_reduces_to_plain_filters_and_follows_buckets():
+    """EXTENSION (per-block filter pairs): a uniform table is the ordinary path, and a two-filter table equals the
+    block-by-block composition of the two plain results, split by pxo_strategy_bucket of the stored value."""
+    import numpy as np
+    import oracle as O
+    rng = np.random.default_rng(12)
+    h, w, bs = 96, 160, 32
+    amp = np.kron(128.0 * 2.0 ** (-8.0 * rng.random((h // bs, w // bs))), np.ones((bs, bs)))[..., None]
+    img = np.clip(128 + (rng.random((h, w, 3)) - 0.5) * 2 * amp, 0, 255).astype(np.uint8)
+    plain = {f: O.shrink(img, bs, bs, O.METRIC_OKLAB_MAD, 0.2, f) for f in (O.NEAREST, O.LANCZOS3)}
+    uni = O.shrink_strategy(img, bs, bs, O.METRIC_OKLAB_MAD, 0.2, np.full(65, O.LANCZOS3, np.uint8))
+    assert np.array_equal(uni.payload, plain[O.LANCZOS3].payload) and np.array_equal(uni.descs, plain[O.LANCZOS3].descs)
+    assert np.array_equal(O.expand_strategy(uni, np.full(65, O.TRIANGLE, np.uint8)), O.expand(uni, O.TRIANGLE))
+    # buckets below 20 -> Nearest, the others -> Lanczos3
+    table = np.where(np.arange(65) < 20, O.NEAREST, O.LANCZOS3).astype(np.uint8)
+    mixed = O.shrink_strategy(img, bs, bs, O.METRIC_OKLAB_MAD, 0.2, table)
+    buckets = np.array([O.strategy_bucket(v) for v in mixed.descs["value"]])
+    assert (buckets < 20).any() and (buckets >= 20).any()
+    for i, b in enumerate(buckets):
+        src = plain[O.NEAREST] if b < 20 else plain[O.LANCZOS3]
+        assert np.array_equal(mixed.block(i), src.block(i)), i
+    up = O.expand_strategy(mixed, table)
+    full = {f: O.expand(mixed, f) for f in (O.NEAREST, O.LANCZOS3)}
+    cols = w // bs
+    for i, b in enumerate(buckets):
+        y, x = (i // cols) * bs, (i % cols) * bs
+        assert np.array_equal(up[y:y + bs, x:x + bs], full[O.NEAREST if b < 20 else O.LANCZOS3][y:y + bs, x:x + bs]), i
