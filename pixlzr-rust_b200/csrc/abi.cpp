@@ -40,6 +40,7 @@ struct TabSet {  // device copy of the axis tables of one (spec, filter, directi
   uint32_t max_words = 0;  // largest single table (left | count | weights), in 32-bit words
   uint32_t ntabs = 0;
   bool warp_ok = false;    // every table has the form the warp-per-tile kernels need
+  bool has_noslide = false;  // direction 0: some table has no slide form (k_shrink_tma leaves those tiles to k_shrink_warp)
 };
 
 using TabKey = std::tuple<std::vector<uint32_t>, std::vector<uint32_t>, int, int>;
@@ -85,7 +86,7 @@ struct pxz_ctx {
   size_t values_cap = 0;
   float* d_minmax = nullptr;
   uint32_t* d_tile_counter = nullptr;  // work counter of the warp-per-tile resample kernels (they leave it at 0)
-  int resample_kernels = 0;            // 0 = by tile count, 1 = warp-per-tile, 2 = CTA-per-tile (PXZ_RESAMPLE_KERNELS=warp|cta)
+  int resample_kernels = 0;            // 0 = by tile count, 1 = warp-per-tile (cp.async ring), 2 = CTA-per-tile, 3 = warp-per-tile with the TMA shrink kernel (PXZ_RESAMPLE_KERNELS=warp|cta|tma)
   void* d_scan = nullptr;
   size_t scan_cap = 0;
   uint8_t* d_scratch = nullptr;
@@ -281,12 +282,14 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
       seen[{n_in, n_out}] = t;
     }
   }
+  pool.resize(pool.size() + 16, 0u);  // staged copies are rounded up to 16 bytes
   TabSet ts;
   ts.ntabs = (uint32_t)tabs.size();
   ts.warp_ok = true;
   for (const AxisTab& t : tabs) {
     ts.max_words = std::max(ts.max_words, std::max(2 * t.n_out + t.n_out * t.stride, t.bwords));
     if (direction == 1 && t.goff == 0xFFFFFFFFu) ts.warp_ok = false;
+    if (direction == 0 && t.s2words == 0) ts.has_noslide = true;
   }
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_tabs, tabs.size() * sizeof(AxisTab))) != PXZ_OK) return st;
@@ -327,7 +330,7 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
   PXZ_CUDA(ctx, launch_resample(direction, img, pitch, g, p->d_descs, tabidx, p->d_pixels, ts.d_tabs, ts.d_pool,
                                 ts.ntabs, max_src_px, max_src_dim, max_tmp_px, ts.max_words, scratch, per_cta, grid, ctx->fast_resample, opaque_flags,
                                 ctx->resample_kernels != 2 ? ctx->d_tile_counter : nullptr, p->d_order(), (uint32_t)p->nblocks_cap,
-                                ts.warp_ok, ctx->resample_kernels == 1, ctx->stream, ctx->sm_count,
+                                ts.warp_ok, ctx->resample_kernels, ts.has_noslide, ctx->stream, ctx->sm_count,
                                 &ctx->launches));
   return PXZ_OK;
 }
@@ -389,7 +392,7 @@ pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx*
   ctx->band.abs_raw = 8.0e-6f; // fast arithmetic, absolute (SFU cube roots; measured <= 4e-6)
   if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
   if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
-  if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->resample_kernels = !strcmp(e, "warp") ? 1 : !strcmp(e, "cta") ? 2 : 0;
+  if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->resample_kernels = !strcmp(e, "warp") ? 1 : !strcmp(e, "cta") ? 2 : !strcmp(e, "tma") ? 3 : 0;
   if (cudaMalloc((void**)&ctx->d_minmax, 4 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_tile_counter, 64) != cudaSuccess || cudaMemset(ctx->d_tile_counter, 0, 64) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_total, 64) != cudaSuccess) {

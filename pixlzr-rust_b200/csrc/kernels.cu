@@ -1403,6 +1403,15 @@ __device__ __forceinline__ u64 mac2(u64 acc, u64 p, u64 w, const TapK& k) {
   if (MODE & 2) return fma2(p, w, acc);
   return fma2(fma2(p, w, k.nz2), k.one2, acc);
 }
+// the same with the accumulator updated in place (one register pair in and out: no copies in loop-carried chains)
+template <int MODE>
+__device__ __forceinline__ void mac2_acc(u64& acc, u64 p, u64 w, const TapK& k) {
+  if (MODE & 2) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(p), "l"(w));
+  } else {
+    asm("{\n.reg .b64 t;\nfma.rn.f32x2 t, %1, %2, %3;\nfma.rn.f32x2 %0, t, %4, %0;\n}" : "+l"(acc) : "l"(p), "l"(w), "l"(k.nz2), "l"(k.one2));
+  }
+}
 template <int MODE>
 __device__ __forceinline__ float mac1(float acc, float p, float w) {
   if (MODE & 2) return fmaf(p, w, acc);
@@ -1906,7 +1915,11 @@ __global__ void __launch_bounds__(kThreads) k_tree_mask(const float* __restrict_
 #ifndef PXZ_EXPAND_WARP_CTAS
 #define PXZ_EXPAND_WARP_CTAS 4
 #endif
+#ifndef PXZ_SHRINK_TMA_CTAS
+#define PXZ_SHRINK_TMA_CTAS 3
+#endif
 #include "resample_warp.cuh"
+#include "resample_tma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // launchers
@@ -2080,11 +2093,39 @@ size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C)
 
 int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (long long)sm_count * 8); }
 
+// cuTensorMapEncodeTiled through the runtime (the library links cudart statically and has no libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// the pitched RGBA8 image as a 2-D tensor of 32-bit pixels, box = 64 px x kTBoxRows rows
+static bool make_image_tmap(const uint8_t* img, size_t pitch, uint32_t W, uint32_t H, CUtensorMap* tm) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {W, H};
+  const cuuint64_t strides[1] = {pitch};
+  const cuuint32_t box[2] = {64, (cuuint32_t)kTBoxRows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
                             uint8_t* scratch, size_t scratch_per_cta, int grid, bool fused, const uint8_t* opaque_flags,
-                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, bool force_warp,
+                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, int prefer, bool has_noslide,
                             cudaStream_t s, int sm_count, uint64_t* launches) {
   cudaError_t e;
   ++*launches;
@@ -2093,21 +2134,46 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                     ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && max_src_px <= (uint32_t)kFastMaxPx && max_src_dim <= 64u &&
                     max_tmp_px <= (uint32_t)kFastMaxPx && max_tab_words <= (uint32_t)kFastMaxTabWords &&
                     ntabs <= (uint32_t)kFastMaxTabs && scratch == nullptr;
-  // warp-per-tile kernels (resample_warp.cuh) once there are enough tiles to keep every warp slot of the GPU busy for
-  // a few tiles; below that one tile's latency (15-40 us on one warp) decides and 8 warps per tile finish sooner
+  // warp-per-tile kernels (resample_warp.cuh, resample_tma.cuh) once there are enough tiles to keep every warp slot of
+  // the GPU busy for a few tiles; below that one tile's latency (15-40 us on one warp) decides and 8 warps per tile
+  // finish sooner.  prefer: 0 = by tile count, 1 = warp kernels (cp.async ring), 2 = CTA kernels, 3 = TMA shrink kernel
   const long long ntiles = (long long)g.cols * g.rows;
-  if (fast && warp_tables && tile_counter != nullptr && (force_warp || ntiles >= (long long)sm_count * 16)) {
+  const bool force_warp = prefer == 1 || prefer == 3;
+  if (fast && warp_tables && tile_counter != nullptr && prefer != 2 && (force_warp || ntiles >= (long long)sm_count * 16)) {
     if (direction == 0) {
+      bool ring_kernel = prefer == 1;
+      if (!ring_kernel) {
+        CUtensorMap tm;
+        if (make_image_tmap(img, pitch, g.W, g.H, &tm)) {
+          const size_t smem = (size_t)kTWarps * kTWarpBytes;
+          const int tgrid = clamp_grid((ntiles + kTWarps - 1) / kTWarps, (long long)sm_count * PXZ_SHRINK_TMA_CTAS);
+          if (fused) {
+            e = set_smem(k_shrink_tma<true>, smem);
+            if (e != cudaSuccess) return e;
+            e = launch_pdl(k_shrink_tma<true>, tgrid, kTWarps * 32, smem, s, tm, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, ntabs, pool, tile_counter, 1.0f, -0.0f);
+          } else {
+            e = set_smem(k_shrink_tma<false>, smem);
+            if (e != cudaSuccess) return e;
+            e = launch_pdl(k_shrink_tma<false>, tgrid, kTWarps * 32, smem, s, tm, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, ntabs, pool, tile_counter, 1.0f, -0.0f);
+          }
+          if (e != cudaSuccess) return e;
+          if (!has_noslide) return cudaGetLastError();
+          ++*launches;  // the tiles without a slide table go to the ring kernel
+        } else {
+          ring_kernel = true;
+        }
+      }
+      const uint32_t only_noslide = ring_kernel ? 0u : 1u;
       const size_t smem = (size_t)kShrinkWarps * kShrinkWarpBytes;
       const int wgrid = clamp_grid((ntiles + kShrinkWarps - 1) / kShrinkWarps, (long long)sm_count * PXZ_SHRINK_WARP_CTAS);
       if (fused) {
         e = set_smem(k_shrink_warp<true>, smem);
         if (e != cudaSuccess) return e;
-        e = launch_pdl(k_shrink_warp<true>, wgrid, kShrinkCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+        e = launch_pdl(k_shrink_warp<true>, wgrid, kShrinkCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f, only_noslide);
       } else {
         e = set_smem(k_shrink_warp<false>, smem);
         if (e != cudaSuccess) return e;
-        e = launch_pdl(k_shrink_warp<false>, wgrid, kShrinkCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f);
+        e = launch_pdl(k_shrink_warp<false>, wgrid, kShrinkCtaThreads, smem, s, img, pitch, g, descs, tabidx, lists, cap, opaque_flags, payload, tabs, pool, tile_counter, 1.0f, -0.0f, only_noslide);
       }
     } else {
       const size_t smem = (size_t)kWarpsPerCta * kExpandWarpBytes;

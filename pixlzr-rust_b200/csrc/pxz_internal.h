@@ -39,7 +39,7 @@ struct AxisTab {
   uint32_t n_in, n_out, stride, off;
   uint32_t boff, nb, brows_total, bwords;
   uint32_t soff, slots, goff, gpoff;
-  uint32_t bpad, pad0_, pad1_, pad2_;
+  uint32_t bpad, s2off, s2words, pad2_;  // s2off / s2words: slide2 form (tables.cpp), 0 words = none
 };
 
 // Geometry of the block grid over a pitched image.
@@ -137,7 +137,7 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,
                             uint32_t ntabs, uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, uint32_t max_tab_words,
                             uint8_t* scratch, size_t scratch_per_cta, int grid_hint, bool fused, const uint8_t* opaque_flags,
-                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, bool force_warp,
+                            uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, int prefer, bool has_noslide,
                             cudaStream_t s, int sm_count, uint64_t* launches);
 size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
 int resample_grid(int sm_count, uint32_t nblocks);

@@ -450,7 +450,8 @@ __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shr
     const uint8_t* __restrict__ img, size_t pitch, Geom g, const pxz_block_desc* __restrict__ descs,
     const uint32_t* __restrict__ tabidx, const uint32_t* __restrict__ lists, uint32_t cap, const uint8_t* __restrict__ opaque_flags,
     uint8_t* __restrict__ payload,
-    const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool, uint32_t* counter, float rt_one, float rt_negzero) {
+    const AxisTab* __restrict__ tabs, const uint32_t* __restrict__ pool, uint32_t* counter, float rt_one, float rt_negzero,
+    uint32_t only_noslide) {
   extern __shared__ float4 s_warp[];
   float4* strip = s_warp + (threadIdx.x >> 5) * (kShrinkWarpBytes / 16);
   uint32_t* ring = reinterpret_cast<uint32_t*>(strip + kStripRows * kStripStride);
@@ -467,6 +468,8 @@ __global__ void __launch_bounds__(kShrinkCtaThreads, PXZ_SHRINK_WARP_CTAS) k_shr
   auto process = [&](uint32_t b, const pxz_block_desc& d, uint32_t ti) {
     const Tile t = tile_of(g, b);
     if (d.w == 0 || d.h == 0) return;  // masked out (quadtree levels)
+    // second launch behind k_shrink_tma: only the tiles whose vertical table has no slide form are left
+    if (only_noslide && ((d.w == t.tw && d.h == t.th) || tabs[ti >> 16].s2words != 0)) return;
     if (d.w == t.tw && d.h == t.th) {
       // block.rs:279-281: clone.  The block is contiguous in the payload (4-byte aligned only).  Two rows per
       // instruction, 16 bytes per lane, 16 rows in flight.

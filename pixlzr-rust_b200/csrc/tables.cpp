@@ -173,7 +173,8 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
   tab->goff = 0xFFFFFFFFu;
   tab->gpoff = 0;
   tab->bpad = bpad;
-  tab->pad0_ = tab->pad1_ = tab->pad2_ = 0;
+  tab->s2off = tab->s2words = 0;
+  tab->pad2_ = 0;
   auto weight_of = [&](uint32_t o, uint32_t i) {
     float w;
     memcpy(&w, &(*pool)[wbase + (size_t)o * stride + i], sizeof(float));
@@ -214,6 +215,22 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
       pool->resize(pool->size() + 12, 0u);  // the kernels prefetch one table row (and one count) past the end
       tab->soff = (uint32_t)sbase;
       tab->slots = slots;
+      // ---- slide2 form (k_shrink_tma): the same rows with every weight stored twice, (w, w) = one f32x2 operand
+      // whose lanes are two image columns, `slots` pairs per row, then end[n_out] = the source sample that holds
+      // output o's last tap.  Staged into shared memory per warp with one bulk copy (16-byte multiple).
+      while (pool->size() % 4) pool->push_back(0u);
+      const size_t s2 = pool->size();
+      pool->resize(s2 + (size_t)n_in * slots * 2, 0u);
+      for (uint32_t r = 0; r < n_in; ++r)
+        for (uint32_t s = 0; s < slots; ++s) {
+          const uint32_t wbits = (*pool)[sbase + (size_t)r * 8 + s];
+          (*pool)[s2 + ((size_t)r * slots + s) * 2] = wbits;
+          (*pool)[s2 + ((size_t)r * slots + s) * 2 + 1] = wbits;
+        }
+      for (uint32_t o = 0; o < n_out; ++o) pool->push_back(tr[o] - 1);
+      while (pool->size() % 4) pool->push_back(0u);
+      tab->s2off = (uint32_t)s2;
+      tab->s2words = (uint32_t)(pool->size() - s2);
     }
   }
   // ---- gather8 form ----

@@ -464,7 +464,8 @@ def test_tree_process_edge_cases(ctx):
 
 # ---------------------------------------------------------------------------------------------
 # Both resample kernel families stay bit-exact.  By default the library picks by tile count (warp-per-tile from
-# 16 tiles per SM, CTA-per-tile below); PXZ_RESAMPLE_KERNELS=warp|cta, read when a context is created, forces one.
+# 16 tiles per SM — the TMA-fed shrink kernel there — CTA-per-tile below); PXZ_RESAMPLE_KERNELS=warp|cta|tma, read when a
+# context is created, forces one (warp = the cp.async ring kernels).
 # ---------------------------------------------------------------------------------------------
 def _forced_ctx(kind):
     old = os.environ.get("PXZ_RESAMPLE_KERNELS")
@@ -480,10 +481,10 @@ def _forced_ctx(kind):
 
 @pytest.fixture(scope="module")
 def forced_ctx():
-    return {"cta": _forced_ctx("cta"), "warp": _forced_ctx("warp")}
+    return {"cta": _forced_ctx("cta"), "warp": _forced_ctx("warp"), "tma": _forced_ctx("tma")}
 
 
-@pytest.mark.parametrize("kind", ["warp", "cta"])
+@pytest.mark.parametrize("kind", ["warp", "cta", "tma"])
 @pytest.mark.parametrize("shape,bs,metric,factor,fd,fu", [
     ((520, 776), 64, 0, 1.0, O.LANCZOS3, O.LANCZOS3),      # trailing 8-px / 8-row tiles
     ((300, 420), 32, 0, 1.0, O.CATMULLROM, O.TRIANGLE),
