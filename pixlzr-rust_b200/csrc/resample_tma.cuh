@@ -196,10 +196,8 @@ __device__ __forceinline__ uint32_t strip_col(uint32_t c) { return (c >> 1) + ((
 
 // ---- horizontal pass over `nrows` strip rows (output rows row0 .. row0 + nrows - 1) -> payload block at dst ------
 template <int MODE>
-__device__ __noinline__ void tma_horizontal(const float4* strip, uint32_t row0, uint32_t nrows, uint32_t dw, const HTab ht, uint32_t* dst,
-                                            float rt_one, float rt_negzero) {
-  // a real call: the pass is shared by every vertical variant (the kernel would not fit the instruction cache otherwise)
-  const TapK k = make_tapk(rt_one, rt_negzero);
+__device__ __forceinline__ void tma_horizontal_body(const float4* strip, uint32_t row0, uint32_t nrows, uint32_t dw, const HTab& ht,
+                                                    uint32_t* dst, const TapK& k) {
   const uint32_t lane = threadIdx.x & 31u;
   if (dw >= kBlockedFrom) {
     const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(ht.tab);
@@ -259,6 +257,21 @@ __device__ __noinline__ void tma_horizontal(const float4* strip, uint32_t row0, 
       reinterpret_cast<uint8_t*>(dst)[((size_t)(row0 + r) * dw + ox) * 4 + c] = (uint8_t)byte;
     }
   }
+}
+
+// A real call for the vertical variants that are not worth their own copy of the pass (2- and 4-slot tables with more
+// output rows than slots: filters other than Lanczos3 / Gaussian); the Lanczos3 path and the short tiles inline it.
+template <int MODE>
+__device__ __noinline__ void tma_horizontal_call(const float4* strip, uint32_t row0, uint32_t nrows, uint32_t dw, const HTab ht,
+                                                 uint32_t* dst, float rt_one, float rt_negzero) {
+  const TapK k = make_tapk(rt_one, rt_negzero);
+  tma_horizontal_body<MODE>(strip, row0, nrows, dw, ht, dst, k);
+}
+template <int MODE, bool INLINE>
+__device__ __forceinline__ void tma_horizontal(const float4* strip, uint32_t row0, uint32_t nrows, uint32_t dw, const HTab& ht,
+                                               uint32_t* dst, const TapK& k) {
+  if (INLINE) tma_horizontal_body<MODE>(strip, row0, nrows, dw, ht, dst, k);
+  else tma_horizontal_call<MODE>(strip, row0, nrows, dw, ht, dst, k.one, k.nz);
 }
 
 // ---- tiles whose output rows all fit the accumulators (dh <= A) ------------------------------------------------------
@@ -345,9 +358,6 @@ __device__ __forceinline__ void tma_shrink_tile_simple(TFeed& f, TQueue& q, cons
       srow[32] = make_float4(hi2(acc[o][0]), hi2(acc[o][1]), hi2(acc[o][2]), NC > 3 ? hi2(acc[o][NC > 3 ? 3 : 0]) : 0.f);
     }
   }
-  __syncwarp();
-  tma_horizontal<MODE>(strip, 0, dh, dw, ht, dst, k.one, k.nz);
-  __syncwarp();
 }
 
 // ---- vertical pass + horizontal batches of one tile -----------------------------------------------------------------
@@ -459,7 +469,7 @@ __device__ __forceinline__ void tma_shrink_tile(TFeed& f, TQueue& q, const CUten
     if (o < dh) e = lds_u32(endp + 4 * o);
     if (o - batch0 == (uint32_t)kTStripRows || o == dh) {
       __syncwarp();
-      tma_horizontal<MODE>(strip, batch0, o - batch0, dw, ht, dst, k.one, k.nz);
+      tma_horizontal<MODE, A == 6>(strip, batch0, o - batch0, dw, ht, dst, k);
       __syncwarp();
       batch0 = o;
       if (o == dh) break;
@@ -610,12 +620,21 @@ __global__ void __launch_bounds__(kTWarps * 32, PXZ_SHRINK_TMA_CTAS) k_shrink_tm
         // output's, so output o sits in slot o)
 #define PXZ_TMA_TILE(M)                                                                                              \
   do {                                                                                                               \
+    bool simple = true;                                                                                              \
     if (slots == 2 && d.h == 1) tma_shrink_tile_simple<M, 1, 2>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k);  \
     else if (slots == 2 && d.h == 2) tma_shrink_tile_simple<M, 2, 2>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k); \
     else if (slots == 4 && d.h <= 4) tma_shrink_tile_simple<M, 4, 4>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k); \
-    else if (slots == 2) tma_shrink_tile<M, 2>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k);                 \
-    else if (slots == 4) tma_shrink_tile<M, 4>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k);                 \
-    else tma_shrink_tile<M, 6>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k);                                 \
+    else {                                                                                                           \
+      simple = false;                                                                                                \
+      if (slots == 2) tma_shrink_tile<M, 2>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k);                    \
+      else if (slots == 4) tma_shrink_tile<M, 4>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k);               \
+      else tma_shrink_tile<M, 6>(f, q, &tm, t.th, d.w, d.h, vtab, strip, ht, dst, k);                               \
+    }                                                                                                                \
+    if (simple) { /* the strip holds the whole block: one shared copy of the pass */                                 \
+      __syncwarp();                                                                                                  \
+      tma_horizontal<M, true>(strip, 0, d.h, d.w, ht, dst, k);                                                       \
+      __syncwarp();                                                                                                  \
+    }                                                                                                                \
   } while (0)
         if (opaque) PXZ_TMA_TILE(F);
         else PXZ_TMA_TILE(F | 1);
