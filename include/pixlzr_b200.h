@@ -196,6 +196,11 @@ pxz_status pxz_tree_process(pxz_ctx* ctx, const pxz_image* img, float threshold,
 pxz_status pxz_comm_unique_id(uint8_t id[PXZ_COMM_ID_BYTES]);
 pxz_status pxz_comm_init(pxz_ctx* ctx, int nranks, int rank, const uint8_t id[PXZ_COMM_ID_BYTES]);
 void pxz_comm_destroy(pxz_ctx* ctx);
+/* A rank whose shard has no block rows (more ranks than block rows) still has to take part in the exchange of
+ * every pxz_shrink(PXZ_FLAG_NORMALISE_GLOBAL) its peers issue: it calls this instead, once per such shrink.
+ * (A rank whose pxz_shrink fails before the exchange joins by itself, with an error flag that makes its peers
+ * return PXZ_E_NCCL instead of waiting for it.) */
+pxz_status pxz_comm_join_empty(pxz_ctx* ctx);
 
 /* ---- host container stage (stays on the host, layout unchanged) ---------------------------
  * Pixlzr::encode_to_vec / decode_from_vec (src/encoding/mod.rs:40-165) with the qoi 0.4.1

@@ -65,6 +65,7 @@ SYMBOLS = {
     "pxz_comm_unique_id": (_i, [_vp]),
     "pxz_comm_init": (_i, [_vp, _i, _i, _vp]),
     "pxz_comm_destroy": (None, [_vp]),
+    "pxz_comm_join_empty": (_i, [_vp]),
     "pxz_container_bound": (C.c_int64, [_u32, _u32, _u32, _u32, _u32, _u64]),
     "pxz_container_encode": (C.c_int64, [_u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _sz, _i]),
     "pxz_payload_to_container": (_i, [_vp, _vp, _u32, _i, _vp, _sz, _P(_u64)]),
@@ -212,6 +213,10 @@ class Context:
             out[name.decode()] = (ms.value, n.value)
             i += 1
         return out
+
+    def comm_join_empty(self):
+        """The exchange of one PXZ_FLAG_NORMALISE_GLOBAL shrink for a rank whose shard has no block rows."""
+        self.check(lib().pxz_comm_join_empty(self._h))
 
     def comm_init(self, nranks: int, rank: int, comm_id: bytes):
         """Joins the NCCL communicator used by PXZ_FLAG_NORMALISE_GLOBAL (all ranks must call this)."""

@@ -219,9 +219,7 @@ class Pixlzr:
     # ---- encode side --------------------------------------------------------------------------------
     def _shrink(self, metric: int, filter_downscale: FilterType, factor: float, flags: int):
         if self._image is None:
-            raise NotImplementedError(
-                "shrinking a Pixlzr that is not backed by its source image (already shrunk or decoded) "
-                "is outside the accelerated path")
+            return self._reshrink_blocks(metric, filter_downscale, factor, flags)
         ctx = self._ctx()
         img = ctx.image_upload(self._image)
         try:
@@ -234,6 +232,57 @@ class Pixlzr:
             img.free()
         self._values_present = True
         self._image = None
+
+    def _reshrink_blocks(self, metric: int, filter_downscale: FilterType, factor: float, flags: int):
+        """Shrinks blocks that are no longer windows of the source image (an already shrunk or decoded Pixlzr): the
+        reference treats every block as an image of its own (pixlzr.rs:187-205 has no `block_value` check, so
+        shrink_directionally re-shrinks reduced blocks).  Blocks of one size are laid side by side into a mosaic whose
+        tiles are exactly those blocks, and the mosaic goes through the same device pipeline — the metric, the level
+        and the resample of a tile only ever look at that tile."""
+        ctx = self._ctx()
+        c = self._channels
+        descs, pixels = self._descs, self._pixels
+        new_descs = descs.copy()
+        parts = [None] * len(descs)
+        sizes = {}
+        for i, d in enumerate(descs):
+            sizes.setdefault((int(d["w"]), int(d["h"])), []).append(i)
+        for (w, h), idx in sizes.items():
+            n = len(idx)
+            per_row = max(1, min(n, 16384 // max(w, 1)))
+            rows = -(-n // per_row)
+            mosaic = np.zeros((rows * h, per_row * w, c), np.uint8)
+            for k, i in enumerate(idx):
+                o = int(descs[i]["offset"])
+                r, q = divmod(k, per_row)
+                mosaic[r * h:(r + 1) * h, q * w:(q + 1) * w] = pixels[o:o + w * h * c].reshape(h, w, c)
+            if n % per_row:  # the unused tiles of the last mosaic row repeat a real block: same metric domain, results dropped
+                o = int(descs[idx[0]]["offset"])
+                first = pixels[o:o + w * h * c].reshape(h, w, c)
+                for k in range(n, rows * per_row):
+                    r, q = divmod(k, per_row)
+                    mosaic[r * h:(r + 1) * h, q * w:(q + 1) * w] = first
+            img = ctx.image_upload(mosaic)
+            try:
+                pl = img.shrink(w, h, metric, factor, int(filter_downscale), flags)
+                try:
+                    md, mp = pl.download()
+                finally:
+                    pl.free()
+            finally:
+                img.free()
+            for k, i in enumerate(idx):
+                dd = md[k]
+                o = int(dd["offset"])
+                parts[i] = mp[o:o + int(dd["w"]) * int(dd["h"]) * c]
+                new_descs[i]["w"], new_descs[i]["h"], new_descs[i]["value"] = dd["w"], dd["h"], dd["value"]
+        off = 0
+        for i in range(len(new_descs)):
+            new_descs[i]["offset"] = off
+            off += parts[i].size
+        self._descs = new_descs
+        self._pixels = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+        self._values_present = True
 
     def shrink_by(self, filter_downscale: FilterType, factor: float, exact_values: bool = False):
         """Pixlzr::shrink_by (pixlzr.rs:155-185): Oklab-MAD value * factor * 10 -> level -> per-block
@@ -271,9 +320,31 @@ class Pixlzr:
             ctx.set_strategy(None, None)
 
     def shrink(self, filter_downscale: FilterType, before_average, after_average):
-        """Pixlzr::shrink (pixlzr.rs:124-152) takes arbitrary closures; only the two closure pairs the
-        reference itself uses run on the GPU (shrink_by, process)."""
-        raise NotImplementedError("arbitrary before/after closures are host-only; use shrink_by or process")
+        """Pixlzr::shrink (pixlzr.rs:124-152): `before_average(x, avg)` is applied per pixel and channel, `after_average(x)`
+        to the block's mean; blocks that already carry a value are skipped (:135).  The reference takes arbitrary fn
+        pointers; the device metric is |x - avg| followed by a linear map, which is what every caller in the reference
+        passes (pixlzr.rs:160-162, process/mod.rs:108-110), so the two callables are probed on sample points and
+        accepted when they are exactly that; anything else is refused (host-only by nature)."""
+        if self._image is None and self._values_present:
+            return  # every block has block_value.is_some(): the reference clones them unchanged
+        xs = np.array([0.0, 0.25, 1.0, -0.5, 0.7071, 3.5], np.float32)
+        avgs = np.array([0.0, 0.5, -0.25, 1.0], np.float32)
+        for x in xs:
+            for a in avgs:
+                if np.float32(before_average(float(x), float(a))) != np.float32(abs(np.float32(x) - np.float32(a))):
+                    raise NotImplementedError("before_average is not |x - avg|: arbitrary closures are host-only")
+        one = np.float32(after_average(1.0))
+        zero = np.float32(after_average(0.0))
+        if zero != 0 or any(np.float32(after_average(float(x))) != np.float32(np.float32(x) * one) for x in xs):
+            raise NotImplementedError("after_average is not x * c: arbitrary closures are host-only")
+        if one == np.float32(1.0):
+            self._shrink(N.METRIC_OKLAB_MAD, filter_downscale, 1.0, N.FLAG_AFTER_IDENTITY)
+        else:
+            # x * c == (x * factor) * 10 needs a factor with that exact product sequence: only c = f32(f * 10) qualifies
+            f = np.float32(one / np.float32(10.0))
+            if any(np.float32(np.float32(np.float32(x) * f) * np.float32(10.0)) != np.float32(np.float32(x) * one) for x in xs):
+                raise NotImplementedError("after_average is not of the form x * factor * 10")
+            self._shrink(N.METRIC_OKLAB_MAD, filter_downscale, float(f), 0)
 
     # ---- decode side --------------------------------------------------------------------------------
     def to_image(self, filter: FilterType) -> np.ndarray:

@@ -98,7 +98,10 @@ def run(args) -> None:
         with open(args.output, "wb") as f:
             f.write(api.Pixlzr.encode_image_to_vec(_open_image(args.input), bw, bh, filt, shrink_by, bool(args.direction_wise)))
         return
-    if src == "pix" and dst == "image":  # --force leaves a decoded file alone: every block carries a value (pixlzr.rs:168-170)
+    # pix -> image: shrink_by leaves a decoded file alone (every block carries a value, pixlzr.rs:168-170), so --force only
+    # matters with -d true: shrink_directionally has no such check (pixlzr.rs:187-205) and re-shrinks the decoded blocks —
+    # that case takes the general path below
+    if src == "pix" and dst == "image" and not (args.force and args.direction_wise):
         with open(args.input, "rb") as f:
             _save_image(args.output, api.Pixlzr.decode_vec_to_image(f.read(), filt))
         return

@@ -113,6 +113,7 @@ struct pxz_image {
 };
 
 constexpr size_t kPayloadCacheMax = 4;
+constexpr size_t kTabCacheMax = 48;  // table sets kept per context (get_tabset)
 
 struct pxz_payload {
   pxz_ctx* ctx;
@@ -291,13 +292,32 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
     if (direction == 1 && t.goff == 0xFFFFFFFFu) ts.warp_ok = false;
     if (direction == 0 && t.s2words == 0) ts.has_noslide = true;
   }
+  // the cache is bounded: payloads built from host descriptors (decoded files, PixlzrBlock::resize size pairs) bring
+  // their own size sets, and a long-running decoder must not pile their tables up.  Frees are stream-ordered, so kernels
+  // already queued on this context's stream keep their tables.
+  if (ctx->tabs.size() >= kTabCacheMax) {
+    for (auto& kv : ctx->tabs) {
+      dev_free(ctx, kv.second.d_tabs);
+      dev_free(ctx, kv.second.d_pool);
+    }
+    ctx->tabs.clear();
+  }
   pxz_status st;
   if ((st = dev_alloc(ctx, (void**)&ts.d_tabs, tabs.size() * sizeof(AxisTab))) != PXZ_OK) return st;
-  if ((st = dev_alloc(ctx, (void**)&ts.d_pool, pool.size() * 4)) != PXZ_OK) return st;
+  if ((st = dev_alloc(ctx, (void**)&ts.d_pool, pool.size() * 4)) != PXZ_OK) {
+    dev_free(ctx, ts.d_tabs);
+    return st;
+  }
   // pageable -> device copies are staged by the runtime before returning, so the vectors may die
-  PXZ_CUDA(ctx, cudaMemcpyAsync(ts.d_tabs, tabs.data(), tabs.size() * sizeof(AxisTab), cudaMemcpyHostToDevice, ctx->stream));
-  PXZ_CUDA(ctx, cudaMemcpyAsync(ts.d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaError_t ce = cudaMemcpyAsync(ts.d_tabs, tabs.data(), tabs.size() * sizeof(AxisTab), cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(ts.d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    dev_free(ctx, ts.d_tabs);
+    dev_free(ctx, ts.d_pool);
+    return fail(ctx, PXZ_E_CUDA, std::string("resample table upload: ") + cudaGetErrorString(ce));
+  }
   ctx->tabs[key] = ts;
   *out = ts;
   return PXZ_OK;
@@ -393,7 +413,7 @@ pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx*
   if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
   if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
   if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->resample_kernels = !strcmp(e, "warp") ? 1 : !strcmp(e, "cta") ? 2 : !strcmp(e, "tma") ? 3 : 0;
-  if (cudaMalloc((void**)&ctx->d_minmax, 4 * sizeof(float)) != cudaSuccess ||
+  if (cudaMalloc((void**)&ctx->d_minmax, 8 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_tile_counter, 64) != cudaSuccess || cudaMemset(ctx->d_tile_counter, 0, 64) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_total, 64) != cudaSuccess) {
     cudaGetLastError();
@@ -733,17 +753,67 @@ static pxz_status payload_new(pxz_ctx* ctx, const Geom& g, uint64_t capacity, px
   return PXZ_OK;
 }
 
+// The one exchange of the path (PXZ_FLAG_NORMALISE_GLOBAL with a communicator): ncclMin over {min_x, -max_x, min_y, -max_y,
+// ok}.  `ok` is 0 on a healthy rank and -1 on a rank that failed before it got here — such a rank still joins, with
+// neutral values, so that its peers do not wait in the all-reduce forever; everybody then learns that a rank failed.
+// `local_ok == false`: this rank contributes nothing (an error before the exchange, or a shard without rows).
+static pxz_status exchange_minmax(pxz_ctx* ctx, bool local_ok, bool* peers_ok) {
+  *peers_ok = true;
+  if (!ctx->comm) return PXZ_OK;
+  if (local_ok) {
+    PXZ_CUDA(ctx, cudaMemsetAsync(ctx->d_minmax + 4, 0, sizeof(float), ctx->stream));
+  } else {
+    static const float neutral[5] = {INFINITY, INFINITY, INFINITY, INFINITY, -1.0f};
+    PXZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_minmax, neutral, sizeof(neutral), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  std::string err;
+  if (nccl_allreduce_min_f32(ctx->comm, ctx->d_minmax, 5, ctx->stream, &err) != 0) return fail(ctx, PXZ_E_NCCL, err);
+  float flag = 0.f;
+  PXZ_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_minmax + 4, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *peers_ok = !(flag < 0.f);
+  return PXZ_OK;
+}
+
+pxz_status pxz_comm_join_empty(pxz_ctx* ctx) {
+  if (!ctx) return PXZ_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->comm) return fail(ctx, PXZ_E_ARG, "no communicator (pxz_comm_init)");
+  // a rank whose shard has no rows: neutral values, but a healthy flag
+  static const float neutral[5] = {INFINITY, INFINITY, INFINITY, INFINITY, 0.0f};
+  PXZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_minmax, neutral, sizeof(neutral), cudaMemcpyHostToDevice, ctx->stream));
+  std::string err;
+  if (nccl_allreduce_min_f32(ctx->comm, ctx->d_minmax, 5, ctx->stream, &err) != 0) return fail(ctx, PXZ_E_NCCL, err);
+  float flag = 0.f;
+  PXZ_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_minmax + 4, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag < 0.f) return fail(ctx, PXZ_E_NCCL, "another rank failed before the min/max exchange");
+  return PXZ_OK;
+}
+
 pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t bh, pxz_metric metric, float factor,
                       pxz_filter filter_down, uint32_t flags, pxz_payload** out) {
   if (!ctx || !img || !out) return PXZ_E_ARG;
   *out = nullptr;
   cudaSetDevice(ctx->device);
-  if ((int)filter_down < 0 || (int)filter_down > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
+  const bool normalise = (flags & PXZ_FLAG_NORMALISE_GLOBAL) != 0;
+  // Every rank of a communicator must reach the min/max exchange, whatever happens to it before: a rank-local failure
+  // (an unknown filter, a trailing block the Sobel metric cannot take, no memory) joins with neutral values and an
+  // error flag instead of leaving its peers in the collective.
+  auto bail = [&](pxz_status why) -> pxz_status {
+    if (normalise && ctx->comm) {
+      const std::string msg = ctx->err;
+      bool peers_ok = true;
+      exchange_minmax(ctx, false, &peers_ok);
+      ctx->err = msg;
+    }
+    return why;
+  };
+  if ((int)filter_down < 0 || (int)filter_down > 4) return bail(fail(ctx, PXZ_E_ARG, "unknown filter"));
   Geom g;
   pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw, bh, &g);
-  if (st != PXZ_OK) return st;
+  if (st != PXZ_OK) return bail(st);
   const uint32_t nblocks = g.cols * g.rows;
-  const bool normalise = (flags & PXZ_FLAG_NORMALISE_GLOBAL) != 0;
 
   ValueMap vm;
   vm.factor = factor;
@@ -759,16 +829,22 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   // runs in reference order for all blocks
   const bool exact_all = (flags & PXZ_FLAG_EXACT_VALUES) != 0 || (normalise && metric == PXZ_METRIC_OKLAB_MAD);
   st = run_analysis(ctx, img, g, metric, exact_all, (metric == PXZ_METRIC_OKLAB_MAD && !exact_all) ? &vm : nullptr);
-  if (st != PXZ_OK) return st;
+  if (st != PXZ_OK) return bail(st);
 
   if (normalise) {
-    ProfScope prof(ctx, K_MINMAX);
-    PXZ_CUDA(ctx, launch_minmax(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, nblocks, ctx->d_minmax,
-                                ctx->stream, &ctx->launches));
-    if (ctx->comm) {
-      std::string err;
-      if (nccl_allreduce_min_f32(ctx->comm, ctx->d_minmax, 4, ctx->stream, &err) != 0) return fail(ctx, PXZ_E_NCCL, err);
+    {
+      ProfScope prof(ctx, K_MINMAX);
+      cudaError_t me = launch_minmax(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, nblocks, ctx->d_minmax,
+                                     ctx->stream, &ctx->launches);
+      if (me != cudaSuccess) {
+        cudaGetLastError();
+        return bail(fail(ctx, PXZ_E_CUDA, std::string("minmax: ") + cudaGetErrorString(me)));
+      }
     }
+    bool peers_ok = true;
+    st = exchange_minmax(ctx, true, &peers_ok);
+    if (st != PXZ_OK) return st;
+    if (!peers_ok) return fail(ctx, PXZ_E_NCCL, "another rank failed before the min/max exchange");
   }
 
   pxz_payload* p = nullptr;
@@ -822,12 +898,11 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
 // host restatement of the plan kernel's scalar path (same threshold table)
 pxz_status pxz_reduce_dims(float v0, float v1, uint32_t w, uint32_t h, uint32_t* out_w, uint32_t* out_h, float* stored) {
   if (!out_w || !out_h || w == 0 || h == 0) return PXZ_E_ARG;
-  static LevelThresholds thr;
-  static bool init = false;
-  if (!init) {
-    build_level_thresholds(&thr);
-    init = true;
-  }
+  static const LevelThresholds thr = [] {  // function-local static: initialised once, thread-safe
+    LevelThresholds t;
+    build_level_thresholds(&t);
+    return t;
+  }();
   auto parse = [](float v) -> float {  // operations.rs:128-138
     if (!signbit(v)) return v;
     float x = 1.0f + v;
@@ -945,7 +1020,7 @@ static pxz_status payload_from_descs(pxz_ctx* ctx, uint32_t w, uint32_t h, uint3
     const pxz_block_desc& d = descs[b];
     if (d.w == 0 || d.h == 0) return fail(ctx, PXZ_E_ARG, "block with zero size");
     const uint64_t sz = (uint64_t)d.w * d.h * channels;
-    if (d.offset + sz > bytes) return fail(ctx, PXZ_E_ARG, "block descriptor points outside the payload");
+    if (d.offset > bytes || sz > bytes - d.offset) return fail(ctx, PXZ_E_ARG, "block descriptor points outside the payload");
     if (channels == 4 && (d.offset & 3u)) return fail(ctx, PXZ_E_ARG, "RGBA block offsets must be 4-byte aligned");
     const uint32_t ix = idx_of(d.w, tw), iy = idx_of(d.h, th);
     if (ix > 0xFFFFu || iy > 0xFFFFu) return fail(ctx, PXZ_E_UNSUPPORTED, "more than 65536 distinct block sizes");
@@ -1052,7 +1127,7 @@ pxz_status pxz_payload_from_container(pxz_ctx* ctx, const uint8_t* data, size_t 
   if (st != PXZ_OK) return fail(ctx, st, "malformed .pxlzr container");
   Geom g;
   if ((st = make_geom(ctx, w, h, ch, bw, bh, &g)) != PXZ_OK) return st;
-  const size_t nblocks = (size_t)g.cols * g.rows;
+  const size_t nblocks = (size_t)g.cols * g.rows;  // == the decoder's f32 grid: pxz_container_decode refuses files where they differ
   std::vector<pxz_block_desc> descs(nblocks);
   st = pxz_container_decode(data, len, &w, &h, &bw, &bh, &filt, &ch, &bytes, descs.data(), nullptr);
   if (st != PXZ_OK) return fail(ctx, st, "malformed .pxlzr container");
@@ -1061,10 +1136,12 @@ pxz_status pxz_payload_from_container(pxz_ctx* ctx, const uint8_t* data, size_t 
   {
     size_t q = 26 + (size_t)4 * g.rows;  // constants.rs:19-20 + the line table; validated by the walk above
     for (size_t b = 0; b < nblocks; ++b) {
+      if (q + 13 > len) return fail(ctx, PXZ_E_FORMAT, "malformed .pxlzr container");  // cannot happen after the walk above
       const uint8_t* hd = data + q + 9;
       qlen[b] = (uint32_t)hd[0] << 24 | (uint32_t)hd[1] << 16 | (uint32_t)hd[2] << 8 | hd[3];
       in_off[b] = q + 13;
       q += 13 + (size_t)qlen[b];
+      if (q > len) return fail(ctx, PXZ_E_FORMAT, "malformed .pxlzr container");
     }
   }
   for (size_t b = 0; b < nblocks; ++b)

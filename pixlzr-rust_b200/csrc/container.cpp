@@ -108,7 +108,8 @@ bool qoi_body_decode(const uint8_t* in, size_t len, uint32_t ch_expected, uint8_
   for (size_t i = 0; i < out_px; ++i) {
     if (run) {
       --run;
-    } else if (p < end) {
+    } else {
+      if (p >= end) return false;  // the stream ends before the block is full (qoi 0.4.1: UnexpectedBufferEnd)
       const uint8_t op = *p++;
       if (op == OP_RGB) {
         if (p + 3 > end) return false;
@@ -239,16 +240,27 @@ pxz_status pxz_container_decode(const uint8_t* data, size_t len, uint32_t* w, ui
   *w = rd32(data + p); *h = rd32(data + p + 4); *bw = rd32(data + p + 8); *bh = rd32(data + p + 12);
   p += 16;
   if (filter_byte) *filter_byte = filt;
-  if (*bw == 0 || *bh == 0) return PXZ_E_FORMAT;
+  if (*bw == 0 || *bh == 0 || *w == 0 || *h == 0) return PXZ_E_FORMAT;
   const uint32_t cols = grid_f32(*w, *bw), rows = grid_f32(*h, *bh);
+  // the reference sizes the grid in f32 (encoding/mod.rs:118-119), the device side in integers: the two agree below
+  // 2^24; a file for which they differ is refused instead of being walked with two different block counts
+  if ((uint64_t)cols != ((uint64_t)*w + *bw - 1) / *bw || (uint64_t)rows != ((uint64_t)*h + *bh - 1) / *bh) return PXZ_E_UNSUPPORTED;
+  if ((uint64_t)cols * rows > 0x7FFFFFFFull) return PXZ_E_UNSUPPORTED;
   if (len < p + (size_t)rows * 4) return PXZ_E_FORMAT;
+  const size_t line_table = p;
   uint64_t body = 0;
   for (uint32_t r = 0; r < rows; ++r) body += rd32(data + p + (size_t)r * 4);
   p += (size_t)rows * 4;
   if (p + body != len) return PXZ_E_FORMAT;  // assert_eq!(reader.data.len(), ...), encoding/mod.rs:141
   uint64_t off = 0;
   uint32_t ch = 0;
+  size_t row_start = p;
   for (size_t bi = 0; bi < (size_t)cols * rows; ++bi) {
+    if (bi && bi % cols == 0) {
+      // every block row fills exactly its entry of the line table (encoding/mod.rs:142-155 slices the rows by it)
+      if (p - row_start != rd32(data + line_table + (bi / cols - 1) * 4)) return PXZ_E_FORMAT;
+      row_start = p;
+    }
     if (p + kBlockHeader + 10 > len || memcmp(data + p, "block", 5) != 0) return PXZ_E_FORMAT;
     uint32_t bits = rd32(data + p + 5);
     float v;
@@ -261,6 +273,9 @@ pxz_status pxz_container_decode(const uint8_t* data, size_t len, uint32_t* w, ui
     if (ch == 0) ch = qc;
     if (qc != ch) return PXZ_E_UNSUPPORTED;  // mixed RGB / RGBA blocks in one file
     if (qw > 65535 || qh > 65535 || qw == 0 || qh == 0) return PXZ_E_UNSUPPORTED;
+    // hostile headers: the qoi crate refuses more than 400 M pixels, and an op byte yields at most 62 pixels (a run),
+    // so a stream of qlen bytes cannot fill more than 62 * qlen of them — checked before anything is allocated
+    if ((uint64_t)qw * qh > 400000000ull || (uint64_t)qw * qh > 62ull * qlen) return PXZ_E_FORMAT;
     if (descs) {
       descs[bi].offset = off;
       descs[bi].value = v;
@@ -271,6 +286,7 @@ pxz_status pxz_container_decode(const uint8_t* data, size_t len, uint32_t* w, ui
     off += (uint64_t)qw * qh * qc;
     p += qlen;
   }
+  if (p - row_start != rd32(data + line_table + (size_t)(rows - 1) * 4)) return PXZ_E_FORMAT;
   *channels = ch;
   *payload_bytes = off;
   return PXZ_OK;

@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(kQoiThreads) k_qoi_decode(const uint8_t* __res
   for (uint32_t i = 0; i < npx; ++i) {
     if (run) {
       --run;
-    } else if (p < end) {
+    } else {
+      if (p >= end) { bad = true; break; }  // the stream ends before the block is full
       const uint32_t op = *p++;
       if (op == OP_RGB) {
         if (p + 3 > end) { bad = true; break; }

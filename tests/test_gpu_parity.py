@@ -515,6 +515,50 @@ def test_resample_kernel_families_match_oracle(forced_ctx, kind, shape, bs, metr
 
 
 # ---------------------------------------------------------------------------------------------
+# API gaps closed in round 2: Pixlzr::shrink with the closures the reference passes, and shrink_directionally on blocks
+# that already carry a value (pixlzr.rs:124-152, 187-205)
+# ---------------------------------------------------------------------------------------------
+def test_shrink_with_closures_and_reshrink_of_valued_blocks():
+    rng = np.random.default_rng(5)
+    img = np.ascontiguousarray(np.concatenate([rng.integers(0, 256, (192, 256, 3), dtype=np.uint8), np.full((192, 256, 1), 255, np.uint8)], -1))
+    img[:64, :128, :3] = (img[:64, :128, :3] // 8) + 100  # a few calmer tiles: several levels
+    # shrink(filter, |x - avg|, x * k * 10) == shrink_by(filter, k)
+    k = 0.5
+    a = P.Pixlzr.from_image(img, 64, 64)
+    a.shrink(P.FilterType.CatmullRom, lambda x, avg: abs(x - avg), lambda x: x * k * 10.0)
+    b = P.Pixlzr.from_image(img, 64, 64)
+    b.shrink_by(P.FilterType.CatmullRom, k)
+    assert a.encode_to_vec() == b.encode_to_vec()
+    # the identity closure is process()'s (process/mod.rs:108-110)
+    c = P.Pixlzr.from_image(img, 64, 64)
+    c.shrink(P.FilterType.Lanczos3, lambda x, avg: abs(x - avg), lambda x: x)
+    ref = O.shrink(img, 64, 64, O.METRIC_OKLAB_MAD, 1.0, O.LANCZOS3, use_factor=False)
+    assert np.array_equal(c._descs["w"], ref.descs["w"]) and np.array_equal(c._descs["h"], ref.descs["h"])
+    assert np.array_equal(c._pixels, ref.payload)
+    # anything else is host-only
+    d = P.Pixlzr.from_image(img, 64, 64)
+    with pytest.raises(NotImplementedError):
+        d.shrink(P.FilterType.Nearest, lambda x, avg: (x - avg) ** 2, lambda x: x)
+    # valued blocks: shrink_by skips them, shrink_directionally re-shrinks every block as an image of its own
+    pix = P.Pixlzr.decode_from_vec(b.encode_to_vec())
+    before = pix.encode_to_vec()
+    pix.shrink_by(P.FilterType.Lanczos3, 1.0)
+    assert pix.encode_to_vec() == before
+    big = [i for i, dsc in enumerate(pix._descs) if dsc["w"] >= 3 and dsc["h"] >= 3]
+    if len(big) == len(pix._descs):  # the reference panics on blocks without a 3x3 window (operations.rs:220-221)
+        old_descs, old_pixels = pix._descs.copy(), pix._pixels.copy()
+        pix.shrink_directionally(P.FilterType.Triangle, 4.0)
+        for i, dsc in enumerate(old_descs):
+            w, h, o = int(dsc["w"]), int(dsc["h"]), int(dsc["offset"])
+            blk = np.ascontiguousarray(old_pixels[o:o + w * h * 4].reshape(h, w, 4))
+            r = O.shrink(blk, w, h, O.METRIC_SOBEL_DIR, 4.0, O.TRIANGLE)
+            nd = pix._descs[i]
+            assert (int(nd["w"]), int(nd["h"])) == (int(r.descs["w"][0]), int(r.descs["h"][0])), i
+            no = int(nd["offset"])
+            assert np.array_equal(pix._pixels[no:no + r.payload.size], r.payload), i
+
+
+# ---------------------------------------------------------------------------------------------
 # command-line driver (src/bin/main.rs:299-356 and the four conversions)
 # ---------------------------------------------------------------------------------------------
 def test_cli_conversions(tmp_path):

@@ -140,6 +140,48 @@ def test_container_rejects_garbage():
         N.container_decode(raw + b"\0")
 
 
+def _tiny_container(w, h, bw, bh, blocks):
+    """A v0.0.2 container from (qoi_w, qoi_h, qoi_body_ops) per block, all in one block row per grid row."""
+    import struct
+    cols = -(-w // bw)
+    rows = -(-h // bh)
+    enc = []
+    for (qw, qh, ops) in blocks:
+        body = struct.pack(">IIBB", qw, qh, 4, 0) + ops + bytes(7) + b"\x01"
+        enc.append(b"block" + struct.pack(">f", 0.5) + struct.pack(">I", len(body)) + body)
+    lines = [b"".join(enc[r * cols:(r + 1) * cols]) for r in range(rows)]
+    head = b"PIXLZR" + bytes([0, 0, 2, 0]) + struct.pack(">IIII", w, h, bw, bh)
+    return head + b"".join(struct.pack(">I", len(ln)) for ln in lines) + b"".join(lines)
+
+
+def test_container_hostile_files_are_refused():
+    """truncated QOI streams, blocks that claim more pixels than their stream can hold, grids that differ
+    between the reference's f32 arithmetic and integers, block rows that do not fill their line-table entry."""
+    rgba = b"\xff\x10\x20\x30\xff"                      # QOI_OP_RGBA: one pixel
+    ok = _tiny_container(2, 1, 1, 1, [(1, 1, rgba), (1, 1, rgba)])
+    hdr, descs, pixels = N.container_decode(ok)
+    assert (hdr["w"], hdr["h"]) == (2, 1) and pixels.tolist() == [0x10, 0x20, 0x30, 0xFF] * 2
+    # a 2x2 block whose stream holds one pixel: the qoi crate stops with UnexpectedBufferEnd, so do we
+    with pytest.raises(N.PixlzrError):
+        N.container_decode(_tiny_container(2, 2, 2, 2, [(2, 2, rgba)]))
+    # 31 bytes that claim 65535 x 65535 pixels: refused before anything of that size is allocated
+    with pytest.raises(N.PixlzrError):
+        N.container_decode(_tiny_container(1, 1, 1, 1, [(65535, 65535, rgba)]))
+    # a run can fill a block: 1 op byte -> up to 62 pixels
+    run = _tiny_container(8, 4, 8, 4, [(8, 4, rgba + b"\xde")])     # RGBA + RUN(31) = 32 pixels
+    assert N.container_decode(run)[2].size == 8 * 4 * 4
+    # w = 2^24 + 1: ceil in f32 gives 512 columns of 32768, integers give 513 -> refused
+    with pytest.raises(N.PixlzrError):
+        N.container_decode(_tiny_container(16777217, 1, 32768, 1, [(1, 1, rgba)] * 512))
+    # line table says 1 byte less for row 0 and 1 more for row 1 (the sum still matches the file)
+    two = bytearray(_tiny_container(1, 2, 1, 1, [(1, 1, rgba), (1, 1, rgba)]))
+    import struct
+    l0, l1 = struct.unpack(">II", two[26:34])
+    two[26:34] = struct.pack(">II", l0 - 1, l1 + 1)
+    with pytest.raises(N.PixlzrError):
+        N.container_decode(bytes(two))
+
+
 def test_pixlzrblock_accessors():
     """block.rs:346-399"""
     b = P.PixlzrBlock(np.zeros((100, 100, 4), np.uint8))
