@@ -5,13 +5,22 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[2], "C3"): synthetic 7680x4320 RGBA8 images, 64x64 blocks, metric
+Headline workload (BASELINE.json configs[2], "C3"): synthetic 7680x4320 RGBA8 frames, 64x64 blocks, metric
 Oklab-MAD with k = 1, Lanczos3 down / Lanczos3 up (the reference CLI's defaults, src/bin/main.rs:19,27-36).
-One step = encode (analyse -> plan -> shrink into the packed payload) + decode (expand + paste) of a batch
-of `--batch` distinct images per rank; images are independent, so ranks share nothing (weak scaling) and
-no collective sits on the data path.  `value` is timed with CUDA events on the launching stream with
-every input already resident in HBM; `e2e` runs the same work through the C ABI with pinned HOST
-buffers, host<->device copies inside the timed region.  Prints ONE JSON line on rank 0.
+One step = encode (analyse -> plan -> shrink into the packed payload) + decode (expand + paste) of `--batch`
+frames per rank (`--distinct` different ones, taken in turn: 531 MB of input, larger than L2); frames are
+independent, so ranks share nothing (weak scaling) and no collective sits on the data path.  `value` is timed
+with CUDA events on the launching stream with every input already resident in HBM; `e2e` runs the same work
+through the C ABI with pinned HOST buffers, host<->device copies inside the timed region.
+
+The same line carries the two sharded configurations of BASELINE.json, measured on the same N ranks:
+  "sharded": C4, one 65536 x 65536 frame (generated on the device) cut into block-row shards, once with the
+             global-normalisation extension (the library's NCCL min/max all-reduce is the only exchange) and once
+             in the default mode; a checksum of descriptors and payload that must not depend on N;
+  "batch":   C5, 4096 frames of 1920x1080 dealt round-robin, through the batch entry points of the C ABI
+             (pxz_shrink_batch / pxz_expand_batch: one launch per stage over a stack of frames);
+and, at N >= 2, "nccl_parity": the sharded result of a small frame equals the single-GPU result, including ranks
+without rows and a rank that fails before the exchange.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -35,7 +44,7 @@ FILTER_DOWN = 4  # Lanczos3
 FILTER_UP = 4
 FACTOR = 1.0
 IMG_W, IMG_H = 7680, 4320
-CPU_SAMPLE_ROWS = 1088  # 17 block rows of the 8K frame = 8.36 MP: the bounded CPU sample
+CPU_SAMPLE_ROWS = 1088  # 17 block rows of the 8K frame = 8.36 MP: the bounded sample of the in-run CPU baseline
 
 
 # --------------------------------------------------------------------------------------------------
@@ -56,131 +65,346 @@ def synth_image_np(seed: int, w: int, h: int) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], -1))
 
 
+def synth_rows_device(torch, y0, y1, width, seed, device, chunk=512):
+    """uint8 [y1-y0, width, 4] on the device: smooth base + per-64x64-tile noise whose amplitude is a hash of the tile
+    (independent of the sharding), alpha 255.  Used for the frames that are too large to cross PCIe (C4) or too many (C5)."""
+    out = torch.empty((y1 - y0, width, 4), dtype=torch.uint8, device=device)
+    out[..., 3] = 255
+    xx = torch.arange(width, device=device, dtype=torch.float32)
+    tx = (torch.arange(width, device=device) // 64).to(torch.int64)
+    amps = torch.tensor([0, 1, 2, 4, 8, 16, 32, 64], device=device, dtype=torch.float32)
+    for g0 in range((y0 // chunk) * chunk, y1, chunk):  # chunks are aligned globally: the pixels do not depend on the sharding
+        yy = torch.arange(g0, g0 + chunk, device=device, dtype=torch.float32)[:, None]
+        ty = (torch.arange(g0, g0 + chunk, device=device) // 64).to(torch.int64)[:, None]
+        h = (ty * 73856093 + tx[None, :] * 19349663 + seed * 83492791) & 0x7FFFFFFF
+        amp = amps[(h >> 7) % 8]
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1000003 + g0)
+        a, b = max(y0, g0), min(y1, g0 + chunk)
+        for ch, base in enumerate((128 + 96 * torch.sin(xx[None, :] / 9700.0 + seed), 128 + 96 * torch.cos(yy / 13100.0),
+                                   128 + 64 * torch.sin((xx[None, :] + yy) / 6100.0))):
+            noise = (torch.rand((chunk, width), device=device, generator=g) - 0.5) * 2 * amp
+            full = torch.clamp(torch.round(base + noise), 0, 255).to(torch.uint8)
+            out[a - y0:b - y0, :, ch] = full[a - g0:b - g0]
+    return out
+
+
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons of one GPU while the timed region runs."""
+    """SM clock and throttle reasons of one GPU while the timed region runs: NVML polled in-process from one thread
+    (no child processes next to the timed region); falls back to one nvidia-smi query before and after."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index: int, period_s: float = 0.01):
+        self.gpu, self.period, self.samples, self.stop_flag = gpu_index, period_s, [], threading.Event()
+        self.nv = self.handle = self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.time(), float(mhz), [n for n, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            self.samples.append((time.time(), float(o[0]), [n for n, v in zip(self.NAMES, o[2:6]) if v.strip().lower().startswith("active")]))
+            self.smax = float(o[1])
+        except Exception:
+            pass
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
-
-    def wait_first(self, timeout: float = 3.0):
-        """nvidia-smi needs a few hundred ms before its first line: do not start the timed region before it polls."""
-        t = time.time()
-        while self.proc is not None and not self.lines and time.time() - t < timeout:
-            time.sleep(0.01)
-
-    def samples_since(self, t0: float) -> int:
-        return sum(1 for (t, _) in self.lines if t >= t0)
+        else:
+            self._smi_once()
 
     def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [ln for (t, ln) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [ln for _, ln in self.lines]
-        for ln in rows:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
+        smax = None
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
             try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-            except ValueError:
-                continue
-            for name, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                smax = float(self.nv.nvmlDeviceGetMaxClockInfo(self.handle, self.nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
+        else:
+            self._smi_once()
+            smax = getattr(self, "smax", None)
+        rows = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        reasons = sorted({r for _, _, rs in rows for r in rs})
+        return {"sm_mhz": float(np.median([m for _, m, _ in rows])) if rows else None, "sm_max_mhz": smax, "reasons": reasons,
+                "samples": len(rows), "source": "NVML, in-process, every 10 ms inside the timed region" if self.nv is not None else
+                "nvidia-smi before and after the timed region (NVML unavailable)"}
 
 
 # --------------------------------------------------------------------------------------------------
 # CPU legs (oracle = C++ port of the reference; the Rust reference itself cannot be built here)
 # --------------------------------------------------------------------------------------------------
-def cpu_encode_decode(O, sample: np.ndarray, threads: int) -> float:
+def cpu_encode_decode(O, sample: np.ndarray, threads: int):
     t0 = time.perf_counter()
     s = O.shrink(sample, BS, BS, O.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, nthreads=threads)
-    O.expand(s, FILTER_UP, nthreads=threads)
-    return time.perf_counter() - t0
+    out = O.expand(s, FILTER_UP, nthreads=threads)
+    return time.perf_counter() - t0, s, out
 
 
-def cpu_baseline(sample: np.ndarray) -> dict:
+def cpu_baseline(sample: np.ndarray):
     import oracle as O
 
     cores = os.cpu_count() or 1
     mp = sample.shape[0] * sample.shape[1] / 1e6
     cpu_encode_decode(O, sample, cores)  # warm-up (thread pool, page faults)
-    best_all = min(cpu_encode_decode(O, sample, cores) for _ in range(5))
-    best_one = min(cpu_encode_decode(O, sample, 1) for _ in range(2))
-    return {"value": mp / best_all, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"top {sample.shape[0]} rows ({mp:.2f} MP) of image 0 of the same workload, best of 5",
+    runs = [cpu_encode_decode(O, sample, cores) for _ in range(5)]
+    best_all = min(r[0] for r in runs)
+    best_one = min(cpu_encode_decode(O, sample, 1)[0] for _ in range(2))
+    info = {"value": mp / best_all, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"top {sample.shape[0]} rows ({mp:.2f} MP) of frame 0 of the same workload, best of 5",
             "one_thread_value": mp / best_one,
             "note": "shrink* is a serial loop in the reference (pixlzr.rs:163-184); the all-core figure is charitable"}
+    return info, runs[-1][1], runs[-1][2]
+
+
+def workload_config(args) -> dict:
+    return {
+        "workload": "C3 synthetic 7680x4320 RGBA8 (alpha 255), 64x64 blocks, Oklab-MAD k=1, Lanczos3 down / Lanczos3 up, "
+                    "encode (analyse+plan+shrink) + decode (expand+paste)",
+        "width": IMG_W, "height": IMG_H, "channels": 4, "block": BS, "metric": "oklab_mad", "factor": FACTOR,
+        "filter_down": "Lanczos3", "filter_up": "Lanczos3", "images_per_step_per_gpu": args.batch,
+        "distinct_images_per_gpu": min(args.distinct, args.batch),
+        "sharding": "independent images per rank, no data-path collective",
+        "cache": "inputs larger than L2 (the distinct frames of a rank are 531 MB and are taken in turn)",
+        "resize_semantics": "image_rs (the branch pinned by the reference's fixtures)",
+    }
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust crate cannot
-    be built in this image: no cargo/rustc) on the host cores, same config/metric."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust crate cannot be built in
+    this image: no cargo/rustc) on all host cores, SAME frames, same images per step."""
     if rank != 0:
         return
     import oracle as O
 
     cores = os.cpu_count() or 1
-    sample = synth_image_np(0, IMG_W, CPU_SAMPLE_ROWS)
-    mp = sample.shape[0] * sample.shape[1] / 1e6
-    for _ in range(args.warmup):
-        cpu_encode_decode(O, sample, cores)
+    distinct = min(args.distinct, args.batch)
+    frames = [synth_image_np(i, IMG_W, IMG_H) for i in range(distinct)]
+    mp_step = args.batch * IMG_W * IMG_H / 1e6
+
+    def step():
+        for i in range(args.batch):
+            cpu_encode_decode(O, frames[i % distinct], cores)
+    for _ in range(min(args.warmup, 1)):  # one full step warms the thread pool and the page cache: more would only cost minutes
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_encode_decode(O, sample, cores)
+        step()
     dt = time.perf_counter() - t0
-    val = mp * args.steps / dt
+    val = mp_step * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, sample_rows=CPU_SAMPLE_ROWS),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"each step = top {CPU_SAMPLE_ROWS} rows ({mp:.2f} MP) of one 8K frame of the workload"},
+                         "sample": f"each step = the same {args.batch} full 8K frames ({mp_step:.0f} MP) as the B200 arm; "
+                                   f"warm-up capped at one step"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, batch: int, sample_rows: int | None = None) -> dict:
-    cfg = {
-        "workload": "C3 synthetic 7680x4320 RGBA8 (alpha 255), 64x64 blocks, Oklab-MAD k=1, Lanczos3 down / Lanczos3 up, "
-                    "encode (analyse+plan+shrink) + decode (expand+paste)",
-        "width": IMG_W, "height": IMG_H, "channels": 4, "block": BS, "metric": "oklab_mad", "factor": FACTOR,
-        "filter_down": "Lanczos3", "filter_up": "Lanczos3", "images_per_step_per_gpu": batch,
-        "sharding": "independent images per rank, no data-path collective",
-        "streams_per_gpu": getattr(args, "streams", 1),
-        "cache": "inputs larger than L2 (batch x 132.7 MB per step)",
-        "resize_semantics": "image_rs (the branch pinned by the reference's fixtures)",
-    }
-    if sample_rows:
-        cfg["cpu_sample_rows"] = sample_rows
-    return cfg
+# --------------------------------------------------------------------------------------------------
+# B200 arm: helpers
+# --------------------------------------------------------------------------------------------------
+def timed_region(torch, dist, world, device, fn, reps):
+    """max over ranks of the mean device-side time of fn (barrier + synchronize on both sides, CUDA events on the
+    current stream; fn must leave every stream it uses joined into the current one)."""
+    fn()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=device, dtype=torch.float64)
+    mine = float(ms.item())
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), mine
+
+
+def run_sharded_c4(torch, dist, N, S, args, rank, world, local_rank, device):
+    """C4: one side x side frame in contiguous block-row shards; global normalisation = the only exchange."""
+    side = args.c4_side
+    ctx = N.Context(local_rank, cuda_stream=torch.cuda.current_stream(device).cuda_stream)
+    if world > 1:
+        S.init_comm(ctx, dist, rank, world, device=device)
+    y0, y1 = S.shard_pixel_rows(side, BS, world, rank)
+    src = synth_rows_device(torch, y0, y1, side, 7, device)
+    dst = torch.empty_like(src)
+    img = ctx.image_wrap(src.data_ptr(), side, y1 - y0, 4, side * 4)
+    out = ctx.image_wrap(dst.data_ptr(), side, y1 - y0, 4, side * 4)
+    res = {}
+    for name, flags in (("normalise_global", N.FLAG_NORMALISE_GLOBAL), ("default", 0)):
+        def step():
+            pl = img.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, flags)
+            pl.expand_to_image(FILTER_UP, out)
+            pl.free()
+        ms, mine = timed_region(torch, dist, world, device, step, args.extra_reps)
+        pl = img.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, flags)
+        descs, px = pl.download()
+        pl.free()
+        chk = torch.tensor([int(descs["w"].astype(np.uint64).sum() * 65537 + descs["h"].astype(np.uint64).sum()),
+                            int(px.astype(np.uint64).sum()), int(px.size)], device=device, dtype=torch.int64)
+        per_rank = torch.tensor([mine], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(chk)
+            g = [torch.zeros_like(per_rank) for _ in range(world)]
+            dist.all_gather(g, per_rank)
+            per_rank_ms = [round(float(t.item()), 3) for t in g]
+        else:
+            per_rank_ms = [round(mine, 3)]
+        res[name] = {"MPps": round(side * side / (ms / 1e3) / 1e6, 1), "ms": round(ms, 3), "ms_per_rank": per_rank_ms,
+                     "payload_fraction": round(int(chk[2]) / (side * side * 4), 4),
+                     "checksum": [int(chk[0]), int(chk[1])]}
+    res["note"] = ("normalise_global = the extension of BASELINE config 4: reference-order Oklab values for every block + one NCCL "
+                   "min all-reduce of {min, -max} per shrink (the only exchange); checksum = sum over ranks of descriptor dims and "
+                   "payload bytes: it must be the same at every N")
+    res["config"] = f"C4 synthetic {side}x{side} RGBA8 generated on the device, 64x64 blocks, contiguous block-row shards, Oklab-MAD k=1, Lanczos3 / Lanczos3, encode+decode, device-resident"
+    res["blocks"] = (side // BS) ** 2
+    del src, dst
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_batch_c5(torch, dist, N, S, args, rank, world, local_rank, device):
+    """C5: args.c5_images frames of 1920x1080 dealt round-robin; every rank runs its share in stacks of args.c5_stack frames
+    through the batch entry points."""
+    w, h = 1920, 1080
+    mine = S.round_robin(args.c5_images, world, rank)
+    stack = max(1, min(args.c5_stack, len(mine)))
+    n_stacks = -(-len(mine) // stack)
+    distinct_stacks = min(n_stacks, 2)  # two different stacks of `stack` different frames (2 x 530 MB at 64), taken in turn
+    stream0 = torch.cuda.current_stream(device)
+    streams = [stream0] + [torch.cuda.Stream(device=device) for _ in range(max(0, min(args.streams, n_stacks) - 1))]
+    ctxs = [N.Context(local_rank, cuda_stream=s.cuda_stream) for s in streams]
+    srcs = []
+    for k in range(distinct_stacks):
+        t = torch.empty((stack, h, w, 4), dtype=torch.uint8, device=device)
+        for i in range(stack):
+            t[i] = synth_rows_device(torch, 0, h, w, 100 + mine[(k * stack + i) % len(mine)], device, chunk=h)
+        srcs.append(t)
+    outs = [torch.empty((stack, h, w, 4), dtype=torch.uint8, device=device) for _ in ctxs]
+    imgs = [[c.image_wrap_batch(t.data_ptr(), w, h, 4, w * 4, stack) for t in srcs] for c in ctxs]
+    wouts = [c.image_wrap_batch(o.data_ptr(), w, h, 4, w * 4, stack) for c, o in zip(ctxs, outs)]
+
+    def step():
+        ev = torch.cuda.Event()
+        ev.record(stream0)
+        for s in streams[1:]:
+            s.wait_event(ev)
+        for n in range(n_stacks):
+            k = n % len(ctxs)
+            pl = imgs[k][n % distinct_stacks].shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+            pl.expand_to_image(FILTER_UP, wouts[k])
+            pl.free()
+        for s in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(s)
+            stream0.wait_event(e)
+    ms, me = timed_region(torch, dist, world, device, step, args.extra_reps)
+    done = n_stacks * stack * world  # frames actually processed (the last stack of a rank is run full)
+    res = {"MPps": round(done * w * h / (ms / 1e3) / 1e6, 1), "images_per_s": round(done / (ms / 1e3)), "ms_per_pass": round(ms, 3),
+           "images": done, "images_per_stack": stack, "streams_per_gpu": len(streams),
+           "config": f"C5 batch of {args.c5_images} synthetic 1920x1080 RGBA8 frames round-robin over the ranks, 64x64 blocks, Oklab-MAD k=1, "
+                     f"Lanczos3 / Lanczos3, encode+decode, device-resident, pxz_shrink_batch / pxz_expand_batch on stacks of {stack} frames"}
+    # the same frames one call per frame (what round 1 measured): shows what the batch entry points buy
+    single = [ctxs[0].image_wrap(srcs[0][i].data_ptr(), w, h, 4, w * 4) for i in range(min(stack, 16))]
+    wo = ctxs[0].image_wrap(outs[0][0].data_ptr(), w, h, 4, w * 4)
+
+    def step1():
+        for im in single:
+            pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+            pl.expand_to_image(FILTER_UP, wo)
+            pl.free()
+    ms1, _ = timed_region(torch, dist, world, device, step1, args.extra_reps)
+    res["one_call_per_image_MPps"] = round(len(single) * world * w * h / (ms1 / 1e3) / 1e6, 1)
+    del srcs, outs
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_nccl_parity(torch, dist, N, S, O_or_none, rank, world, local_rank, device):
+    """N >= 2: the sharded encode of a small frame (global normalisation through the library's NCCL exchange) equals the
+    single-GPU encode of the whole frame; ranks without rows join the exchange; a rank that fails before the exchange does
+    not leave the others waiting."""
+    res = {}
+    ctx = N.Context(local_rank, cuda_stream=torch.cuda.current_stream(device).cuda_stream)
+    S.init_comm(ctx, dist, rank, world, device=device)
+    for name, (w, h) in (("rows_ge_ranks", (328, 64 * 2 * world + 24)), ("fewer_rows_than_ranks", (328, 64 * max(1, world // 2)))):
+        img = synth_image_np(900 + h, w, h)
+        y0, y1 = S.shard_pixel_rows(h, BS, world, rank)
+        if y1 > y0:
+            d = ctx.image_upload(np.ascontiguousarray(img[y0:y1]))
+            pl = d.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, N.FLAG_NORMALISE_GLOBAL)
+            descs, px = pl.download()
+            pl.free(); d.free()
+            mine = [int(descs["w"].astype(np.uint64).sum() * 65537 + descs["h"].astype(np.uint64).sum()), int(px.astype(np.uint64).sum()), int(px.size)]
+        else:
+            ctx.comm_join_empty()
+            mine = [0, 0, 0]
+        chk = torch.tensor(mine, device=device, dtype=torch.int64)
+        dist.all_reduce(chk)
+        ok = None
+        if rank == 0:
+            solo = N.Context(local_rank)
+            d = solo.image_upload(img)
+            pl = d.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, N.FLAG_NORMALISE_GLOBAL)
+            descs, px = pl.download()
+            pl.free(); d.free()
+            want = [int(descs["w"].astype(np.uint64).sum() * 65537 + descs["h"].astype(np.uint64).sum()), int(px.astype(np.uint64).sum()), int(px.size)]
+            ok = want == [int(v) for v in chk]
+        res[name] = ok
+    # a rank-local failure before the exchange: the last rank's shard ends in a 1-row block, which the Sobel metric
+    # refuses (the reference panics there) — every rank must come back, the healthy ones with PXZ_E_NCCL
+    h = 64 * world + 1
+    img = synth_image_np(77, 328, h)
+    y0, y1 = S.shard_pixel_rows(h, BS, world, rank)
+    status = "ok"
+    try:
+        d = ctx.image_upload(np.ascontiguousarray(img[y0:y1]))
+        pl = d.shrink(BS, BS, N.METRIC_SOBEL_DIR, 4.0, FILTER_DOWN, N.FLAG_NORMALISE_GLOBAL)
+        pl.free(); d.free()
+    except N.PixlzrError as e:
+        status = N.STATUS_NAMES.get(e.status, str(e.status))
+    flags = torch.tensor([1 if status != "ok" else 0], device=device, dtype=torch.int64)
+    dist.all_reduce(flags)
+    if rank == 0:
+        res["failing_rank_does_not_hang"] = int(flags.item()) == world  # every rank returned, each with an error
+    return res
 
 
 # --------------------------------------------------------------------------------------------------
@@ -192,7 +416,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     import pixlzr_b200 as P
 
-    N = P.native
+    N, S = P.native, P.sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -200,37 +424,34 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
-    batch = args.batch
+    batch, distinct = args.batch, min(args.distinct, args.batch)
+    t_start = time.time()
 
     with torch.cuda.stream(stream):
         ctx = N.Context(local_rank, cuda_stream=stream.cuda_stream)
         # inputs: host (pinned) for the e2e leg, device-resident copies for the kernel leg
-        host_imgs = []
-        for i in range(batch):
-            a = synth_image_np(rank * 1000 + i, IMG_W, IMG_H)
-            t = torch.from_numpy(a).pin_memory()
-            host_imgs.append(t)
+        host_imgs = [torch.from_numpy(synth_image_np(rank * 1000 + i, IMG_W, IMG_H)).pin_memory() for i in range(distinct)]
         dev_imgs = [t.to(dev, non_blocking=True) for t in host_imgs]
-        dev_out = torch.empty((IMG_H, IMG_W, 4), dtype=torch.uint8, device=dev)
         stream.synchronize()
-        # device-resident leg: `--streams` contexts (one CUDA stream each) take the images of a step in turn, so the
-        # latency-bound kernels of one image (guard-band recompute, plan) overlap the throughput kernels of another
+        # device-resident leg: `--streams` contexts (one CUDA stream each) take the frames of a step in turn, so the
+        # latency-bound kernels of one frame (guard-band recompute, plan) overlap the throughput kernels of another
         n_streams = max(1, min(args.streams, batch))
         streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
         ctxs = [ctx] + [N.Context(local_rank, cuda_stream=st.cuda_stream) for st in streams[1:]]
-        outs = [dev_out] + [torch.empty_like(dev_out) for _ in range(n_streams - 1)]
-        wrapped = [ctxs[i % n_streams].image_wrap(t.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for i, t in enumerate(dev_imgs)]
+        outs = [torch.empty((IMG_H, IMG_W, 4), dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+        wrapped = [[c.image_wrap(t.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for t in dev_imgs] for c in ctxs]
         wrapped_out = [ctxs[k].image_wrap(outs[k].data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for k in range(n_streams)]
 
         def step_device():
-            for i, im in enumerate(wrapped):
-                pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
-                pl.expand_to_image(FILTER_UP, wrapped_out[i % n_streams])
+            for i in range(batch):
+                k = i % n_streams
+                pl = wrapped[k][i % distinct].shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+                pl.expand_to_image(FILTER_UP, wrapped_out[k])
                 pl.free()
 
         # payload sizes (for the algorithmic-byte counts), untimed
         payload_bytes, nblocks = [], 0
-        for im in wrapped:
+        for im in wrapped[0]:
             pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
             info = pl.info()
             payload_bytes.append(info["bytes"])
@@ -246,10 +467,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
                                int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
         sampler.start()
-        sampler.wait_first()
         launches0 = sum(c.launch_count() for c in ctxs)
-        for c in ctxs:
-            c.profile_enable(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.time()
         ev0.record(stream)               # the timed region starts on the launching stream ...
@@ -269,55 +487,73 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         if world > 1:
             dist.barrier()
         elapsed_ms = ev0.elapsed_time(ev1)
-        prof = {}
-        for c in ctxs:
-            for name, (ms, n) in c.profile_read().items():
-                a, b = prof.get(name, (0.0, 0))
-                prof[name] = (a + ms, b + n)
-            c.profile_enable(False)
         launches = sum(c.launch_count() for c in ctxs) - launches0
-        # the timed region is a few ms, nvidia-smi polls every >= 20 ms: the same steps keep running (untimed, outside the
-        # launch count) until at least two polls have seen the GPU under this load
-        t_keep = time.time()
-        while sampler.proc is not None and sampler.samples_since(t_wall0) < 2 and time.time() - t_keep < 1.0:
-            step_device()
-            torch.cuda.synchronize()
-        t_wall1 = time.time()
         clocks = sampler.stop(t_wall0, t_wall1)
-        clocks["window"] = "timed region + the same steps continued (untimed) until two nvidia-smi polls"
-        # per-kernel durations without cross-stream contention: the same K steps again on the launching stream only
-        prof_overlapped = prof
-        if n_streams > 1:
-            solo = [ctx.image_wrap(t.data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4) for t in dev_imgs]
-            ctx.profile_enable(True)
-            ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev2.record(stream)
-            for _ in range(args.steps):
-                for im in solo:
-                    pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
-                    pl.expand_to_image(FILTER_UP, wrapped_out[0])
-                    pl.free()
-            ev3.record(stream)
+
+        # per-kernel durations without cross-stream overlap: the same frames on the launching stream only, CUDA events
+        # around every launch (pxz_profile_*).  This pass is what the roofline of the dominant kernel is computed from.
+        solo_steps = max(2, min(args.steps, 6))
+        ctx.profile_enable(True)
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record(stream)
+        for _ in range(solo_steps):
+            for i in range(batch):
+                pl = wrapped[0][i % distinct].shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+                pl.expand_to_image(FILTER_UP, wrapped_out[0])
+                pl.free()
+        ev3.record(stream)
+        stream.synchronize()
+        solo_ms = ev2.elapsed_time(ev3)
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        # the same single-stream pass without the per-launch events (they cost a few microseconds per kernel)
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev4.record(stream)
+        for _ in range(solo_steps):
+            for i in range(batch):
+                pl = wrapped[0][i % distinct].shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+                pl.expand_to_image(FILTER_UP, wrapped_out[0])
+                pl.free()
+        ev5.record(stream)
+        stream.synchronize()
+        solo_plain_ms = ev4.elapsed_time(ev5)
+
+        # ---- in-run parity on the timed workload: frame 0, top CPU_SAMPLE_ROWS rows, against the oracle ----------------
+        parity = None
+        cpu = None
+        if rank == 0:
+            sample = np.ascontiguousarray(host_imgs[0].numpy()[:CPU_SAMPLE_ROWS])
+            cpu, ref_s, ref_out = cpu_baseline(sample)
+            pl = wrapped[0][0].shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+            descs, px = pl.download()
+            pl.expand_to_image(FILTER_UP, wrapped_out[0])
             stream.synchronize()
-            solo_ms = ev2.elapsed_time(ev3)
-            prof = ctx.profile_read()
-            ctx.profile_enable(False)
-        else:
-            solo_ms = elapsed_ms
+            got = outs[0][:CPU_SAMPLE_ROWS].cpu().numpy()
+            pl.free()
+            nb = len(ref_s.descs)
+            dims_ok = bool(np.array_equal(descs["w"][:nb], ref_s.descs["w"]) and np.array_equal(descs["h"][:nb], ref_s.descs["h"]) and
+                           np.array_equal(descs["offset"][:nb], ref_s.descs["offset"]))
+            payload_ok = bool(np.array_equal(px[:ref_s.payload.size], ref_s.payload))
+            diff = np.abs(got.astype(np.int16) - ref_out.astype(np.int16))
+            mse = float(np.mean(diff.astype(np.float64) ** 2))
+            parity = {"parity_on_workload": dims_ok and payload_ok and int(diff.max()) == 0,
+                      "blocks_checked": int(nb), "dims_and_offsets_equal": dims_ok, "payload_bytes_equal": payload_ok,
+                      "decoded_max_abs_diff_lsb": int(diff.max()), "decoded_psnr_db": None if mse == 0 else round(10 * np.log10(255.0 ** 2 / mse), 2),
+                      "stored_values_max_abs_diff": float(np.max(np.abs(descs["value"][:nb].astype(np.float64) - ref_s.descs["value"]))),
+                      "what": f"frame 0 of the timed workload, top {CPU_SAMPLE_ROWS} rows: GPU descriptors / payload / decoded pixels against the CPU oracle run of cpu_baseline"}
 
         # ---- informative: the opt-in fused-multiply-add resample (pixels within +-1 LSB of the reference, the tolerance
-        # BASELINE.json states; tests/test_gpu_parity.py checks it).  Single stream, same K steps; not the headline.
+        # BASELINE.json states; tests/test_gpu_parity.py checks it).  Single stream; not the headline.
         fused_info = None
         if rank == 0:
-            im0 = ctx.image_wrap(dev_imgs[0].data_ptr(), IMG_W, IMG_H, 4, IMG_W * 4)
             ctx.set_fast_resample(True)
             for _ in range(2):
-                pl = im0.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+                pl = wrapped[0][0].shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
                 pl.expand_to_image(FILTER_UP, wrapped_out[0])
                 pl.free()
             ctx.profile_enable(True)
-            for _ in range(args.steps):
-                pl = im0.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+            for i in range(2 * distinct):
+                pl = wrapped[0][i % distinct].shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
                 pl.expand_to_image(FILTER_UP, wrapped_out[0])
                 pl.free()
             stream.synchronize()
@@ -329,8 +565,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             fused_info["MPps_single_stream"] = round(IMG_W * IMG_H / 1e6 / (sum(fused_info["kernel_us"].values()) * 1e-6), 1)
 
         # ---- e2e: same work through the C ABI with pinned host buffers ---------------------------------
-        # `E2E_WORKERS` host threads, each with its own context (= its own stream) and pinned staging buffers, take
-        # the images of the step in turn, so one image's H2D overlaps another's kernels and D2H (PCIe is full duplex).
+        # `--e2e-workers` host threads, each with its own context (= its own stream) and pinned staging buffers, take
+        # the frames of the step in turn, so one frame's H2D overlaps another's kernels and D2H (PCIe is full duplex).
         img_bytes = IMG_W * IMG_H * 4
         n_workers = max(1, min(args.e2e_workers, batch))
         np_imgs = [t.numpy() for t in host_imgs]
@@ -344,11 +580,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 self.descs = self.pin[0].numpy().view(N.DESC_DTYPE)
                 self.pixels, self.out = self.pin[1].numpy(), self.pin[2].numpy()
                 self.h2d = self.d2h = 0
-                self.busy_s = 0.0
 
             def encode_decode(self, a):
                 c = self.ctx
-                t_in = time.perf_counter()
                 im = c.image_upload(a)                                                  # H2D image
                 pl = im.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
                 nbytes = pl.download_into(self.descs, self.pixels)                      # D2H descs + payload (encode result)
@@ -359,27 +593,25 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 pl2.free()
                 self.h2d += img_bytes + nbytes + nblocks * 16
                 self.d2h += nbytes + nblocks * 16 + img_bytes
-                self.busy_s += time.perf_counter() - t_in
 
         workers = [Worker() for _ in range(n_workers)]
 
         def run_steps(k: int):
-            # worker w takes images w, w + n_workers, ... of every step; steps run back to back (no per-step join)
+            # worker w takes frames w, w + n_workers, ... of every step; steps run back to back (no per-step join)
             def loop(wi: int):
                 for _ in range(k):
-                    for a in np_imgs[wi::n_workers]:
-                        workers[wi].encode_decode(a)
+                    for i in range(wi, batch, n_workers):
+                        workers[wi].encode_decode(np_imgs[i % distinct])
             th = [threading.Thread(target=loop, args=(wi,)) for wi in range(n_workers)]
             for t in th:
                 t.start()
             for t in th:
                 t.join()
 
-        e2e_steps = max(2, min(args.steps, 8))
-        run_steps(2)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        run_steps(1)
         for wk in workers:
             wk.h2d = wk.d2h = 0
-            wk.busy_s = 0.0
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -387,21 +619,64 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         e2e_s = time.perf_counter() - t0
         h2d = sum(wk.h2d for wk in workers)
         d2h = sum(wk.d2h for wk in workers)
-        if os.environ.get("PXZ_BENCH_DEBUG"):
-            sys.stderr.write(f"[rank {rank}] e2e {e2e_s * 1e3:.1f} ms for {e2e_steps * batch} images; per-worker busy "
-                             f"{[round(wk.busy_s * 1e3, 1) for wk in workers]} ms\n")
+        # the ceiling of that path: the same bytes of one step as plain pinned copies, both directions at once
+        pcie = None
+        if args.pcie_probe:
+            src_pin, dst_pin = workers[0].pin[2], workers[0].pin[1]
+            dbuf = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
+            dbuf2 = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
+            s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            tp0 = time.perf_counter()
+            for _ in range(4):
+                with torch.cuda.stream(s_up):
+                    dbuf.copy_(src_pin.view(-1)[:img_bytes], non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    dst_pin.copy_(dbuf2, non_blocking=True)
+            torch.cuda.synchronize()
+            tp = time.perf_counter() - tp0
+            pcie = {"h2d_plus_d2h_GBps": round(8 * img_bytes / tp / 1e9, 1), "what": "4 x (132.7 MB up + 132.7 MB down) pinned, two streams, all ranks at once"}
+        for wk in workers:
+            del wk.pin
+        del workers
+
+    # ---- the sharded configurations, on the same ranks ---------------------------------------------------------------
+    sharded = batch_c5 = nccl_parity = None
+    if not args.skip_extras:
+        torch.cuda.synchronize()
+        del dev_imgs, outs, wrapped, wrapped_out
+        torch.cuda.empty_cache()
+        with torch.cuda.stream(stream):
+            try:
+                sharded = run_sharded_c4(torch, dist, N, S, args, rank, world, local_rank, dev)
+            except Exception as e:  # a missing block is reported, it does not take the headline down
+                sharded = {"error": repr(e)}
+            try:
+                batch_c5 = run_batch_c5(torch, dist, N, S, args, rank, world, local_rank, dev)
+            except Exception as e:
+                batch_c5 = {"error": repr(e)}
+            if world > 1:
+                try:
+                    nccl_parity = run_nccl_parity(torch, dist, N, S, None, rank, world, local_rank, dev)
+                except Exception as e:
+                    nccl_parity = {"error": repr(e)}
 
     # ---- reduce over ranks: max time -------------------------------------------------------------------
-    reason_names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    reason_bits = sum(1 << i for i, n in enumerate(reason_names) if n in (clocks.get("reasons") or []))
-    times = torch.tensor([elapsed_ms, e2e_s * 1e3, (t_launched - t_wall0) * 1e3, clocks.get("sm_mhz") or -1.0, float(reason_bits)],
-                         dtype=torch.float64, device=dev)
+    names = ClockSampler.NAMES
+    reason_bits = sum(1 << i for i, n in enumerate(names) if n in (clocks.get("reasons") or []))
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3, (t_launched - t_wall0) * 1e3, clocks.get("sm_mhz") or -1.0, float(reason_bits),
+                          solo_plain_ms], dtype=torch.float64, device=dev)
     per_rank_ms = [elapsed_ms / args.steps]
+    per_rank_e2e = [batch * e2e_steps * IMG_W * IMG_H / 1e6 / e2e_s]
+    per_rank_issue = [(t_launched - t_wall0) * 1e3 / args.steps]
     if world > 1:
         gathered = [torch.zeros_like(times) for _ in range(world)]
         dist.all_gather(gathered, times)
-        per_rank_ms = [float(t[0]) / args.steps for t in gathered]  # diagnostic: which rank sets the max
-        # clocks of every rank's GPU: the line reports the slowest one and the union of the throttle reasons
+        per_rank_ms = [float(t[0]) / args.steps for t in gathered]  # which rank sets the max
+        per_rank_e2e = [batch * e2e_steps * IMG_W * IMG_H / 1e6 / (float(t[1]) / 1e3) for t in gathered]
+        per_rank_issue = [float(t[2]) / args.steps for t in gathered]
         mhz = [float(t[3]) for t in gathered]
         bits = 0
         for t in gathered:
@@ -409,7 +684,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         clocks["sm_mhz_per_rank"] = mhz
         if all(m > 0 for m in mhz):
             clocks["sm_mhz"] = min(mhz)
-        clocks["reasons"] = sorted(set(clocks.get("reasons") or []) | {n for i, n in enumerate(reason_names) if bits >> i & 1})
+        clocks["reasons"] = sorted(set(clocks.get("reasons") or []) | {n for i, n in enumerate(names) if bits >> i & 1})
         head = times[:3].clone()
         dist.all_reduce(head, op=dist.ReduceOp.MAX)
         times[:3] = head
@@ -432,10 +707,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         n_px = IMG_W * IMG_H
         mean_payload = float(np.mean(payload_bytes))
-        # algorithmic bytes per launch of every kernel (DESIGN.md "algorithmic bytes")
+        # algorithmic bytes per launch of every kernel (DESIGN.md "algorithmic bytes"); the guard-band recompute only
+        # touches the banded tiles (about 1 %), so it gets no bandwidth figure
         algo = {
             "analyze_mad_fast": 4 * n_px + 5 * nblocks,
-            "mad_exact": 4 * n_px + 4 * nblocks,
+            "mad_exact": None,
             "plan": 4 * nblocks + 20 * nblocks,
             "resample_down": 4 * n_px + mean_payload + 20 * nblocks,
             "resample_up": mean_payload + 20 * nblocks + 4 * n_px,
@@ -444,53 +720,67 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         for name, (ms, n) in prof.items():
             if n:
                 us = ms / n * 1e3
-                gbs = algo.get(name, 0) / (us * 1e-6) / 1e9
-                kernels[name] = {"us": round(us, 2), "launches": int(n), "algo_GBps": round(gbs, 1),
-                                 "frac": round(gbs / peak, 4), "share": round(ms / solo_ms, 4)}
-                if n_streams > 1 and name in prof_overlapped and prof_overlapped[name][1]:
-                    kernels[name]["us_in_timed_region"] = round(prof_overlapped[name][0] / prof_overlapped[name][1] * 1e3, 2)
+                a = algo.get(name)
+                kernels[name] = {"us": round(us, 2), "launches": int(n), "share": round(ms / solo_ms, 4)}
+                if a:
+                    gbs = a / (us * 1e-6) / 1e9
+                    kernels[name].update({"algo_GBps": round(gbs, 1), "frac": round(gbs / peak, 4)})
         traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         except OSError:
             pass
-        dom = max(kernels, key=lambda k: kernels[k]["us"] * kernels[k]["launches"]) if kernels else None
+        with_bw = [k for k in kernels if "frac" in kernels[k]]
+        dom = max(with_bw, key=lambda k: kernels[k]["us"] * kernels[k]["launches"]) if with_bw else None
         roofline = None
         if dom:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["algo_GBps"], "peak": peak,
                         "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic.get(dom),
-                        "traffic_source": "profiles/r01_traffic.json (ncu --set full capture of the same workload)" if dom in traffic else None,
+                        "traffic_source": "profiles/r02_traffic.json (ncu --set full capture of the same workload)" if dom in traffic else None,
                         "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(algo[dom]), "avg_launch_us": kernels[dom]["us"],
-                        "timing": ("CUDA events around every launch; single-stream pass of the same K steps right after the "
-                                   "timed region (in the multi-stream timed region kernels of different images overlap: see "
-                                   "kernels[*].us_in_timed_region)") if n_streams > 1 else
-                                  "CUDA events around every launch inside the timed region",
-                        "single_stream_value_MPps": round(world * batch * IMG_W * IMG_H / 1e6 * args.steps / (solo_ms / 1e3), 1)}
-        # whole encode+decode stage against the roofline (image read once + payload written, payload read + image written)
-        stage_bytes = (4 * n_px + mean_payload + 16 * nblocks) + (mean_payload + 16 * nblocks + 4 * n_px)
+                        "timing": "CUDA events around every launch; single-stream pass over the same frames right after the timed region "
+                                  "(in the multi-stream timed region kernels of different frames overlap)",
+                        "single_stream_value_MPps": round(batch * IMG_W * IMG_H / 1e6 * solo_steps / (solo_plain_ms / 1e3), 1)}
+        # whole stages against the roofline, the frame counted ONCE per stage: encode = frame read + payload and
+        # descriptors written; decode = payload and descriptors read + frame written
+        enc_bytes = 4 * n_px + mean_payload + 16 * nblocks
+        dec_bytes = mean_payload + 16 * nblocks + 4 * n_px
+        enc_us = sum(kernels[k]["us"] for k in ("analyze_mad_fast", "mad_exact", "plan", "resample_down") if k in kernels)
+        dec_us = kernels.get("resample_up", {}).get("us", 0.0)
         per_image_s = elapsed_ms / 1e3 / (args.steps * batch)
-        stage = {"algorithmic_bytes_per_image": int(stage_bytes), "GBps": round(stage_bytes / per_image_s / 1e9, 1),
-                 "frac_of_hbm_peak": round(stage_bytes / per_image_s / 1e9 / peak, 4),
-                 "payload_fraction": round(mean_payload / (4 * n_px), 4)}
-        cpu = cpu_baseline(np.ascontiguousarray(np_imgs[0][:CPU_SAMPLE_ROWS])) if world == 1 else None
+        stage = {"algorithmic_bytes_per_image": int(enc_bytes + dec_bytes),
+                 "GBps": round((enc_bytes + dec_bytes) / per_image_s / 1e9, 1),
+                 "frac_of_hbm_peak": round((enc_bytes + dec_bytes) / per_image_s / 1e9 / peak, 4),
+                 "payload_fraction": round(mean_payload / (4 * n_px), 4),
+                 "encode_stage_frac": round(enc_bytes / (enc_us * 1e-6) / 1e9 / peak, 4) if enc_us else None,
+                 "decode_stage_frac": round(dec_bytes / (dec_us * 1e-6) / 1e9 / peak, 4) if dec_us else None,
+                 "encode_stage_us_single_stream": round(enc_us, 2), "decode_stage_us_single_stream": round(dec_us, 2),
+                 "note": "frac_of_hbm_peak: the timed multi-stream region; encode / decode_stage_frac: sums of the per-launch times of the "
+                         "single-stream pass, the frame counted once per stage"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, batch),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args), "streams_per_gpu": n_streams,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // e2e_steps),
                     "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps,
-                    "host_threads": n_workers,
+                    "host_threads": n_workers, "per_rank_MPps": [round(x, 1) for x in per_rank_e2e], "pcie_ceiling": pcie,
                     "path": "pxz_image_upload -> pxz_shrink -> pxz_payload_download -> pxz_payload_upload -> pxz_expand, pinned host buffers"},
             "gpu_launches": int(launches),
-            # host wall time to issue one step's launches (max over ranks): the step is launch-bound when this nears ms_per_step
+            # host wall time to issue one step's launches (per rank): the step is launch-bound when this nears ms_per_step
             "host_issue_ms_per_step": round(host_issue_ms / args.steps, 4),
+            "host_issue_ms_per_step_per_rank": [round(x, 4) for x in per_rank_issue],
             "ms_per_step_per_rank": [round(x, 4) for x in per_rank_ms],
+            "parity": parity,
             "fused_resample_mode": fused_info,
             "roofline": roofline,
             "kernels": kernels,
             "encode_decode_stage": stage,
+            "sharded": sharded,
+            "batch": batch_c5,
+            "nccl_parity": nccl_parity,
+            "bench_wall_s": round(time.time() - t_start, 1),
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -503,12 +793,20 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="8K images per rank per step")
+    ap.add_argument("--batch", type=int, default=16, help="8K frames per rank per step")
+    ap.add_argument("--distinct", type=int, default=4, help="different 8K frames per rank (taken in turn)")
     ap.add_argument("--streams", type=int, default=4, help="contexts / CUDA streams of the device-resident leg")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads (contexts) of the end-to-end leg")
+    ap.add_argument("--e2e-steps", type=int, default=2, help="steps of the end-to-end leg")
+    ap.add_argument("--no-pcie-probe", dest="pcie_probe", action="store_false")
+    ap.add_argument("--skip-extras", action="store_true", help="only the C3 headline: no sharded (C4) / batch (C5) blocks")
+    ap.add_argument("--c4-side", type=int, default=65536)
+    ap.add_argument("--c5-images", type=int, default=4096)
+    ap.add_argument("--c5-stack", type=int, default=64, help="frames per pxz_shrink_batch call")
+    ap.add_argument("--extra-reps", type=int, default=2, help="timed repetitions of the C4 / C5 passes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

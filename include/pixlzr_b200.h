@@ -134,6 +134,22 @@ pxz_status pxz_image_info(const pxz_image* img, uint32_t* w, uint32_t* h, uint32
                           void** device_ptr);
 pxz_status pxz_image_download(pxz_ctx* ctx, const pxz_image* img, uint8_t* host, size_t host_pitch);
 void pxz_image_free(pxz_image* img);
+
+/* ---- batches of images (SURVEY.md 8b "batch round-robin entry points"; BASELINE config 5) ------------------------
+ * A batch is n_images images of one size stacked in one pitched device allocation (image i at rows
+ * [i * h, (i + 1) * h)).  pxz_shrink_batch / pxz_expand_batch run ONE launch per stage over the tiles of all images
+ * — what a loop of Pixlzr::from_image(..).shrink_by(..) / to_image(..) over the batch computes (pixlzr.rs:155-185,
+ * pixlzr_image.rs:24-74), image by image identical to the single-image calls.  The payload of a batch is one buffer:
+ * descriptors in image order, then row-major per image (pxz_payload_info reports cols / rows of ONE image,
+ * pxz_payload_batch_count the images), offsets running through the whole batch.  pxz_image_download /
+ * pxz_payload_download / pxz_expand take host buffers laid out the same way (images back to back).
+ * Not available on a batch: PXZ_FLAG_NORMALISE_GLOBAL (per image by definition), the container stage, tree processing. */
+pxz_status pxz_image_alloc_batch(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t channels, uint32_t n_images, pxz_image** out);
+pxz_status pxz_image_upload_batch(pxz_ctx* ctx, const uint8_t* host, uint32_t w, uint32_t h, uint32_t channels, size_t host_pitch,
+                                  uint32_t n_images, pxz_image** out);
+pxz_status pxz_image_wrap_batch(pxz_ctx* ctx, void* device_ptr, uint32_t w, uint32_t h, uint32_t channels, size_t pitch,
+                                uint32_t n_images, pxz_image** out);
+uint32_t pxz_image_batch_count(const pxz_image* img);
 /* block grid: cols = ceil(w/bw), rows = ceil(h/bh) (split.rs:45-46, pixlzr.rs:37-42) */
 pxz_status pxz_grid(uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t* cols, uint32_t* rows);
 
@@ -178,6 +194,15 @@ void pxz_payload_free(pxz_payload* p);
  * pitched output image. */
 pxz_status pxz_expand(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, uint8_t* host_out, size_t host_pitch);
 pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, pxz_image* out);
+/* batch forms (see "batches of images" above): same arguments, the image / payload handles hold n_images images */
+pxz_status pxz_shrink_batch(pxz_ctx* ctx, const pxz_image* batch, uint32_t bw, uint32_t bh, pxz_metric metric, float factor,
+                            pxz_filter filter_down, uint32_t flags, pxz_payload** out);
+pxz_status pxz_expand_batch(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, pxz_image* out_batch);
+pxz_status pxz_payload_upload_batch(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t channels,
+                                    uint32_t n_images, const pxz_block_desc* descs, const uint8_t* pixels, uint64_t bytes,
+                                    pxz_payload** out);
+uint32_t pxz_payload_batch_count(const pxz_payload* p);
+
 
 /* ---- quadtree processing: tree::process_custom (src/process/tree.rs:23-83) with before = |x-avg|, after = identity.
  * Blocks whose value is below |threshold| are reduced and re-expanded (filter_down / filter_up); the others are split

@@ -50,6 +50,14 @@ SYMBOLS = {
     "pxz_image_info": (_i, [_vp, _P(_u32), _P(_u32), _P(_u32), _P(_sz), _P(_vp)]),
     "pxz_image_download": (_i, [_vp, _vp, _vp, _sz]),
     "pxz_image_free": (None, [_vp]),
+    "pxz_image_alloc_batch": (_i, [_vp, _u32, _u32, _u32, _u32, _P(_vp)]),
+    "pxz_image_upload_batch": (_i, [_vp, _vp, _u32, _u32, _u32, _sz, _u32, _P(_vp)]),
+    "pxz_image_wrap_batch": (_i, [_vp, _vp, _u32, _u32, _u32, _sz, _u32, _P(_vp)]),
+    "pxz_image_batch_count": (_u32, [_vp]),
+    "pxz_shrink_batch": (_i, [_vp, _vp, _u32, _u32, _i, C.c_float, _i, _u32, _P(_vp)]),
+    "pxz_expand_batch": (_i, [_vp, _vp, _i, _vp]),
+    "pxz_payload_upload_batch": (_i, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _u64, _P(_vp)]),
+    "pxz_payload_batch_count": (_u32, [_vp]),
     "pxz_grid": (_i, [_u32, _u32, _u32, _u32, _P(_u32), _P(_u32)]),
     "pxz_analyze": (_i, [_vp, _vp, _u32, _u32, _i, _u32, _vp, _vp]),
     "pxz_shrink": (_i, [_vp, _vp, _u32, _u32, _i, C.c_float, _i, _u32, _P(_vp)]),
@@ -254,6 +262,33 @@ class Context:
         self.check(lib().pxz_image_wrap(self._h, C.c_void_p(device_ptr), w, h, c, pitch, C.byref(hd)))
         return Image(self, hd, w, h, c)
 
+    # ---- batches: n images of one size stacked in one allocation (include/pixlzr_b200.h "batches of images") ----
+    def image_upload_batch(self, imgs: np.ndarray) -> "Image":
+        """imgs: uint8 [n, h, w, c], C-contiguous."""
+        assert imgs.dtype == np.uint8 and imgs.ndim == 4 and imgs.shape[3] in (3, 4) and imgs.flags.c_contiguous
+        n, h, w, c = imgs.shape
+        hd = C.c_void_p()
+        self.check(lib().pxz_image_upload_batch(self._h, ptr(imgs), w, h, c, imgs.strides[1], n, C.byref(hd)))
+        return Image(self, hd, w, h, c, n)
+
+    def image_alloc_batch(self, w: int, h: int, c: int, n: int) -> "Image":
+        hd = C.c_void_p()
+        self.check(lib().pxz_image_alloc_batch(self._h, w, h, c, n, C.byref(hd)))
+        return Image(self, hd, w, h, c, n)
+
+    def image_wrap_batch(self, device_ptr: int, w: int, h: int, c: int, pitch: int, n: int) -> "Image":
+        hd = C.c_void_p()
+        self.check(lib().pxz_image_wrap_batch(self._h, C.c_void_p(device_ptr), w, h, c, pitch, n, C.byref(hd)))
+        return Image(self, hd, w, h, c, n)
+
+    def payload_upload_batch(self, w, h, bw, bh, c, n, descs: np.ndarray, pixels: np.ndarray) -> "Payload":
+        assert descs.dtype == DESC_DTYPE and pixels.dtype == np.uint8
+        descs = np.ascontiguousarray(descs)
+        pixels = np.ascontiguousarray(pixels)
+        hd = C.c_void_p()
+        self.check(lib().pxz_payload_upload_batch(self._h, w, h, bw, bh, c, n, ptr(descs), ptr(pixels), pixels.size, C.byref(hd)))
+        return Payload(self, hd)
+
     # ---- payload ------------------------------------------------------------------------------
     def payload_upload(self, w, h, bw, bh, c, descs: np.ndarray, pixels: np.ndarray) -> "Payload":
         assert descs.dtype == DESC_DTYPE and pixels.dtype == np.uint8
@@ -273,8 +308,8 @@ class Context:
 
 
 class Image:
-    def __init__(self, ctx: Context, handle, w, h, c):
-        self.ctx, self._h, self.w, self.h, self.c = ctx, handle, w, h, c
+    def __init__(self, ctx: Context, handle, w, h, c, n: int = 1):
+        self.ctx, self._h, self.w, self.h, self.c, self.n = ctx, handle, w, h, c, n
 
     @property
     def handle(self):
@@ -286,9 +321,10 @@ class Image:
         return dict(w=w.value, h=h.value, channels=c.value, pitch=pitch.value, device_ptr=p.value)
 
     def download(self) -> np.ndarray:
-        out = np.empty((self.h, self.w, self.c), np.uint8)
+        """[h, w, c], or [n, h, w, c] for a batch."""
+        out = np.empty((self.n * self.h, self.w, self.c), np.uint8)
         self.ctx.check(lib().pxz_image_download(self.ctx.handle, self._h, ptr(out), out.strides[0]))
-        return out
+        return out if self.n == 1 else out.reshape(self.n, self.h, self.w, self.c)
 
     def analyze(self, bw: int, bh: int, metric: int, flags: int = 0):
         cols, rows = grid(self.w, self.h, bw, bh)
@@ -355,11 +391,12 @@ class Payload:
         keys = ["w", "h", "bw", "bh", "cols", "rows", "channels"]
         d = {k: x.value for k, x in zip(keys, v)}
         d["bytes"] = b.value
+        d["images"] = int(lib().pxz_payload_batch_count(self._h))  # cols / rows describe ONE image
         return d
 
     def download(self):
         i = self.info()
-        descs = np.empty(i["cols"] * i["rows"], DESC_DTYPE)
+        descs = np.empty(i["cols"] * i["rows"] * i["images"], DESC_DTYPE)
         pixels = np.empty(max(1, i["bytes"]), np.uint8)
         self.ctx.check(lib().pxz_payload_download(self.ctx.handle, self._h, ptr(descs), ptr(pixels)))
         return descs, pixels[:i["bytes"]]
@@ -367,7 +404,7 @@ class Payload:
     def download_into(self, descs: np.ndarray, pixels: np.ndarray) -> int:
         """Like download(), into caller-provided (e.g. pinned) buffers; returns the payload byte count."""
         i = self.info()
-        assert descs.dtype == DESC_DTYPE and descs.size >= i["cols"] * i["rows"] and pixels.size >= i["bytes"]
+        assert descs.dtype == DESC_DTYPE and descs.size >= i["cols"] * i["rows"] * i["images"] and pixels.size >= i["bytes"]
         self.ctx.check(lib().pxz_payload_download(self.ctx.handle, self._h, ptr(descs), ptr(pixels)))
         return i["bytes"]
 
@@ -376,9 +413,9 @@ class Payload:
 
     def expand(self, filter_up: int) -> np.ndarray:
         i = self.info()
-        out = np.empty((i["h"], i["w"], i["channels"]), np.uint8)
+        out = np.empty((i["images"] * i["h"], i["w"], i["channels"]), np.uint8)
         self.ctx.check(lib().pxz_expand(self.ctx.handle, self._h, int(filter_up), ptr(out), out.strides[0]))
-        return out
+        return out if i["images"] == 1 else out.reshape(i["images"], i["h"], i["w"], i["channels"])
 
     def expand_to_image(self, filter_up: int, out: Image):
         self.ctx.check(lib().pxz_expand_to_image(self.ctx.handle, self._h, int(filter_up), out.handle))

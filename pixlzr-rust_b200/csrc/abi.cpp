@@ -110,6 +110,7 @@ struct pxz_image {
   size_t pitch;
   uint32_t w, h, c;
   bool owned;
+  uint32_t nimg = 1;  // > 1: a batch, image i at rows [i * h, (i + 1) * h) of the allocation
 };
 
 constexpr size_t kPayloadCacheMax = 4;
@@ -184,17 +185,21 @@ struct ProfScope {
 
 inline uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a + b - 1) / b); }
 
-pxz_status make_geom(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t c, uint32_t bw, uint32_t bh, Geom* g) {
-  if (w == 0 || h == 0) return fail(ctx, PXZ_E_ARG, "empty image");
+pxz_status make_geom(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t c, uint32_t bw, uint32_t bh, Geom* g, uint32_t nimg = 1) {
+  if (w == 0 || h == 0 || nimg == 0) return fail(ctx, PXZ_E_ARG, "empty image");
   if (c != 3 && c != 4) return fail(ctx, PXZ_E_ARG, "channels must be 3 (RGB8) or 4 (RGBA8)");
   if (bw == 0 || bh == 0) return fail(ctx, PXZ_E_ARG, "block size must be >= 1 (the reference divides by it)");
   if (bw > 65535u || bh > 65535u) return fail(ctx, PXZ_E_UNSUPPORTED, "block size above 65535 is not supported");
   g->W = w; g->H = h; g->bw = bw; g->bh = bh; g->C = c;
   g->cols = ceil_div_u32(w, bw);  // == ceil(w as f64 / bw as f64), split.rs:45-46
-  g->rows = ceil_div_u32(h, bh);
+  g->rows_img = ceil_div_u32(h, bh);
+  g->nimg = nimg;
+  g->img_rows = h;
   g->trail_w = w % bw;
   g->trail_h = h % bh;
-  if ((uint64_t)g->cols * g->rows > 0x7FFFFFFFull) return fail(ctx, PXZ_E_UNSUPPORTED, "more than 2^31 blocks");
+  if ((uint64_t)g->cols * g->rows_img * nimg > 0x7FFFFFFFull) return fail(ctx, PXZ_E_UNSUPPORTED, "more than 2^31 blocks");
+  if ((uint64_t)h * nimg > 0xFFFFFFFFull) return fail(ctx, PXZ_E_UNSUPPORTED, "batch taller than 2^32 rows");
+  g->rows = g->rows_img * nimg;  // block rows of the whole batch
   return PXZ_OK;
 }
 
@@ -589,16 +594,21 @@ pxz_status pxz_grid(uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t* 
 
 // ---- images ---------------------------------------------------------------------------------------
 pxz_status pxz_image_alloc(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t channels, pxz_image** out) {
+  return pxz_image_alloc_batch(ctx, w, h, channels, 1, out);
+}
+
+pxz_status pxz_image_alloc_batch(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t channels, uint32_t n_images, pxz_image** out) {
   if (!ctx || !out) return PXZ_E_ARG;
   *out = nullptr;
-  if (w == 0 || h == 0) return fail(ctx, PXZ_E_ARG, "empty image");
+  if (w == 0 || h == 0 || n_images == 0) return fail(ctx, PXZ_E_ARG, "empty image");
+  if ((uint64_t)h * n_images > 0xFFFFFFFFull) return fail(ctx, PXZ_E_UNSUPPORTED, "batch taller than 2^32 rows");
   if (channels != 3 && channels != 4) return fail(ctx, PXZ_E_ARG, "channels must be 3 or 4");
   cudaSetDevice(ctx->device);
   pxz_image* im = new (std::nothrow) pxz_image();
   if (!im) return fail(ctx, PXZ_E_OOM, "host allocation failed");
-  im->ctx = ctx; im->w = w; im->h = h; im->c = channels; im->owned = true;
+  im->ctx = ctx; im->w = w; im->h = h; im->c = channels; im->owned = true; im->nimg = n_images;
   im->pitch = (((size_t)w * channels) + 127) & ~(size_t)127;  // 128-byte rows: every tile row starts 16 B aligned for RGBA
-  pxz_status st = dev_alloc(ctx, (void**)&im->d, im->pitch * h);
+  pxz_status st = dev_alloc(ctx, (void**)&im->d, im->pitch * h * n_images);
   if (st != PXZ_OK) { delete im; return st; }
   *out = im;
   return PXZ_OK;
@@ -606,11 +616,17 @@ pxz_status pxz_image_alloc(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t channe
 
 pxz_status pxz_image_upload(pxz_ctx* ctx, const uint8_t* host, uint32_t w, uint32_t h, uint32_t channels, size_t host_pitch,
                             pxz_image** out) {
+  return pxz_image_upload_batch(ctx, host, w, h, channels, host_pitch, 1, out);
+}
+
+pxz_status pxz_image_upload_batch(pxz_ctx* ctx, const uint8_t* host, uint32_t w, uint32_t h, uint32_t channels, size_t host_pitch,
+                                  uint32_t n_images, pxz_image** out) {
   if (!ctx || !host || !out) return PXZ_E_ARG;
   if (host_pitch < (size_t)w * channels) return fail(ctx, PXZ_E_ARG, "host pitch smaller than a row");
-  pxz_status st = pxz_image_alloc(ctx, w, h, channels, out);
+  pxz_status st = pxz_image_alloc_batch(ctx, w, h, channels, n_images, out);
   if (st != PXZ_OK) return st;
-  cudaError_t e = cudaMemcpy2DAsync((*out)->d, (*out)->pitch, host, host_pitch, (size_t)w * channels, h,
+  // the host images follow each other without a gap (image i at host + i * h * host_pitch): one 2-D copy
+  cudaError_t e = cudaMemcpy2DAsync((*out)->d, (*out)->pitch, host, host_pitch, (size_t)w * channels, (size_t)h * n_images,
                                     cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) {
     pxz_image_free(*out);
@@ -622,12 +638,19 @@ pxz_status pxz_image_upload(pxz_ctx* ctx, const uint8_t* host, uint32_t w, uint3
 
 pxz_status pxz_image_wrap(pxz_ctx* ctx, void* device_ptr, uint32_t w, uint32_t h, uint32_t channels, size_t pitch,
                           pxz_image** out) {
+  return pxz_image_wrap_batch(ctx, device_ptr, w, h, channels, pitch, 1, out);
+}
+
+pxz_status pxz_image_wrap_batch(pxz_ctx* ctx, void* device_ptr, uint32_t w, uint32_t h, uint32_t channels, size_t pitch,
+                                uint32_t n_images, pxz_image** out) {
   if (!ctx || !device_ptr || !out) return PXZ_E_ARG;
-  if (w == 0 || h == 0 || (channels != 3 && channels != 4) || pitch < (size_t)w * channels)
+  if (w == 0 || h == 0 || n_images == 0 || (channels != 3 && channels != 4) || pitch < (size_t)w * channels ||
+      (uint64_t)h * n_images > 0xFFFFFFFFull)
     return fail(ctx, PXZ_E_ARG, "bad image geometry");
   pxz_image* im = new (std::nothrow) pxz_image();
   if (!im) return fail(ctx, PXZ_E_OOM, "host allocation failed");
   im->ctx = ctx; im->d = (uint8_t*)device_ptr; im->pitch = pitch; im->w = w; im->h = h; im->c = channels; im->owned = false;
+  im->nimg = n_images;
   *out = im;
   return PXZ_OK;
 }
@@ -645,7 +668,7 @@ pxz_status pxz_image_info(const pxz_image* img, uint32_t* w, uint32_t* h, uint32
 pxz_status pxz_image_download(pxz_ctx* ctx, const pxz_image* img, uint8_t* host, size_t host_pitch) {
   if (!ctx || !img || !host) return PXZ_E_ARG;
   if (host_pitch < (size_t)img->w * img->c) return fail(ctx, PXZ_E_ARG, "host pitch smaller than a row");
-  PXZ_CUDA(ctx, cudaMemcpy2DAsync(host, host_pitch, img->d, img->pitch, (size_t)img->w * img->c, img->h,
+  PXZ_CUDA(ctx, cudaMemcpy2DAsync(host, host_pitch, img->d, img->pitch, (size_t)img->w * img->c, (size_t)img->h * img->nimg,
                                   cudaMemcpyDeviceToHost, ctx->stream));
   PXZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PXZ_OK;
@@ -701,7 +724,7 @@ pxz_status pxz_analyze(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t
   if (!ctx || !img || !host_values_x) return PXZ_E_ARG;
   cudaSetDevice(ctx->device);
   Geom g;
-  pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw, bh, &g);
+  pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw, bh, &g, img->nimg);
   if (st != PXZ_OK) return st;
   st = run_analysis(ctx, img, g, metric, (flags & PXZ_FLAG_EXACT_VALUES) != 0, nullptr);
   if (st != PXZ_OK) return st;
@@ -811,8 +834,9 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   };
   if ((int)filter_down < 0 || (int)filter_down > 4) return bail(fail(ctx, PXZ_E_ARG, "unknown filter"));
   Geom g;
-  pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw, bh, &g);
+  pxz_status st = make_geom(ctx, img->w, img->h, img->c, bw, bh, &g, img->nimg);
   if (st != PXZ_OK) return bail(st);
+  if (normalise && img->nimg > 1) return bail(fail(ctx, PXZ_E_UNSUPPORTED, "global normalisation is per image: not available on a batch"));
   const uint32_t nblocks = g.cols * g.rows;
 
   ValueMap vm;
@@ -848,7 +872,7 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
   }
 
   pxz_payload* p = nullptr;
-  st = payload_new(ctx, g, (uint64_t)g.W * g.H * g.C, &p);
+  st = payload_new(ctx, g, (uint64_t)g.W * g.H * g.C * g.nimg, &p);
   if (st != PXZ_OK) return st;
   p->spec = spec_for_geom(g);
   {
@@ -966,7 +990,7 @@ pxz_status pxz_payload_info(pxz_ctx* ctx, const pxz_payload* p, uint32_t* w, uin
   if (bw) *bw = p->g.bw;
   if (bh) *bh = p->g.bh;
   if (cols) *cols = p->g.cols;
-  if (rows) *rows = p->g.rows;
+  if (rows) *rows = p->g.rows_img;  /* per image; pxz_payload_batch_count() images */
   if (channels) *channels = p->g.C;
   if (bytes) return payload_bytes(ctx, p, bytes);
   return PXZ_OK;
@@ -988,11 +1012,11 @@ pxz_status pxz_payload_download(pxz_ctx* ctx, const pxz_payload* p, pxz_block_de
 // pixels == NULL with copy_pixels == false: the caller fills p->d_pixels on the device (pxz_payload_from_container)
 static pxz_status payload_from_descs(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t channels,
                                      const pxz_block_desc* descs, const uint8_t* pixels, bool copy_pixels, uint64_t bytes,
-                                     pxz_payload** out) {
+                                     pxz_payload** out, uint32_t nimg = 1) {
   *out = nullptr;
   cudaSetDevice(ctx->device);
   Geom g;
-  pxz_status st = make_geom(ctx, w, h, channels, bw, bh, &g);
+  pxz_status st = make_geom(ctx, w, h, channels, bw, bh, &g, nimg);
   if (st != PXZ_OK) return st;
   // the decoder sizes the grid in f32 (encoding/mod.rs:118-119); identical to the integer ceil below 2^24
   const size_t nblocks = (size_t)g.cols * g.rows;
@@ -1013,10 +1037,10 @@ static pxz_status payload_from_descs(pxz_ctx* ctx, uint32_t w, uint32_t h, uint3
     return id;
   };
   for (size_t b = 0; b < nblocks; ++b) {
-    const uint32_t by = (uint32_t)(b / g.cols), bx = (uint32_t)(b % g.cols);
+    const uint32_t by = (uint32_t)((b / g.cols) % g.rows_img), bx = (uint32_t)(b % g.cols);
     // target size as Pixlzr::expand computes it (pixlzr.rs:92-107)
     const uint32_t tw = (bx == g.cols - 1 && g.trail_w) ? g.trail_w : g.bw;
-    const uint32_t th = (by == g.rows - 1 && g.trail_h) ? g.trail_h : g.bh;
+    const uint32_t th = (by == g.rows_img - 1 && g.trail_h) ? g.trail_h : g.bh;
     const pxz_block_desc& d = descs[b];
     if (d.w == 0 || d.h == 0) return fail(ctx, PXZ_E_ARG, "block with zero size");
     const uint64_t sz = (uint64_t)d.w * d.h * channels;
@@ -1073,11 +1097,32 @@ pxz_status pxz_payload_upload(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw,
   return payload_from_descs(ctx, w, h, bw, bh, channels, descs, pixels, true, bytes, out);
 }
 
+pxz_status pxz_payload_upload_batch(pxz_ctx* ctx, uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t channels,
+                                    uint32_t n_images, const pxz_block_desc* descs, const uint8_t* pixels, uint64_t bytes,
+                                    pxz_payload** out) {
+  if (!ctx || !descs || (!pixels && bytes) || !out || n_images == 0) return PXZ_E_ARG;
+  return payload_from_descs(ctx, w, h, bw, bh, channels, descs, pixels, true, bytes, out, n_images);
+}
+
+uint32_t pxz_image_batch_count(const pxz_image* img) { return img ? img->nimg : 0; }
+uint32_t pxz_payload_batch_count(const pxz_payload* p) { return p ? p->g.nimg : 0; }
+
+pxz_status pxz_shrink_batch(pxz_ctx* ctx, const pxz_image* batch, uint32_t bw, uint32_t bh, pxz_metric metric, float factor,
+                            pxz_filter filter_down, uint32_t flags, pxz_payload** out) {
+  // one launch per stage over the tiles of all images: the batch is one block grid (pxz_internal.h, Geom)
+  return pxz_shrink(ctx, batch, bw, bh, metric, factor, filter_down, flags, out);
+}
+
+pxz_status pxz_expand_batch(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, pxz_image* out_batch) {
+  return pxz_expand_to_image(ctx, p, filter_up, out_batch);
+}
+
 // ---- container stage on the device (qoi_device.cu) ------------------------------------------------------------
 pxz_status pxz_payload_to_container(pxz_ctx* ctx, const pxz_payload* p, uint32_t filter_byte, int values_present, uint8_t* host_out,
                                     size_t cap, uint64_t* bytes_out) {
   if (!ctx || !p || !host_out || !bytes_out) return PXZ_E_ARG;
   cudaSetDevice(ctx->device);
+  if (p->g.nimg != 1) return fail(ctx, PXZ_E_UNSUPPORTED, "a container holds one image: not available on a batch");
   uint64_t bytes = 0;
   pxz_status st = payload_bytes(ctx, p, &bytes);
   if (st != PXZ_OK) return st;
@@ -1189,7 +1234,8 @@ pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter fi
   if (!ctx || !p || !out) return PXZ_E_ARG;
   cudaSetDevice(ctx->device);
   if ((int)filter_up < 0 || (int)filter_up > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
-  if (out->w != p->g.W || out->h != p->g.H || out->c != p->g.C) return fail(ctx, PXZ_E_ARG, "output image geometry mismatch");
+  if (out->w != p->g.W || out->h != p->g.H || out->c != p->g.C || out->nimg != p->g.nimg)
+    return fail(ctx, PXZ_E_ARG, "output image geometry mismatch");
   TabSet ts;
   pxz_status st = get_tabset(ctx, *p->spec, p->strategy ? -1 : (int)filter_up, 1, &ts);
   if (st != PXZ_OK) return st;
@@ -1199,7 +1245,7 @@ pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter fi
 pxz_status pxz_expand(pxz_ctx* ctx, const pxz_payload* p, pxz_filter filter_up, uint8_t* host_out, size_t host_pitch) {
   if (!ctx || !p || !host_out) return PXZ_E_ARG;
   pxz_image* im = nullptr;
-  pxz_status st = pxz_image_alloc(ctx, p->g.W, p->g.H, p->g.C, &im);
+  pxz_status st = pxz_image_alloc_batch(ctx, p->g.W, p->g.H, p->g.C, p->g.nimg, &im);
   if (st != PXZ_OK) return st;
   st = pxz_expand_to_image(ctx, p, filter_up, im);
   if (st == PXZ_OK) st = pxz_image_download(ctx, im, host_out, host_pitch);
@@ -1214,6 +1260,7 @@ pxz_status pxz_tree_process(pxz_ctx* ctx, const pxz_image* img, float threshold,
   cudaSetDevice(ctx->device);
   if ((int)filter_down < 0 || (int)filter_down > 4 || (int)filter_up < 0 || (int)filter_up > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
   if (out->w != img->w || out->h != img->h || out->c != img->c) return fail(ctx, PXZ_E_ARG, "output image geometry mismatch");
+  if (img->nimg != 1 || out->nimg != 1) return fail(ctx, PXZ_E_UNSUPPORTED, "tree processing takes one image at a time");
   if (bw == 0 || bh == 0) return fail(ctx, PXZ_E_ARG, "block size must be >= 1");
   // unchanged pixels (blocks that reach the minimum size, tree.rs:35-37) come straight from the source
   PXZ_CUDA(ctx, cudaMemcpy2DAsync(out->d, out->pitch, img->d, img->pitch, (size_t)img->w * img->c, img->h, cudaMemcpyDeviceToDevice,

@@ -130,10 +130,16 @@ struct Tile {
 __device__ __forceinline__ Tile tile_of(const Geom& g, uint32_t b) {
   Tile t;
   uint32_t by = b / g.cols, bx = b - by * g.cols;
+  uint32_t base = 0;
+  if (g.nimg > 1) {  // stacked batch: block row -> (image, block row of that image)
+    const uint32_t im = by / g.rows_img;
+    by -= im * g.rows_img;
+    base = im * g.img_rows;
+  }
   t.x0 = bx * g.bw;
-  t.y0 = by * g.bh;
   t.tw = min(g.bw, g.W - t.x0);  // split.rs:18-19
-  t.th = min(g.bh, g.H - t.y0);
+  t.th = min(g.bh, g.H - by * g.bh);
+  t.y0 = base + by * g.bh;
   return t;
 }
 
@@ -2144,7 +2150,7 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
       bool ring_kernel = prefer == 1;
       if (!ring_kernel) {
         CUtensorMap tm;
-        if (make_image_tmap(img, pitch, g.W, g.H, &tm)) {
+        if (make_image_tmap(img, pitch, g.W, g.nimg > 1 ? (g.nimg - 1) * g.img_rows + g.H : g.H, &tm)) {
           const size_t smem = (size_t)kTWarps * kTWarpBytes;
           const int tgrid = clamp_grid((ntiles + kTWarps - 1) / kTWarps, (long long)sm_count * PXZ_SHRINK_TMA_CTAS);
           if (fused) {

@@ -43,9 +43,13 @@ struct AxisTab {
 };
 
 // Geometry of the block grid over a pitched image.
+// A batch is `nimg` images of one size stacked in one pitched allocation, image i at pixel rows [i * img_rows, ...): the
+// block grid of the batch is the images' grids one below the other, so `rows` counts the block rows of ALL images
+// (cols * rows = blocks of the batch) while H, trail_h and rows_img describe one image.  nimg = 1: a plain image.
 struct Geom {
   uint32_t W, H, bw, bh, cols, rows, C;
   uint32_t trail_w, trail_h;  // W % bw, H % bh (0 = no trailing column / row)
+  uint32_t rows_img, nimg, img_rows;
 };
 
 // How raw metric values become (v0, v1): pixlzr.rs:162 (`x * factor * 10`), :199 (`x * factor`),
