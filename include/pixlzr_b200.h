@@ -89,6 +89,16 @@ uint64_t pxz_launch_count(const pxz_ctx* ctx);
 /* Resample arithmetic of this context.  0 (default): the reference's order — separate multiply and add, no
  * contraction — resampled pixels are bit-identical to the CPU result.  1: fused multiply-add on the RGBA fast paths;
  * faster, dims / offsets / values unchanged, pixels within +-1 LSB of the reference (the bar BASELINE.json states). */
+/* Which branch of PixlzrBlock::resize (src/data_types/block.rs:273-334) the resample kernels compute.
+ *   PXZ_RESIZE_IMAGE_RS (default): the `image` crate branch (block.rs:282-290) — f32, vertical pass first; this is the
+ *       branch the reference's committed fixtures were produced with, reproduced bit for bit.
+ *   PXZ_RESIZE_FIR: the `fast_image_resize` branch (block.rs:292-333 with FilterType::to_fir_resizing_algorithm,
+ *       data_types/mod.rs:65-107), the crate's default cargo feature — 16-bit fixed-point convolution, horizontal pass
+ *       first into a u8 image, Triangle = Hamming when shrinking / Bilinear when growing, pre-multiplied alpha for RGBA.
+ *       Restated from the crate's published algorithm: PARITY UNPINNED (no artefact of the reference was made with it).
+ * Also selectable with PXZ_RESIZE_SEMANTICS=fir in the environment when the context is created. */
+typedef enum { PXZ_RESIZE_IMAGE_RS = 0, PXZ_RESIZE_FIR = 1 } pxz_resize_semantics;
+pxz_status pxz_ctx_set_resize_semantics(pxz_ctx* ctx, pxz_resize_semantics semantics);
 pxz_status pxz_ctx_set_fast_resample(pxz_ctx* ctx, int on);
 /* ---- per-block filter pairs ("strategy") --------------------------------------------------
  * The reference's author measured, per bucket of width 1/64 of the value that enters the level quantiser, which

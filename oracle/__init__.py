@@ -63,6 +63,9 @@ def lib():
         L.pxo_level_exp.restype = C.c_int32
         L.pxo_reduce_dims.argtypes = [C.c_float, C.c_float, C.c_uint32, C.c_uint32, u32p, u32p, f32p]
         L.pxo_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.pxo_resize_fir.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.pxo_set_resize_semantics.argtypes = [C.c_int]
+        L.pxo_set_resize_semantics.restype = None
         L.pxo_axis_weights.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.pxo_analyze.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_size_t, C.c_uint32, C.c_uint32,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -150,6 +153,37 @@ def reduce_dims(v0, v1, w, h):
     ow, oh, st = C.c_uint32(), C.c_uint32(), C.c_float()
     lib().pxo_reduce_dims(v0, v1, w, h, C.byref(ow), C.byref(oh), C.byref(st))
     return ow.value, oh.value, st.value
+
+
+IMAGE_RS, FIR = 0, 1
+
+
+def set_resize_semantics(sem: int) -> None:
+    """Which branch of PixlzrBlock::resize shrink / expand / tree_process use: IMAGE_RS (default, pinned by the reference's
+    fixtures) or FIR (fast_image_resize, the reference's default cargo feature; parity unpinned).  Process-wide."""
+    lib().pxo_set_resize_semantics(int(sem))
+
+
+class resize_semantics:
+    """with O.resize_semantics(O.FIR): ..."""
+
+    def __init__(self, sem: int):
+        self.sem = sem
+
+    def __enter__(self):
+        set_resize_semantics(self.sem)
+
+    def __exit__(self, *a):
+        set_resize_semantics(IMAGE_RS)
+
+
+def resize_fir(block: np.ndarray, nw: int, nh: int, filt: int) -> np.ndarray:
+    block = np.ascontiguousarray(block)
+    h, w, c = block.shape
+    out = np.zeros((nh, nw, c), np.uint8)
+    if lib().pxo_resize_fir(_ptr(block), w, h, c, _ptr(out), nw, nh, filt) != 0:
+        raise ValueError("pxo_resize_fir failed")
+    return out
 
 
 def resize(block: np.ndarray, nw: int, nh: int, filt: int) -> np.ndarray:

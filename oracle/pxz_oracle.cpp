@@ -330,6 +330,163 @@ int resize_image_rs(const uint8_t* src, uint32_t w, uint32_t h, int C, uint8_t* 
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * PixlzrBlock::resize, `fir` branch (block.rs:292-333) — the reference's DEFAULT cargo feature: fast_image_resize
+ * 4.2.1 driven by FilterType::to_fir_resizing_algorithm (data_types/mod.rs:65-107).
+ *
+ * PARITY UNPINNED.  The crate's source is not under /root/reference (Cargo.lock pins fast_image_resize 4.2.1) and no
+ * fixture of the reference was produced with this branch; what follows restates the crate's published algorithm (the
+ * Pillow-SIMD lineage it documents) from the call site's arguments:
+ *   - algorithm: Nearest -> nearest; growing in either axis -> SuperSampling(f, 2), which for an enlargement is a plain
+ *     convolution with f (the pre-shrink only happens when the reduction exceeds 2 x 1.2); otherwise Convolution(f),
+ *     with Triangle -> Bilinear when growing and -> Hamming when shrinking (mod.rs:75-101);
+ *   - coefficients per axis in f64: scale = in / out, filter_scale = max(scale, 1), radius = support * filter_scale,
+ *     centre = (o + 0.5) * scale, taps x in [floor(centre - radius) clamped to 0, ceil(centre + radius) clamped to in),
+ *     w = f((x + 0.5 - centre) / filter_scale), normalised to sum 1;
+ *   - 16-bit fixed point with adaptive precision: the largest p < 22 with round(max_w * 2^(p+1)) < 2^15, coefficient =
+ *     round-half-away(w * 2^p); a sample is clip8((2^(p-1) + sum(pixel * coefficient)) >> p);
+ *   - HORIZONTAL pass first into a u8 image of (new width x old height), then the vertical pass; an axis whose size
+ *     does not change is not convolved;
+ *   - U8x4 with a non-nearest algorithm: alpha is pre-multiplied before and divided out after the resize
+ *     (ResizeOptions::new() has use_alpha = true): c' = mul_div_255(c, a), back = min(255, (c' * 255 + a / 2) / a).
+ * The only constraint the reference's own tests put on it is block.rs:401-435 (constant images stay constant).
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum FirFilter { FIR_BOX = 0, FIR_BILINEAR = 1, FIR_CATMULLROM = 2, FIR_GAUSSIAN = 3, FIR_LANCZOS3 = 4, FIR_HAMMING = 5 };
+
+double fir_sinc(double x) { return x == 0.0 ? 1.0 : sin(x * M_PI) / (x * M_PI); }
+double fir_kernel(int f, double x) {
+  switch (f) {
+    case FIR_BILINEAR: { x = fabs(x); return x < 1.0 ? 1.0 - x : 0.0; }
+    case FIR_HAMMING: {
+      x = fabs(x);
+      if (x == 0.0) return 1.0;
+      if (x >= 1.0) return 0.0;
+      x *= M_PI;
+      return (0.54 + 0.46 * cos(x)) * sin(x) / x;
+    }
+    case FIR_CATMULLROM: {
+      const double a = -0.5;
+      x = fabs(x);
+      if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0;
+      if (x < 2.0) return (((x - 5.0) * x + 8.0) * x - 4.0) * a;
+      return 0.0;
+    }
+    case FIR_GAUSSIAN: {
+      if (fabs(x) >= 3.0) return 0.0;
+      const double r = 0.5;
+      return exp(-(x * x) / (2.0 * r * r)) / (sqrt(2.0 * M_PI) * r);
+    }
+    case FIR_LANCZOS3: return (x >= -3.0 && x < 3.0) ? fir_sinc(x) * fir_sinc(x / 3.0) : 0.0;
+  }
+  return 0.0;
+}
+double fir_support(int f) { return f == FIR_CATMULLROM ? 2.0 : (f == FIR_GAUSSIAN || f == FIR_LANCZOS3) ? 3.0 : 1.0; }
+
+struct FirAxis { std::vector<uint32_t> left, count; std::vector<int32_t> k; uint32_t stride; int precision; };
+
+void fir_axis(uint32_t n_in, uint32_t n_out, int f, FirAxis* t) {
+  const double scale = (double)n_in / (double)n_out, fscale = scale > 1.0 ? scale : 1.0, radius = fir_support(f) * fscale;
+  t->left.assign(n_out, 0); t->count.assign(n_out, 0);
+  std::vector<std::vector<double>> w(n_out);
+  double maxw = 0.0;
+  uint32_t stride = 1;
+  for (uint32_t o = 0; o < n_out; ++o) {
+    const double centre = ((double)o + 0.5) * scale;
+    double lo = floor(centre - radius), hi = ceil(centre + radius);
+    if (lo < 0.0) lo = 0.0;
+    if (hi > (double)n_in) hi = (double)n_in;
+    const uint32_t x0 = (uint32_t)lo, x1 = (uint32_t)hi;
+    double ww = 0.0;
+    for (uint32_t x = x0; x < x1; ++x) { const double v = fir_kernel(f, ((double)x + 0.5 - centre) / fscale); w[o].push_back(v); ww += v; }
+    if (ww != 0.0) for (double& v : w[o]) v /= ww;
+    for (double v : w[o]) maxw = std::max(maxw, v);
+    t->left[o] = x0; t->count[o] = x1 - x0;
+    stride = std::max(stride, x1 - x0);
+  }
+  int p = 0;
+  for (p = 0; p < 22; ++p) { if ((int)lround(maxw * (double)(1 << (p + 1))) >= (1 << 15)) break; }
+  t->precision = p; t->stride = stride;
+  t->k.assign((size_t)n_out * stride, 0);
+  for (uint32_t o = 0; o < n_out; ++o)
+    for (size_t i = 0; i < w[o].size(); ++i) t->k[(size_t)o * stride + i] = (int32_t)lround(w[o][i] * (double)(1 << p));
+}
+
+inline uint8_t fir_clip8(int32_t v, int p) { v >>= p; return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
+inline uint8_t mul_div_255(uint32_t a, uint32_t b) { const uint32_t t = a * b + 128; return (uint8_t)(((t >> 8) + t) >> 8); }
+
+int resize_fir(const uint8_t* src, uint32_t w, uint32_t h, int C, uint8_t* dst, uint32_t nw, uint32_t nh, int filter) {
+  if (w == 0 || h == 0 || nw == 0 || nh == 0) return -1;
+  if (w == nw && h == nh) { memcpy(dst, src, (size_t)w * h * C); return 0; } /* block.rs:279-281 */
+  if (filter == PXO_NEAREST) { /* ResizeAlg::Nearest */
+    const double xs = (double)w / nw, ys = (double)h / nh;
+    for (uint32_t y = 0; y < nh; ++y) {
+      const uint32_t sy = std::min(h - 1, (uint32_t)(ys * 0.5 + ys * y));
+      for (uint32_t x = 0; x < nw; ++x) {
+        const uint32_t sx = std::min(w - 1, (uint32_t)(xs * 0.5 + xs * x));
+        memcpy(dst + ((size_t)y * nw + x) * C, src + ((size_t)sy * w + sx) * C, C);
+      }
+    }
+    return 0;
+  }
+  const bool upscale = nw > w || nh > h; /* block.rs:302 */
+  int f;
+  switch (filter) {
+    case PXO_TRIANGLE: f = upscale ? FIR_BILINEAR : FIR_HAMMING; break;
+    case PXO_CATMULLROM: f = FIR_CATMULLROM; break;
+    case PXO_GAUSSIAN: f = FIR_GAUSSIAN; break;
+    case PXO_LANCZOS3: f = FIR_LANCZOS3; break;
+    default: return -1;
+  }
+  std::vector<uint8_t> in(src, src + (size_t)w * h * C);
+  if (C == 4)
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+      const uint32_t a = in[i * 4 + 3];
+      for (int c = 0; c < 3; ++c) in[i * 4 + c] = mul_div_255(in[i * 4 + c], a);
+    }
+  std::vector<uint8_t> tmp;
+  const uint8_t* hsrc = in.data();
+  if (nw != w) {
+    FirAxis tx;
+    fir_axis(w, nw, f, &tx);
+    tmp.resize((size_t)nw * h * C);
+    for (uint32_t y = 0; y < h; ++y)
+      for (uint32_t x = 0; x < nw; ++x)
+        for (int c = 0; c < C; ++c) {
+          int32_t ss = 1 << (tx.precision - 1);
+          for (uint32_t i = 0; i < tx.count[x]; ++i) ss += (int32_t)in[((size_t)y * w + tx.left[x] + i) * C + c] * tx.k[(size_t)x * tx.stride + i];
+          tmp[((size_t)y * nw + x) * C + c] = fir_clip8(ss, tx.precision);
+        }
+    hsrc = tmp.data();
+  }
+  std::vector<uint8_t> out((size_t)nw * nh * C);
+  if (nh != h) {
+    FirAxis ty;
+    fir_axis(h, nh, f, &ty);
+    for (uint32_t y = 0; y < nh; ++y)
+      for (uint32_t x = 0; x < nw; ++x)
+        for (int c = 0; c < C; ++c) {
+          int32_t ss = 1 << (ty.precision - 1);
+          for (uint32_t i = 0; i < ty.count[y]; ++i) ss += (int32_t)hsrc[((size_t)(ty.left[y] + i) * nw + x) * C + c] * ty.k[(size_t)y * ty.stride + i];
+          out[((size_t)y * nw + x) * C + c] = fir_clip8(ss, ty.precision);
+        }
+  } else {
+    memcpy(out.data(), hsrc, out.size());
+  }
+  if (C == 4)
+    for (size_t i = 0; i < (size_t)nw * nh; ++i) {
+      const uint32_t a = out[i * 4 + 3];
+      for (int c = 0; c < 3; ++c) out[i * 4 + c] = a == 0 ? 0 : (uint8_t)std::min<uint32_t>(255u, (out[i * 4 + c] * 255u + a / 2) / a);
+    }
+  memcpy(dst, out.data(), out.size());
+  return 0;
+}
+
+/* which branch of PixlzrBlock::resize the drivers below use: 0 = image crate (pinned), 1 = fast_image_resize (unpinned) */
+int g_resize_semantics = 0;
+inline int resize_block(const uint8_t* src, uint32_t w, uint32_t h, int C, uint8_t* dst, uint32_t nw, uint32_t nh, int filter) {
+  return g_resize_semantics ? resize_fir(src, w, h, C, dst, nw, nh, filter) : resize_image_rs(src, w, h, C, dst, nw, nh, filter);
+}
+
 inline uint32_t ceil_div_f64(uint32_t a, uint32_t b) { /* split.rs:45-46 (f64 ceil) */
   return (uint32_t)ceil((double)a / (double)b);
 }
@@ -501,6 +658,11 @@ void pxo_reduce_dims(float v0, float v1, uint32_t w, uint32_t h, uint32_t* ow, u
 int pxo_resize(const uint8_t* src, uint32_t w, uint32_t h, int channels, uint8_t* dst, uint32_t nw, uint32_t nh, int filter) {
   return resize_image_rs(src, w, h, channels, dst, nw, nh, filter);
 }
+int pxo_resize_fir(const uint8_t* src, uint32_t w, uint32_t h, int channels, uint8_t* dst, uint32_t nw, uint32_t nh, int filter) {
+  return resize_fir(src, w, h, channels, dst, nw, nh, filter);
+}
+void pxo_set_resize_semantics(int fir) { g_resize_semantics = fir ? 1 : 0; }
+int pxo_get_resize_semantics(void) { return g_resize_semantics; }
 
 int pxo_axis_weights(uint32_t n, uint32_t nn, int filter, uint32_t* left, uint32_t* count, float* weights, uint32_t max_taps) {
   Filter flt;
@@ -615,7 +777,7 @@ static int64_t shrink_impl(const uint8_t* img, uint32_t w, uint32_t h, int C, si
     for (uint32_t y = 0; y < th[bi]; ++y)
       memcpy(&blk[(size_t)y * tw[bi] * C], img + (size_t)(by * bh + y) * pitch + (size_t)bx * bw * C, (size_t)tw[bi] * C);
     const int filt = down_by_bucket ? down_by_bucket[pxo_strategy_bucket(descs[bi].value)] : filter_down;
-    if (resize_image_rs(blk.data(), tw[bi], th[bi], C, payload + descs[bi].offset, ow[bi], oh[bi], filt) != 0) {
+    if (resize_block(blk.data(), tw[bi], th[bi], C, payload + descs[bi].offset, ow[bi], oh[bi], filt) != 0) {
 #ifdef _OPENMP
 #pragma omp atomic write
 #endif
@@ -656,7 +818,7 @@ static int expand_impl(const pxo_block_desc* descs, const uint8_t* payload, uint
     const uint32_t nh = (by == rows - 1 && trail_h > 0) ? trail_h : bh; /* :92-96 */
     std::vector<uint8_t> blk((size_t)nw * nh * C);
     const int filt = up_by_bucket ? up_by_bucket[pxo_strategy_bucket(descs[bi].value)] : filter_up;
-    if (resize_image_rs(payload + descs[bi].offset, descs[bi].w, descs[bi].h, C, blk.data(), nw, nh, filt) != 0) {
+    if (resize_block(payload + descs[bi].offset, descs[bi].w, descs[bi].h, C, blk.data(), nw, nh, filt) != 0) {
 #ifdef _OPENMP
 #pragma omp atomic write
 #endif
@@ -702,9 +864,9 @@ static std::vector<uint8_t> tree_rec(const std::vector<uint8_t>& img, uint32_t w
         uint32_t ow, oh;
         pxo_reduce_dims(value, value, w0, h0, &ow, &oh, nullptr);
         std::vector<uint8_t> small((size_t)ow * oh * C);
-        resize_image_rs(blk.data(), w0, h0, C, small.data(), ow, oh, fdown);
+        resize_block(blk.data(), w0, h0, C, small.data(), ow, oh, fdown);
         res.resize((size_t)w0 * h0 * C);
-        resize_image_rs(small.data(), ow, oh, C, res.data(), w0, h0, fup);
+        resize_block(small.data(), ow, oh, C, res.data(), w0, h0, fup);
       } else {
         /* :68-76 — note that the recursion receives the ABSOLUTE threshold */
         res = tree_rec(blk, w0, h0, C, thr, bw >> 1, bh >> 1, mbw, mbh, fdown, fup);

@@ -16,8 +16,9 @@
  *     unpinned (restated from the `image` 0.25.5 algorithm).
  *   - container v0.0.2 + QOI (qoi 0.4.1 incl. its run-of-1 quirk): PINNED byte-exact by
  *     benches/base.pixlzr and Big-Ruscher.pix.
- *   - `fast_image_resize` branch (the reference's default cargo feature): NOT restated;
- *     parity unpinned (no fixture, source not available).
+ *   - `fast_image_resize` branch (the reference's default cargo feature, block.rs:292-333): restated from the
+ *     crate's published algorithm (pxo_resize_fir, pxo_set_resize_semantics); PARITY UNPINNED — no fixture was made
+ *     with it and its source is not under /root/reference; only block.rs:401-435 constrains it.
  */
 #ifndef PXZ_ORACLE_H
 #define PXZ_ORACLE_H
@@ -57,6 +58,13 @@ void pxo_reduce_dims(float v0, float v1, uint32_t w, uint32_t h, uint32_t* ow, u
 /* PixlzrBlock::resize, image-crate branch (block.rs:273-290). src/dst tightly packed. */
 int pxo_resize(const uint8_t* src, uint32_t w, uint32_t h, int channels, uint8_t* dst,
                uint32_t nw, uint32_t nh, int filter);
+/* PixlzrBlock::resize, fast_image_resize branch (block.rs:292-333, data_types/mod.rs:65-107): parity unpinned. */
+int pxo_resize_fir(const uint8_t* src, uint32_t w, uint32_t h, int channels, uint8_t* dst,
+                   uint32_t nw, uint32_t nh, int filter);
+/* which branch the drivers (shrink / expand / tree) use: 0 = image crate (default, pinned), 1 = fast_image_resize.
+   Process-wide, not thread-safe: set it between calls. */
+void pxo_set_resize_semantics(int fir);
+int pxo_get_resize_semantics(void);
 /* normalised f32 weight table of one axis (image 0.25.5 sample loops): for each output o,
    left[o], count[o] and weights (row stride = max_taps). returns max taps or <0 */
 int pxo_axis_weights(uint32_t n, uint32_t nn, int filter, uint32_t* left, uint32_t* count,

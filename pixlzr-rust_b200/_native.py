@@ -19,6 +19,7 @@ STATUS_NAMES = {0: "PXZ_OK", -1: "PXZ_E_ARG", -2: "PXZ_E_CUDA", -3: "PXZ_E_OOM",
 METRIC_OKLAB_MAD, METRIC_SOBEL_DIR = 0, 1
 FLAG_AFTER_IDENTITY, FLAG_NORMALISE_GLOBAL, FLAG_EXACT_VALUES = 1, 2, 4
 COMM_ID_BYTES = 128
+RESIZE_IMAGE_RS, RESIZE_FIR = 0, 1
 
 DESC_DTYPE = np.dtype([("offset", "<u8"), ("value", "<f4"), ("w", "<u2"), ("h", "<u2")])
 assert DESC_DTYPE.itemsize == 16
@@ -36,6 +37,7 @@ SYMBOLS = {
     "pxz_synchronize": (_i, [_vp]),
     "pxz_launch_count": (_u64, [_vp]),
     "pxz_ctx_set_fast_resample": (_i, [_vp, _i]),
+    "pxz_ctx_set_resize_semantics": (_i, [_vp, _i]),
     "pxz_strategy_bucket": (_u32, [C.c_float]),
     "pxz_strategy_by_level": (_i, [_vp]),
     "pxz_ctx_set_strategy": (_i, [_vp, _vp]),
@@ -221,6 +223,11 @@ class Context:
             out[name.decode()] = (ms.value, n.value)
             i += 1
         return out
+
+    def set_resize_semantics(self, semantics: int):
+        """RESIZE_IMAGE_RS (default, pinned by the reference's fixtures) or RESIZE_FIR (the reference's default cargo
+        feature; parity unpinned)."""
+        self.check(lib().pxz_ctx_set_resize_semantics(self._h, int(semantics)))
 
     def comm_join_empty(self):
         """The exchange of one PXZ_FLAG_NORMALISE_GLOBAL shrink for a rank whose shard has no block rows."""

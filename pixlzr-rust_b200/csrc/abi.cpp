@@ -95,6 +95,7 @@ struct pxz_ctx {
   std::map<TabKey, TabSet> tabs;
   void* comm = nullptr;
   bool fast_resample = false;
+  int resize_semantics = PXZ_RESIZE_IMAGE_RS;  // which branch of PixlzrBlock::resize (pxz_ctx_set_resize_semantics)
   std::vector<PayloadBufs> payload_cache;  // at most kPayloadCacheMax entries
   // per-kernel timing
   bool profiling = false;
@@ -261,7 +262,8 @@ std::shared_ptr<TabSpec> spec_for_geom(const Geom& g) {
 
 // direction 0: tile -> reduced (filter_down); 1: reduced -> tile (filter_up)
 pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int direction, TabSet* out) {
-  TabKey key(spec.n_small, spec.n_tile, filter, direction);
+  const bool fir = ctx->resize_semantics == PXZ_RESIZE_FIR;
+  TabKey key(spec.n_small, spec.n_tile, filter, direction + (fir ? 2 : 0));
   auto it = ctx->tabs.find(key);
   if (it != ctx->tabs.end()) {
     *out = it->second;
@@ -284,7 +286,15 @@ pxz_status get_tabset(pxz_ctx* ctx, const TabSpec& spec, int filter, int directi
         t = s->second;
         continue;
       }
-      if (!build_axis_table(n_in, n_out, f, &pool, &t)) return fail(ctx, PXZ_E_ARG, "bad resample table request");
+      if (fir) {
+        // FilterType::to_fir_resizing_algorithm (data_types/mod.rs:65-107): Triangle is Hamming when a block shrinks and
+        // Bilinear when it grows; the other filters keep their kernel, Nearest stays nearest
+        const int alg = f == PXZ_NEAREST ? PXZ_FIR_NEAREST : f == PXZ_TRIANGLE ? (direction == 0 ? PXZ_FIR_HAMMING : PXZ_FIR_BILINEAR)
+                        : f == PXZ_CATMULLROM ? PXZ_FIR_CATMULLROM : f == PXZ_GAUSSIAN ? PXZ_FIR_GAUSSIAN : PXZ_FIR_LANCZOS3;
+        if (!build_axis_table_fir(n_in, n_out, alg, &pool, &t)) return fail(ctx, PXZ_E_ARG, "bad resample table request");
+      } else if (!build_axis_table(n_in, n_out, f, &pool, &t)) {
+        return fail(ctx, PXZ_E_ARG, "bad resample table request");
+      }
       seen[{n_in, n_out}] = t;
     }
   }
@@ -332,6 +342,17 @@ pxz_status run_resample(pxz_ctx* ctx, int direction, uint8_t* img, size_t pitch,
                         uint32_t max_src_px, uint32_t max_src_dim, uint32_t max_tmp_px, const uint8_t* opaque_flags = nullptr) {
   const Geom& g = p->g;
   const uint32_t nblocks = g.cols * g.rows;
+  if (ctx->resize_semantics == PXZ_RESIZE_FIR) {
+    // integer convolution, horizontal pass first: its own kernel (one CTA per block, source + u8 intermediate in smem)
+    const uint32_t tmp_px = max_src_dim * std::max(g.bw, max_src_dim);  // source rows x widest destination row
+    const size_t fsmem = resample_fir_smem_bytes(max_src_px, tmp_px, g.C);
+    if (fsmem > ctx->max_smem_optin) return fail(ctx, PXZ_E_UNSUPPORTED, "blocks too large for the fir resize path");
+    ProfScope prof(ctx, direction == 0 ? K_RESAMPLE_DOWN : K_RESAMPLE_UP);
+    const uint32_t* tabidx = (direction == 1 && p->strategy == 1) ? p->d_up() : p->d_tabidx;
+    PXZ_CUDA(ctx, launch_resample_fir(direction, img, pitch, g, p->d_descs, tabidx, p->d_pixels, ts.d_tabs, ts.d_pool, fsmem,
+                                      (uint32_t)(((size_t)max_src_px * g.C + 15) & ~(size_t)15), ctx->stream, ctx->sm_count, &ctx->launches));
+    return PXZ_OK;
+  }
   size_t smem = resample_smem_bytes(max_src_px, max_tmp_px, g.C);
   int grid = resample_grid(ctx->sm_count, nblocks);
   uint8_t* scratch = nullptr;
@@ -417,6 +438,7 @@ pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx*
   ctx->band.abs_raw = 8.0e-6f; // fast arithmetic, absolute (SFU cube roots; measured <= 4e-6)
   if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
   if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
+  if (const char* e = getenv("PXZ_RESIZE_SEMANTICS")) ctx->resize_semantics = !strcmp(e, "fir") ? PXZ_RESIZE_FIR : PXZ_RESIZE_IMAGE_RS;
   if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->resample_kernels = !strcmp(e, "warp") ? 1 : !strcmp(e, "cta") ? 2 : !strcmp(e, "tma") ? 3 : 0;
   if (cudaMalloc((void**)&ctx->d_minmax, 8 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_tile_counter, 64) != cudaSuccess || cudaMemset(ctx->d_tile_counter, 0, 64) != cudaSuccess ||
@@ -491,6 +513,13 @@ pxz_status pxz_synchronize(pxz_ctx* ctx) {
 }
 
 uint64_t pxz_launch_count(const pxz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+pxz_status pxz_ctx_set_resize_semantics(pxz_ctx* ctx, pxz_resize_semantics semantics) {
+  if (!ctx) return PXZ_E_ARG;
+  if (semantics != PXZ_RESIZE_IMAGE_RS && semantics != PXZ_RESIZE_FIR) return fail(ctx, PXZ_E_ARG, "unknown resize semantics");
+  ctx->resize_semantics = (int)semantics;
+  return PXZ_OK;
+}
 
 pxz_status pxz_ctx_set_fast_resample(pxz_ctx* ctx, int on) {
   if (!ctx) return PXZ_E_ARG;

@@ -1915,6 +1915,126 @@ __global__ void __launch_bounds__(kThreads) k_tree_mask(const float* __restrict_
   recurse[b] = (uint8_t)(active && !reduce);
 }
 
+// ------------------------------------------------------------------------------------------------
+// `fir` resize semantics (PixlzrBlock::resize with the fast_image_resize feature, block.rs:292-333): integer
+// convolution with 16-bit coefficients (tables.cpp build_axis_table_fir), HORIZONTAL pass first into a u8 image, then the
+// vertical pass; an axis that keeps its size is not convolved; RGBA with a non-nearest algorithm runs on alpha
+// pre-multiplied samples.  One CTA per block, source and intermediate in shared memory.  Bit-exact against the oracle's
+// restatement by construction (integer arithmetic); "parity unpinned" against the crate itself.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mul_div_255_dev(uint32_t a, uint32_t b) {
+  const uint32_t t = a * b + 128u;
+  return ((t >> 8) + t) >> 8;
+}
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_resample_fir(int direction, uint8_t* __restrict__ img, size_t pitch, Geom g,
+                                                           const pxz_block_desc* __restrict__ descs, const uint32_t* __restrict__ tabidx,
+                                                           uint8_t* __restrict__ payload, const AxisTab* __restrict__ tabs,
+                                                           const uint32_t* __restrict__ pool, uint32_t src_cap_bytes) {
+  extern __shared__ uint8_t s_fir[];
+  uint8_t* s_src = s_fir;
+  uint8_t* s_tmp = s_fir + src_cap_bytes;
+  const uint32_t nblocks = g.cols * g.rows;
+  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const pxz_block_desc d = descs[b];
+    if (d.w == 0 || d.h == 0) continue;  // masked out
+    const Tile t = tile_of(g, b);
+    uint8_t* tile0 = img + (size_t)t.y0 * pitch + (size_t)t.x0 * C;
+    uint8_t* blk = payload + d.offset;
+    const uint32_t sw = direction == 0 ? t.tw : d.w, sh = direction == 0 ? t.th : d.h;
+    const uint32_t dw = direction == 0 ? d.w : t.tw, dh = direction == 0 ? d.h : t.th;
+    const uint8_t* src = direction == 0 ? tile0 : blk;
+    const size_t sstride = direction == 0 ? pitch : (size_t)sw * C;
+    uint8_t* dst = direction == 0 ? blk : tile0;
+    const size_t dstride = direction == 0 ? (size_t)dw * C : pitch;
+    if (sw == dw && sh == dh) {  // block.rs:279-281: clone
+      for (uint32_t i = threadIdx.x; i < sh * sw * C; i += kThreads) {
+        const uint32_t y = i / (sw * C), x = i - y * (sw * C);
+        dst[(size_t)y * dstride + x] = src[(size_t)y * sstride + x];
+      }
+      continue;
+    }
+    const uint32_t ti = tabidx[b];
+    const AxisTab tx = tabs[ti & 0xFFFFu], ty = tabs[ti >> 16];
+    const bool premul = C == 4 && !(tx.pad2_ & kFirNearestFlag);
+    __syncthreads();  // the previous block's passes are done with the buffers
+    for (uint32_t i = threadIdx.x; i < sw * sh; i += kThreads) {
+      const uint32_t y = i / sw, x = i - y * sw;
+      const uint8_t* p = src + (size_t)y * sstride + (size_t)x * C;
+      uint32_t c0 = p[0], c1 = p[1], c2 = p[2];
+      if (C == 4) {
+        const uint32_t a = p[3];
+        if (premul) { c0 = mul_div_255_dev(c0, a); c1 = mul_div_255_dev(c1, a); c2 = mul_div_255_dev(c2, a); }
+        s_src[(size_t)i * 4 + 3] = (uint8_t)a;
+      }
+      s_src[(size_t)i * C] = (uint8_t)c0; s_src[(size_t)i * C + 1] = (uint8_t)c1; s_src[(size_t)i * C + 2] = (uint8_t)c2;
+    }
+    __syncthreads();
+    const uint8_t* hsrc = s_src;  // [sh][dw] after the horizontal pass
+    if (sw != dw) {
+      const uint32_t* left = pool + tx.off;
+      const uint32_t* cnt = left + dw;
+      const int32_t* kk = reinterpret_cast<const int32_t*>(cnt + dw);
+      const int p = (int)(tx.pad2_ & 0xFFu);
+      for (uint32_t i = threadIdx.x; i < sh * dw; i += kThreads) {
+        const uint32_t y = i / dw, x = i - y * dw;
+        const uint32_t l = left[x], n = cnt[x];
+        const int32_t* kr = kk + (size_t)x * tx.stride;
+        int32_t ss[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ss[c] = 1 << (p - 1);
+        const uint8_t* q = s_src + ((size_t)y * sw + l) * C;
+        for (uint32_t j = 0; j < n; ++j) {
+          const int32_t k = kr[j];
+#pragma unroll
+          for (int c = 0; c < C; ++c) ss[c] += (int32_t)q[j * C + c] * k;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_tmp[(size_t)i * C + c] = (uint8_t)min(255, max(0, ss[c] >> p));
+      }
+      hsrc = s_tmp;
+      __syncthreads();
+    }
+    {
+      const uint32_t* left = pool + ty.off;
+      const uint32_t* cnt = left + dh;
+      const int32_t* kk = reinterpret_cast<const int32_t*>(cnt + dh);
+      const int p = (int)(ty.pad2_ & 0xFFu);
+      const bool vert = sh != dh;
+      for (uint32_t i = threadIdx.x; i < dh * dw; i += kThreads) {
+        const uint32_t y = i / dw, x = i - y * dw;
+        uint32_t o[4] = {0, 0, 0, 255};
+        if (vert) {
+          const uint32_t l = left[y], n = cnt[y];
+          const int32_t* kr = kk + (size_t)y * ty.stride;
+          int32_t ss[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) ss[c] = 1 << (p - 1);
+          for (uint32_t j = 0; j < n; ++j) {
+            const int32_t k = kr[j];
+            const uint8_t* q = hsrc + ((size_t)(l + j) * dw + x) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) ss[c] += (int32_t)q[c] * k;
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) o[c] = (uint32_t)min(255, max(0, ss[c] >> p));
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) o[c] = hsrc[((size_t)y * dw + x) * C + c];
+        }
+        if (premul) {
+          const uint32_t a = o[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) o[c] = a == 0 ? 0u : min(255u, (o[c] * 255u + a / 2) / a);
+        }
+        uint8_t* out = dst + (size_t)y * dstride + (size_t)x * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = (uint8_t)o[c];
+      }
+    }
+  }
+}
+
 #ifndef PXZ_SHRINK_WARP_CTAS
 #define PXZ_SHRINK_WARP_CTAS 3
 #endif
@@ -2222,6 +2342,28 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
     if (e != cudaSuccess) return e;
     k_resample<3><<<grid, kThreads, smem, s>>>(direction, img, pitch, g, descs, tabidx, payload, tabs, pool, max_src_px,
                                               max_tmp_px, scratch, scratch_per_cta);
+  }
+  return cudaGetLastError();
+}
+
+size_t resample_fir_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C) {
+  return (((size_t)max_src_px * C + 15) & ~(size_t)15) + (size_t)max_tmp_px * C;
+}
+
+cudaError_t launch_resample_fir(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
+                                const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool, size_t smem,
+                                uint32_t src_cap_bytes, cudaStream_t s, int sm_count, uint64_t* launches) {
+  ++*launches;
+  const int grid = clamp_grid((long long)g.cols * g.rows, (long long)sm_count * 8);
+  cudaError_t e;
+  if (g.C == 4) {
+    e = set_smem(k_resample_fir<4>, smem);
+    if (e != cudaSuccess) return e;
+    k_resample_fir<4><<<grid, kThreads, smem, s>>>(direction, img, pitch, g, descs, tabidx, payload, tabs, pool, src_cap_bytes);
+  } else {
+    e = set_smem(k_resample_fir<3>, smem);
+    if (e != cudaSuccess) return e;
+    k_resample_fir<3><<<grid, kThreads, smem, s>>>(direction, img, pitch, g, descs, tabidx, payload, tabs, pool, src_cap_bytes);
   }
   return cudaGetLastError();
 }

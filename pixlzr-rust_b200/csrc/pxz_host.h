@@ -13,6 +13,7 @@ namespace pxz {
 
 // tables.cpp
 bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uint32_t>* pool, AxisTab* tab);
+bool build_axis_table_fir(uint32_t n_in, uint32_t n_out, int alg, std::vector<uint32_t>* pool, AxisTab* tab);
 void build_level_thresholds(LevelThresholds* out);
 
 // nccl_dyn.cpp — NCCL is loaded lazily (dlopen) so the library has no link-time dependency on it

@@ -42,6 +42,9 @@ struct AxisTab {
   uint32_t bpad, s2off, s2words, pad2_;  // s2off / s2words: slide2 form (tables.cpp), 0 words = none
 };
 
+// fast_image_resize filter kernels (tables.cpp build_axis_table_fir; data_types/mod.rs:65-107 picks them)
+enum { PXZ_FIR_NEAREST = 0, PXZ_FIR_BILINEAR = 1, PXZ_FIR_CATMULLROM = 2, PXZ_FIR_GAUSSIAN = 3, PXZ_FIR_LANCZOS3 = 4, PXZ_FIR_HAMMING = 5 };
+
 // Geometry of the block grid over a pitched image.
 // A batch is `nimg` images of one size stacked in one pitched allocation, image i at pixel rows [i * img_rows, ...): the
 // block grid of the batch is the images' grids one below the other, so `rows` counts the block rows of ALL images
@@ -144,6 +147,12 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                             uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, int prefer, bool has_noslide,
                             cudaStream_t s, int sm_count, uint64_t* launches);
 size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
+// `fir` resize semantics (integer convolution, horizontal pass first, pre-multiplied alpha): one CTA per block
+size_t resample_fir_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
+cudaError_t launch_resample_fir(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
+                                const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool, size_t smem,
+                                uint32_t src_cap_bytes, cudaStream_t s, int sm_count, uint64_t* launches);
+constexpr uint32_t kFirNearestFlag = 0x100u;  // AxisTab::pad2_ of a fir table: precision | this flag for ResizeAlg::Nearest
 int resample_grid(int sm_count, uint32_t nblocks);
 
 }  // namespace pxz

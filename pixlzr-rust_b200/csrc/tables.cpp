@@ -255,6 +255,97 @@ bool build_axis_table(uint32_t n_in, uint32_t n_out, int filter, std::vector<uin
   return true;
 }
 
+// ---- fast_image_resize 4.2.1 semantics (PixlzrBlock::resize, `fir` branch, block.rs:292-333) -----------------------
+// The crate is not in the reference tree (Cargo.lock pins it): this follows its published algorithm — f64 weights,
+// radius = support * max(scale, 1), taps [floor(centre - radius), ceil(centre + radius)) clamped to the axis, weights
+// normalised to sum 1 and converted to 16-bit fixed point with the largest precision p < 22 for which
+// round(max_w * 2^(p+1)) < 2^15.  "parity unpinned": no artefact of the reference was produced with this branch.
+// Table at `off`: left[n_out] | count[n_out] | coefficient[n_out * stride] (i16 values in 32-bit words); tab->pad2_ = p.
+namespace {
+double fir_sinc(double x) { return x == 0.0 ? 1.0 : sin(x * M_PI) / (x * M_PI); }
+double fir_eval(int alg, double x) {
+  switch (alg) {
+    case PXZ_FIR_BILINEAR: x = fabs(x); return x < 1.0 ? 1.0 - x : 0.0;
+    case PXZ_FIR_HAMMING:
+      x = fabs(x);
+      if (x == 0.0) return 1.0;
+      if (x >= 1.0) return 0.0;
+      x *= M_PI;
+      return (0.54 + 0.46 * cos(x)) * sin(x) / x;
+    case PXZ_FIR_CATMULLROM: {
+      const double a = -0.5;
+      x = fabs(x);
+      if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0;
+      if (x < 2.0) return (((x - 5.0) * x + 8.0) * x - 4.0) * a;
+      return 0.0;
+    }
+    case PXZ_FIR_GAUSSIAN: {
+      if (fabs(x) >= 3.0) return 0.0;
+      const double r = 0.5;
+      return exp(-(x * x) / (2.0 * r * r)) / (sqrt(2.0 * M_PI) * r);
+    }
+    case PXZ_FIR_LANCZOS3: return (x >= -3.0 && x < 3.0) ? fir_sinc(x) * fir_sinc(x / 3.0) : 0.0;
+  }
+  return 0.0;
+}
+}  // namespace
+
+bool build_axis_table_fir(uint32_t n_in, uint32_t n_out, int alg, std::vector<uint32_t>* pool, AxisTab* tab) {
+  if (n_in == 0 || n_out == 0 || alg < PXZ_FIR_NEAREST || alg > PXZ_FIR_HAMMING) return false;
+  memset(tab, 0, sizeof(*tab));
+  tab->n_in = n_in;
+  tab->n_out = n_out;
+  tab->goff = 0xFFFFFFFFu;
+  std::vector<uint32_t> lefts(n_out), counts(n_out);
+  std::vector<std::vector<double>> w(n_out);
+  const double scale = (double)n_in / (double)n_out;
+  double maxw = 0.0;
+  uint32_t stride = 1;
+  if (alg == PXZ_FIR_NEAREST) {
+    // ResizeAlg::Nearest: source sample (scale / 2 + scale * o) truncated; one tap of weight 1
+    for (uint32_t o = 0; o < n_out; ++o) {
+      uint32_t x = (uint32_t)(scale * 0.5 + scale * (double)o);
+      if (x > n_in - 1) x = n_in - 1;
+      lefts[o] = x; counts[o] = 1; w[o].assign(1, 1.0);
+    }
+    maxw = 1.0;
+  } else {
+    const double support = alg == PXZ_FIR_CATMULLROM ? 2.0 : (alg == PXZ_FIR_GAUSSIAN || alg == PXZ_FIR_LANCZOS3) ? 3.0 : 1.0;
+    const double fscale = scale > 1.0 ? scale : 1.0, radius = support * fscale;
+    for (uint32_t o = 0; o < n_out; ++o) {
+      const double centre = ((double)o + 0.5) * scale;
+      double lo = floor(centre - radius), hi = ceil(centre + radius);
+      if (lo < 0.0) lo = 0.0;
+      if (hi > (double)n_in) hi = (double)n_in;
+      const uint32_t x0 = (uint32_t)lo, x1 = (uint32_t)hi;
+      double ww = 0.0;
+      for (uint32_t x = x0; x < x1; ++x) {
+        const double v = fir_eval(alg, ((double)x + 0.5 - centre) / fscale);
+        w[o].push_back(v);
+        ww += v;
+      }
+      if (ww != 0.0)
+        for (double& v : w[o]) v /= ww;
+      for (double v : w[o]) maxw = std::max(maxw, v);
+      lefts[o] = x0; counts[o] = x1 - x0;
+      stride = std::max(stride, x1 - x0);
+    }
+  }
+  int p = 0;
+  for (p = 0; p < 22; ++p)
+    if ((int)lround(maxw * (double)(1 << (p + 1))) >= (1 << 15)) break;
+  tab->stride = stride;
+  tab->pad2_ = (uint32_t)p | (alg == PXZ_FIR_NEAREST ? kFirNearestFlag : 0u);
+  tab->off = (uint32_t)pool->size();
+  pool->insert(pool->end(), lefts.begin(), lefts.end());
+  pool->insert(pool->end(), counts.begin(), counts.end());
+  const size_t kbase = pool->size();
+  pool->resize(kbase + (size_t)n_out * stride, 0u);
+  for (uint32_t o = 0; o < n_out; ++o)
+    for (size_t i = 0; i < w[o].size(); ++i) (*pool)[kbase + (size_t)o * stride + i] = (uint32_t)(int32_t)lround(w[o][i] * (double)(1 << p));
+  return true;
+}
+
 // thr[k] = smallest positive f32 v with round(log2f(v)) >= -k  (round = half away from zero).
 // Built with the host libm exactly as the reference evaluates `value.log2().round()`, so the
 // device-side comparison `v >= thr[k]` reproduces the CPU decision for every f32 input.

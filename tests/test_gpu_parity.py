@@ -515,6 +515,43 @@ def test_resample_kernel_families_match_oracle(forced_ctx, kind, shape, bs, metr
 
 
 # ---------------------------------------------------------------------------------------------
+# resize_semantics = fir: the reference's default cargo feature (block.rs:292-333, data_types/mod.rs:65-107).  Integer
+# arithmetic: the GPU must equal the oracle's restatement bit for bit (which itself is "parity unpinned" against the crate)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def fir_ctx():
+    c = N.Context(0)
+    c.set_resize_semantics(N.RESIZE_FIR)
+    return c
+
+
+@pytest.mark.parametrize("shape,ch,bs,metric,factor,fd,fu", [
+    ((200, 264), 4, 64, 0, 0.05, O.LANCZOS3, O.LANCZOS3),
+    ((200, 264), 4, 64, 0, 0.1, O.TRIANGLE, O.TRIANGLE),      # Hamming down, Bilinear up
+    ((136, 192), 4, 32, 1, 6.0, O.CATMULLROM, O.GAUSSIAN),
+    ((136, 192), 3, 32, 0, 0.5, O.GAUSSIAN, O.CATMULLROM),
+    ((130, 170), 3, 48, 1, 8.0, O.NEAREST, O.LANCZOS3),
+    ((96, 128), 4, 16, 0, 2.0, O.LANCZOS3, O.NEAREST),
+])
+def test_fir_semantics_match_oracle(fir_ctx, shape, ch, bs, metric, factor, fd, fu):
+    img = synth(shape[1], shape[0], ch, seed=31)  # odd seed: alpha varies for 4 channels (pre-multiplied path)
+    with O.resize_semantics(O.FIR):
+        ref = O.shrink(img, bs, bs, metric, factor, fd)
+        want = O.expand(ref, fu)
+    d = fir_ctx.image_upload(img)
+    pl = d.shrink(bs, bs, metric, factor, fd, N.FLAG_EXACT_VALUES)
+    descs, px = pl.download()
+    assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+    assert np.array_equal(px, ref.payload)
+    assert np.array_equal(pl.expand(fu), want)
+    pl.free(); d.free()
+    # the image-crate semantics give other pixels for the same blocks (else this test would prove nothing)
+    reduced = (ref.descs["w"].astype(int) * ref.descs["h"] > 1) & ((ref.descs["w"] < bs) | (ref.descs["h"] < bs))
+    if fd != O.NEAREST and reduced.sum() > 4:
+        assert not np.array_equal(O.shrink(img, bs, bs, metric, factor, fd).payload, ref.payload)
+
+
+# ---------------------------------------------------------------------------------------------
 # batch entry points (pxz_shrink_batch / pxz_expand_batch): one launch per stage over all images, image by image
 # identical to the single-image calls — which the other tests hold against the oracle
 # ---------------------------------------------------------------------------------------------

@@ -181,3 +181,41 @@ def test_oracle_strategy_reduces_to_plain_filters_and_follows_buckets():
     for i, b in enumerate(buckets):
         y, x = (i // cols) * bs, (i % cols) * bs
         assert np.array_equal(up[y:y + bs, x:x + bs], full[O.NEAREST if b < 20 else O.LANCZOS3][y:y + bs, x:x + bs]), i
+
+
+def test_fir_branch_constant_images_stay_constant():
+    """block.rs:401-435 (test_resize): 100x100 RGB all-0 and all-255 -> 10x10 Lanczos3 stays constant — the only
+    constraint the reference puts on its default (fast_image_resize) branch; the oracle's restatement of that branch
+    is otherwise PARITY UNPINNED."""
+    for v in (0, 255):
+        for c in (3, 4):
+            blk = np.full((100, 100, c), v, np.uint8)
+            for f in (O.NEAREST, O.TRIANGLE, O.CATMULLROM, O.GAUSSIAN, O.LANCZOS3):
+                assert (O.resize_fir(blk, 10, 10, f) == v).all(), (v, c, f)
+                assert (O.resize_fir(blk[:10, :10], 64, 37, f) == v).all(), (v, c, f)
+
+
+def test_fir_branch_properties():
+    rng = np.random.default_rng(3)
+    blk = rng.integers(0, 256, (64, 48, 3), dtype=np.uint8)
+    # same size: clone (block.rs:279-281); nearest picks source pixels; the drivers follow the process-wide switch
+    assert np.array_equal(O.resize_fir(blk, 48, 64, O.LANCZOS3), blk)
+    near = O.resize_fir(blk, 24, 32, O.NEAREST)
+    assert np.array_equal(near, blk[1::2, 1::2])
+    # opaque RGBA == RGB with alpha 255 appended (pre-multiplication by 255 is the identity)
+    rgba = np.concatenate([blk, np.full((64, 48, 1), 255, np.uint8)], -1)
+    for f in (O.TRIANGLE, O.CATMULLROM, O.GAUSSIAN, O.LANCZOS3):
+        a, b = O.resize_fir(blk, 20, 30, f), O.resize_fir(rgba, 20, 30, f)
+        assert np.array_equal(a, b[..., :3]) and (b[..., 3] == 255).all()
+    # same kernels as the image-crate branch for CatmullRom / Gaussian / Lanczos3, but a rounded and clipped u8
+    # intermediate: close, not equal — SURVEY.md 8c measured up to 9 LSB between the two semantics on hard-edged content
+    for f in (O.CATMULLROM, O.GAUSSIAN, O.LANCZOS3):
+        dlt = np.abs(O.resize_fir(blk, 24, 32, f).astype(int) - O.resize(blk, 24, 32, f).astype(int))
+        assert 0 < dlt.max() <= 12 and dlt.mean() < 1.0
+    img = np.ascontiguousarray(np.concatenate([rng.integers(0, 256, (96, 128, 3), dtype=np.uint8), np.full((96, 128, 1), 255, np.uint8)], -1))
+    ref = O.shrink(img, 32, 32, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3)
+    with O.resize_semantics(O.FIR):
+        fir = O.shrink(img, 32, 32, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3)
+    assert np.array_equal(fir.descs["w"], ref.descs["w"]) and np.array_equal(fir.descs["value"], ref.descs["value"])  # the metric does not depend on it
+    assert not np.array_equal(fir.payload, ref.payload)
+    assert np.array_equal(O.shrink(img, 32, 32, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3).payload, ref.payload)  # the switch is back
