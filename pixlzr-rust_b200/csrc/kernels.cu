@@ -1444,8 +1444,8 @@ struct Acc4 {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const u64 pp = pk2(pc[c], pc[c]);
-      a01[c] = mac2<MODE>(a01[c], pp, w.x, k);
-      a23[c] = mac2<MODE>(a23[c], pp, w.y, k);
+      mac2_acc<MODE>(a01[c], pp, w.x, k);  // in place: no copies of the accumulators in unrolled walks
+      mac2_acc<MODE>(a23[c], pp, w.y, k);
     }
   }
   __device__ __forceinline__ float4 out(int j) const {  // j is a compile-time constant at every call site

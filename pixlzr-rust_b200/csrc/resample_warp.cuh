@@ -267,8 +267,8 @@ __device__ __forceinline__ void shrink_vrun(ShrinkRun<MODE>& st, const uint8_t* 
       const u64 ppa = pk2(ca[c], ca[c]), ppb = pk2(cb[c], cb[c]);
 #pragma unroll
       for (int jp = 0; jp < NP; ++jp) {
-        st.acc[0][c][jp] = mac2<MODE>(st.acc[0][c][jp], ppa, w[jp], k);
-        st.acc[1][c][jp] = mac2<MODE>(st.acc[1][c][jp], ppb, w[jp], k);
+        mac2_acc<MODE>(st.acc[0][c][jp], ppa, w[jp], k);
+        mac2_acc<MODE>(st.acc[1][c][jp], ppb, w[jp], k);
       }
     }
     st.r = r + 1;
@@ -331,8 +331,8 @@ __device__ __forceinline__ void shrink_vsimple(const uint8_t* tile0, size_t pitc
           const u64 ppa = pk2(ca[c], ca[c]), ppb = pk2(cb[c], cb[c]);
 #pragma unroll
           for (int jp = 0; jp < NP; ++jp) {
-            acc[0][c][jp] = mac2<MODE>(acc[0][c][jp], ppa, w[jp], k);
-            acc[1][c][jp] = mac2<MODE>(acc[1][c][jp], ppb, w[jp], k);
+            mac2_acc<MODE>(acc[0][c][jp], ppa, w[jp], k);
+            mac2_acc<MODE>(acc[1][c][jp], ppb, w[jp], k);
           }
         }
       }
@@ -668,17 +668,17 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) a[c] = mac2<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
+          for (int c = 0; c < NC; ++c) mac2_acc<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
         if (sh > 2) {
 #pragma unroll
           for (int j = 2; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < NC; ++c) a[c] = mac2<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
+            for (int c = 0; c < NC; ++c) mac2_acc<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
           if (sh > 4) {
 #pragma unroll
             for (int j = 4; j < 7; ++j)
 #pragma unroll
-              for (int c = 0; c < NC; ++c) a[c] = mac2<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
+              for (int c = 0; c < NC; ++c) mac2_acc<MODE>(a[c], pk2(win[j][c], win[j][c]), w[j], k);
           }
         }
         if (vact) {
