@@ -671,12 +671,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     per_rank_ms = [elapsed_ms / args.steps]
     per_rank_e2e = [batch * e2e_steps * IMG_W * IMG_H / 1e6 / e2e_s]
     per_rank_issue = [(t_launched - t_wall0) * 1e3 / args.steps]
+    per_rank_solo = [solo_plain_ms / solo_steps]
     if world > 1:
         gathered = [torch.zeros_like(times) for _ in range(world)]
         dist.all_gather(gathered, times)
         per_rank_ms = [float(t[0]) / args.steps for t in gathered]  # which rank sets the max
         per_rank_e2e = [batch * e2e_steps * IMG_W * IMG_H / 1e6 / (float(t[1]) / 1e3) for t in gathered]
         per_rank_issue = [float(t[2]) / args.steps for t in gathered]
+        per_rank_solo = [float(t[5]) / solo_steps for t in gathered]
         mhz = [float(t[3]) for t in gathered]
         bits = 0
         for t in gathered:
@@ -772,6 +774,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "host_issue_ms_per_step": round(host_issue_ms / args.steps, 4),
             "host_issue_ms_per_step_per_rank": [round(x, 4) for x in per_rank_issue],
             "ms_per_step_per_rank": [round(x, 4) for x in per_rank_ms],
+            # the same frames on ONE stream per rank (no overlap between frames): tells a slow GPU from stream contention
+            "single_stream_ms_per_step_per_rank": [round(x, 4) for x in per_rank_solo],
             "parity": parity,
             "fused_resample_mode": fused_info,
             "roofline": roofline,
