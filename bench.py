@@ -564,6 +564,28 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                           "kernel_us": {k: round(ms / n * 1e3, 2) for k, (ms, n) in fprof.items() if n}}
             fused_info["MPps_single_stream"] = round(IMG_W * IMG_H / 1e6 / (sum(fused_info["kernel_us"].values()) * 1e-6), 1)
 
+        # ---- informative: the directional (Sobel) metric on the same frames (shrink_directionally, pixlzr.rs:187-205) ----
+        sobel_info = None
+        if rank == 0:
+            for _ in range(2):
+                pl = wrapped[0][0].shrink(BS, BS, N.METRIC_SOBEL_DIR, 8.0, FILTER_DOWN, 0)
+                pl.free()
+            ctx.profile_enable(True)
+            for i in range(2 * distinct):
+                pl = wrapped[0][i % distinct].shrink(BS, BS, N.METRIC_SOBEL_DIR, 8.0, FILTER_DOWN, 0)
+                pl.expand_to_image(FILTER_UP, wrapped_out[0])
+                pl.free()
+            stream.synchronize()
+            sprof = ctx.profile_read()
+            ctx.profile_enable(False)
+            sobel_info = {"note": "metric = directional Sobel, factor 8, Lanczos3 both ways; single stream",
+                          "kernel_us": {k: round(ms / n * 1e3, 2) for k, (ms, n) in sprof.items() if n}}
+            if "analyze_sobel" in sobel_info["kernel_us"]:
+                us = sobel_info["kernel_us"]["analyze_sobel"]
+                sobel_info["analyze_sobel_frac_of_hbm_peak"] = round((4 * IMG_W * IMG_H + 8 * nblocks) / (us * 1e-6) / 1e9 /
+                                                                     float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+                                                                     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 0.0, 4)
+
         # ---- e2e: same work through the C ABI with pinned host buffers ---------------------------------
         # `--e2e-workers` host threads, each with its own context (= its own stream) and pinned staging buffers, take
         # the frames of the step in turn, so one frame's H2D overlaps another's kernels and D2H (PCIe is full duplex).
@@ -778,6 +800,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "single_stream_ms_per_step_per_rank": [round(x, 4) for x in per_rank_solo],
             "parity": parity,
             "fused_resample_mode": fused_info,
+            "sobel_metric": sobel_info,
             "roofline": roofline,
             "kernels": kernels,
             "encode_decode_stage": stage,
