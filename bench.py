@@ -430,7 +430,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     with torch.cuda.stream(stream):
         ctx = N.Context(local_rank, cuda_stream=stream.cuda_stream)
         # inputs: host (pinned) for the e2e leg, device-resident copies for the kernel leg
-        host_imgs = [torch.from_numpy(synth_image_np(rank * 1000 + i, IMG_W, IMG_H)).pin_memory() for i in range(distinct)]
+        # every rank gets the SAME frames (seeds 0 .. distinct-1): weak scaling means the same work per rank, and the work of a
+        # frame depends on its content (the level mix); round 1 seeded by rank and two of eight ranks drew heavier frames
+        host_imgs = [torch.from_numpy(synth_image_np(i, IMG_W, IMG_H)).pin_memory() for i in range(distinct)]
         dev_imgs = [t.to(dev, non_blocking=True) for t in host_imgs]
         stream.synchronize()
         # device-resident leg: `--streams` contexts (one CUDA stream each) take the frames of a step in turn, so the
