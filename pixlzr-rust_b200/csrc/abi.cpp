@@ -95,6 +95,7 @@ struct pxz_ctx {
   std::map<TabKey, TabSet> tabs;
   void* comm = nullptr;
   bool fast_resample = false;
+  bool rgb_via_rgba = true;            // RGB images run on the RGBA fast kernels (PXZ_RGB_VIA_RGBA=0: the 3-channel kernels)
   int resize_semantics = PXZ_RESIZE_IMAGE_RS;  // which branch of PixlzrBlock::resize (pxz_ctx_set_resize_semantics)
   std::vector<PayloadBufs> payload_cache;  // at most kPayloadCacheMax entries
   // per-kernel timing
@@ -438,6 +439,7 @@ pxz_status ctx_create_common(int device, cudaStream_t stream, bool own, pxz_ctx*
   ctx->band.abs_raw = 8.0e-6f; // fast arithmetic, absolute (SFU cube roots; measured <= 4e-6)
   if (const char* e = getenv("PXZ_GUARD_REL")) ctx->band.rel = (float)atof(e);
   if (const char* e = getenv("PXZ_GUARD_ABS")) ctx->band.abs_raw = (float)atof(e);
+  if (const char* e = getenv("PXZ_RGB_VIA_RGBA")) ctx->rgb_via_rgba = atoi(e) != 0;
   if (const char* e = getenv("PXZ_RESIZE_SEMANTICS")) ctx->resize_semantics = !strcmp(e, "fir") ? PXZ_RESIZE_FIR : PXZ_RESIZE_IMAGE_RS;
   if (const char* e = getenv("PXZ_RESAMPLE_KERNELS")) ctx->resample_kernels = !strcmp(e, "warp") ? 1 : !strcmp(e, "cta") ? 2 : !strcmp(e, "tma") ? 3 : 0;
   if (cudaMalloc((void**)&ctx->d_minmax, 8 * sizeof(float)) != cudaSuccess ||
@@ -843,11 +845,64 @@ pxz_status pxz_comm_join_empty(pxz_ctx* ctx) {
   return PXZ_OK;
 }
 
+// RGB images whose geometry suits the RGBA fast kernels run on them (kernels.cu "RGB images on the RGBA fast kernels")
+static bool rgb_on_rgba(const pxz_ctx* ctx, uint32_t w, uint32_t c, uint32_t bw, uint32_t bh) {
+  return c == 3 && ctx->rgb_via_rgba && ctx->resize_semantics == PXZ_RESIZE_IMAGE_RS && bw <= 64 && bh <= 64 && bw % 4 == 0 && w % 4 == 0;
+}
+
+// payload of the other channel count (3 <-> 4) with the same blocks, tables and work order
+static pxz_status payload_rechannel(pxz_ctx* ctx, const pxz_payload* src, uint32_t dc, pxz_payload** out) {
+  *out = nullptr;
+  Geom g = src->g;
+  const uint32_t sc = g.C;
+  g.C = dc;
+  const uint32_t nblocks = g.cols * g.rows;
+  pxz_payload* p = nullptr;
+  pxz_status st = payload_new(ctx, g, (uint64_t)g.W * g.H * dc * g.nimg, &p);
+  if (st != PXZ_OK) return st;
+  p->spec = src->spec;
+  p->strategy = src->strategy;
+  p->max_small_px = src->max_small_px; p->max_small_dim = src->max_small_dim;
+  p->max_tmp_down = src->max_tmp_down; p->max_tmp_up = src->max_tmp_up;
+  if (src->bytes_known) { p->bytes = src->bytes / sc * dc; p->bytes_known = true; }
+  cudaError_t e = launch_payload_convert(src->d_descs, src->d_pixels, src->d_tabidx, (uint32_t)src->nblocks_cap, src->d_total, p->d_descs,
+                                         p->d_pixels, p->d_tabidx, (uint32_t)p->nblocks_cap, p->d_total, nblocks, (int)sc, (int)dc,
+                                         ctx->stream, ctx->sm_count, &ctx->launches);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    payload_release(p);
+    return fail(ctx, PXZ_E_CUDA, std::string("payload convert: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return PXZ_OK;
+}
+
 pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t bh, pxz_metric metric, float factor,
                       pxz_filter filter_down, uint32_t flags, pxz_payload** out) {
   if (!ctx || !img || !out) return PXZ_E_ARG;
   *out = nullptr;
   cudaSetDevice(ctx->device);
+  if (rgb_on_rgba(ctx, img->w, img->c, bw, bh)) {
+    // widen to RGBA (alpha 255: its metric term is exactly +0 and the opaque resample path never touches it), run the
+    // 4-channel pipeline, narrow the payload back
+    pxz_image* wide = nullptr;
+    pxz_status st = pxz_image_alloc_batch(ctx, img->w, img->h, 4, img->nimg, &wide);
+    if (st != PXZ_OK) return st;
+    cudaError_t e = launch_rgb_widen(img->d, img->pitch, wide->d, wide->pitch, img->w, img->h * img->nimg, 1, ctx->stream, ctx->sm_count,
+                                     &ctx->launches);
+    pxz_payload* p4 = nullptr;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      st = fail(ctx, PXZ_E_CUDA, std::string("rgb widen: ") + cudaGetErrorString(e));
+    } else {
+      st = pxz_shrink(ctx, wide, bw, bh, metric, factor, filter_down, flags, &p4);
+    }
+    pxz_image_free(wide);  // stream-ordered: the kernels queued above keep it
+    if (st != PXZ_OK) return st;
+    st = payload_rechannel(ctx, p4, 3, out);
+    payload_release(p4);
+    return st;
+  }
   const bool normalise = (flags & PXZ_FLAG_NORMALISE_GLOBAL) != 0;
   // Every rank of a communicator must reach the min/max exchange, whatever happens to it before: a rank-local failure
   // (an unknown filter, a trailing block the Sobel metric cannot take, no memory) joins with neutral values and an
@@ -1265,6 +1320,25 @@ pxz_status pxz_expand_to_image(pxz_ctx* ctx, const pxz_payload* p, pxz_filter fi
   if ((int)filter_up < 0 || (int)filter_up > 4) return fail(ctx, PXZ_E_ARG, "unknown filter");
   if (out->w != p->g.W || out->h != p->g.H || out->c != p->g.C || out->nimg != p->g.nimg)
     return fail(ctx, PXZ_E_ARG, "output image geometry mismatch");
+  if (rgb_on_rgba(ctx, p->g.W, p->g.C, p->g.bw, p->g.bh) && p->max_small_dim <= 64) {
+    pxz_payload* p4 = nullptr;
+    pxz_status st = payload_rechannel(ctx, p, 4, &p4);
+    if (st != PXZ_OK) return st;
+    pxz_image* wide = nullptr;
+    st = pxz_image_alloc_batch(ctx, out->w, out->h, 4, out->nimg, &wide);
+    if (st == PXZ_OK) st = pxz_expand_to_image(ctx, p4, filter_up, wide);
+    if (st == PXZ_OK) {
+      cudaError_t e = launch_rgb_widen(wide->d, wide->pitch, out->d, out->pitch, out->w, out->h * out->nimg, 0, ctx->stream, ctx->sm_count,
+                                       &ctx->launches);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        st = fail(ctx, PXZ_E_CUDA, std::string("rgb narrow: ") + cudaGetErrorString(e));
+      }
+    }
+    pxz_image_free(wide);
+    payload_release(p4);
+    return st;
+  }
   TabSet ts;
   pxz_status st = get_tabset(ctx, *p->spec, p->strategy ? -1 : (int)filter_up, 1, &ts);
   if (st != PXZ_OK) return st;

@@ -2346,6 +2346,103 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// RGB (3-channel) images on the RGBA fast kernels: an RGB image is widened to RGBA with alpha 255 (the 4-channel
+// metric's alpha term is then exactly +0 and the opaque resample path never touches alpha, so every value and pixel is
+// bit-identical to the 3-channel computation), processed, and the payload narrowed back.  Three streaming kernels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_rgb_to_rgba(const uint8_t* __restrict__ src, size_t spitch, uint8_t* __restrict__ dst,
+                                                          size_t dpitch, uint32_t w, uint32_t rows) {
+  // 4 pixels per thread: 12 bytes in, 16 bytes out
+  const uint32_t quads = (w + 3) / 4;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < (size_t)quads * rows; i += (size_t)gridDim.x * kThreads) {
+    const uint32_t y = (uint32_t)(i / quads), q = (uint32_t)(i - (size_t)y * quads);
+    const uint8_t* s = src + (size_t)y * spitch + (size_t)q * 12;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + (size_t)y * dpitch) + (size_t)q * 4;
+    const uint32_t n = min(4u, w - q * 4);
+    for (uint32_t k = 0; k < n; ++k) d[k] = (uint32_t)s[3 * k] | ((uint32_t)s[3 * k + 1] << 8) | ((uint32_t)s[3 * k + 2] << 16) | 0xFF000000u;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_rgba_to_rgb(const uint8_t* __restrict__ src, size_t spitch, uint8_t* __restrict__ dst,
+                                                          size_t dpitch, uint32_t w, uint32_t rows) {
+  const uint32_t quads = (w + 3) / 4;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < (size_t)quads * rows; i += (size_t)gridDim.x * kThreads) {
+    const uint32_t y = (uint32_t)(i / quads), q = (uint32_t)(i - (size_t)y * quads);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src + (size_t)y * spitch) + (size_t)q * 4;
+    uint8_t* d = dst + (size_t)y * dpitch + (size_t)q * 12;
+    const uint32_t n = min(4u, w - q * 4);
+    for (uint32_t k = 0; k < n; ++k) {
+      const uint32_t p = s[k];
+      d[3 * k] = (uint8_t)p; d[3 * k + 1] = (uint8_t)(p >> 8); d[3 * k + 2] = (uint8_t)(p >> 16);
+    }
+  }
+}
+// payload + metadata of one channel count -> the other: block pixels (a warp per block), descriptors with rescaled
+// offsets (a block's offset is a multiple of its channel count), table indices, work-order lists, total
+__global__ void __launch_bounds__(kThreads) k_payload_convert(const pxz_block_desc* __restrict__ sdescs, const uint8_t* __restrict__ spx,
+                                                              const uint32_t* __restrict__ smeta, uint32_t scap, const unsigned long long* stotal,
+                                                              pxz_block_desc* __restrict__ ddescs, uint8_t* __restrict__ dpx,
+                                                              uint32_t* __restrict__ dmeta, uint32_t dcap, unsigned long long* dtotal,
+                                                              uint32_t nblocks, int sc, int dc) {
+  const uint32_t lane = threadIdx.x & 31u, wpc = kThreads / 32;
+  for (uint32_t b = blockIdx.x * wpc + (threadIdx.x >> 5); b < nblocks; b += gridDim.x * wpc) {
+    const pxz_block_desc d = sdescs[b];
+    const unsigned long long doff = d.offset / (unsigned)sc * (unsigned)dc;
+    if (lane == 0) {
+      pxz_block_desc o = d;
+      o.offset = doff;
+      ddescs[b] = o;
+      dmeta[b] = smeta[b];                                                         // tabidx
+      dmeta[(size_t)dcap + order_list_words(dcap) + b] = smeta[(size_t)scap + order_list_words(scap) + b];  // expand-side indices
+    }
+    const uint32_t npx = (uint32_t)d.w * d.h;
+    const uint8_t* s = spx + d.offset;
+    uint8_t* o = dpx + doff;
+    if (sc == 4) {
+      for (uint32_t i = lane; i < npx; i += 32) {
+        const uint32_t p = reinterpret_cast<const uint32_t*>(s)[i];
+        o[3 * i] = (uint8_t)p; o[3 * i + 1] = (uint8_t)(p >> 8); o[3 * i + 2] = (uint8_t)(p >> 16);
+      }
+    } else {
+      for (uint32_t i = lane; i < npx; i += 32)
+        reinterpret_cast<uint32_t*>(o)[i] = (uint32_t)s[3 * i] | ((uint32_t)s[3 * i + 1] << 8) | ((uint32_t)s[3 * i + 2] << 16) | 0xFF000000u;
+    }
+  }
+  // work-order lists: lists[c * cap + i], then the 8 class counts
+  const uint32_t* sl = smeta + scap;
+  uint32_t* dl = dmeta + dcap;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < (size_t)kOrderClasses * nblocks + kOrderClasses; i += (size_t)gridDim.x * kThreads) {
+    if (i < (size_t)kOrderClasses * nblocks) {
+      const uint32_t c = (uint32_t)(i / nblocks), k = (uint32_t)(i - (size_t)c * nblocks);
+      dl[(size_t)c * dcap + k] = sl[(size_t)c * scap + k];
+    } else {
+      const uint32_t c = (uint32_t)(i - (size_t)kOrderClasses * nblocks);
+      dl[(size_t)kOrderClasses * dcap + c] = sl[(size_t)kOrderClasses * scap + c];
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *dtotal = *stotal / (unsigned)sc * (unsigned)dc;
+}
+
+cudaError_t launch_rgb_widen(const uint8_t* src, size_t spitch, uint8_t* dst, size_t dpitch, uint32_t w, uint32_t rows, int widen,
+                             cudaStream_t s, int sm_count, uint64_t* launches) {
+  ++*launches;
+  const long long quads = (long long)((w + 3) / 4) * rows;
+  const int grid = clamp_grid((quads + kThreads - 1) / kThreads, (long long)sm_count * 8);
+  if (widen) k_rgb_to_rgba<<<grid, kThreads, 0, s>>>(src, spitch, dst, dpitch, w, rows);
+  else k_rgba_to_rgb<<<grid, kThreads, 0, s>>>(src, spitch, dst, dpitch, w, rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_payload_convert(const pxz_block_desc* sdescs, const uint8_t* spx, const uint32_t* smeta, uint32_t scap,
+                                   const uint64_t* stotal, pxz_block_desc* ddescs, uint8_t* dpx, uint32_t* dmeta, uint32_t dcap,
+                                   uint64_t* dtotal, uint32_t nblocks, int sc, int dc, cudaStream_t s, int sm_count, uint64_t* launches) {
+  ++*launches;
+  const int grid = clamp_grid(((long long)nblocks + 7) / 8, (long long)sm_count * 8);
+  k_payload_convert<<<grid, kThreads, 0, s>>>(sdescs, spx, smeta, scap, reinterpret_cast<const unsigned long long*>(stotal), ddescs, dpx, dmeta,
+                                              dcap, reinterpret_cast<unsigned long long*>(dtotal), nblocks, sc, dc);
+  return cudaGetLastError();
+}
+
 size_t resample_fir_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C) {
   return (((size_t)max_src_px * C + 15) & ~(size_t)15) + (size_t)max_tmp_px * C;
 }

@@ -123,6 +123,9 @@ cudaError_t launch_plan(const float* vx, const float* vy, const Geom& g, const V
 // expensive), lists[8 * cap + c] = how many.  launch_plan fills them; this entry point does the same for descriptors
 // that came from the host.
 constexpr uint32_t kOrderClasses = 8;
+#ifdef __CUDACC__
+__host__ __device__
+#endif
 inline size_t order_list_words(size_t cap) { return (size_t)kOrderClasses * cap + kOrderClasses; }
 cudaError_t launch_class_lists(const pxz_block_desc* descs, const Geom& g, void* scan_state, uint32_t* lists, uint32_t cap,
                                cudaStream_t s, uint64_t* launches);
@@ -147,6 +150,13 @@ cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geo
                             uint32_t* tile_counter, const uint32_t* lists, uint32_t cap, bool warp_tables, int prefer, bool has_noslide,
                             cudaStream_t s, int sm_count, uint64_t* launches);
 size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
+// RGB images on the RGBA kernels: widen = 1: RGB rows -> RGBA rows (alpha 255); 0: RGBA rows -> RGB rows
+cudaError_t launch_rgb_widen(const uint8_t* src, size_t spitch, uint8_t* dst, size_t dpitch, uint32_t w, uint32_t rows, int widen,
+                             cudaStream_t s, int sm_count, uint64_t* launches);
+// payload of `sc` channels (descs, pixels, meta = tabidx | order lists | expand-side indices with capacity scap) -> `dc` channels
+cudaError_t launch_payload_convert(const pxz_block_desc* sdescs, const uint8_t* spx, const uint32_t* smeta, uint32_t scap,
+                                   const uint64_t* stotal, pxz_block_desc* ddescs, uint8_t* dpx, uint32_t* dmeta, uint32_t dcap,
+                                   uint64_t* dtotal, uint32_t nblocks, int sc, int dc, cudaStream_t s, int sm_count, uint64_t* launches);
 // `fir` resize semantics (integer convolution, horizontal pass first, pre-multiplied alpha): one CTA per block
 size_t resample_fir_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C);
 cudaError_t launch_resample_fir(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,

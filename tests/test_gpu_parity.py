@@ -515,6 +515,41 @@ def test_resample_kernel_families_match_oracle(forced_ctx, kind, shape, bs, metr
 
 
 # ---------------------------------------------------------------------------------------------
+# RGB images run on the RGBA fast kernels by default (widened with alpha 255, payload narrowed back); PXZ_RGB_VIA_RGBA=0
+# keeps them on the 3-channel kernels.  Both must give the oracle's 3-channel result bit for bit, values included.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("via_rgba", ["1", "0"])
+@pytest.mark.parametrize("shape,bs,metric,factor,fd,fu", [
+    ((200, 264), 64, 0, 1.0, O.LANCZOS3, O.LANCZOS3),
+    ((136, 192), 32, 1, 6.0, O.CATMULLROM, O.TRIANGLE),
+    ((130, 172), 16, 0, 0.25, O.GAUSSIAN, O.NEAREST),
+])
+def test_rgb_paths_match_oracle(via_rgba, shape, bs, metric, factor, fd, fu):
+    old = os.environ.get("PXZ_RGB_VIA_RGBA")
+    os.environ["PXZ_RGB_VIA_RGBA"] = via_rgba
+    try:
+        c = N.Context(0)
+    finally:
+        if old is None:
+            del os.environ["PXZ_RGB_VIA_RGBA"]
+        else:
+            os.environ["PXZ_RGB_VIA_RGBA"] = old
+    img = synth(shape[1], shape[0], 3, seed=41)
+    ref = O.shrink(img, bs, bs, metric, factor, fd)
+    d = c.image_upload(img)
+    pl = d.shrink(bs, bs, metric, factor, fd, N.FLAG_EXACT_VALUES)
+    descs, px = pl.download()
+    assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+    assert np.array_equal(descs["offset"], ref.descs["offset"])
+    assert np.array_equal(descs["value"].view(np.uint32), ref.descs["value"].view(np.uint32))
+    assert np.array_equal(px, ref.payload)
+    assert np.array_equal(pl.expand(fu), O.expand(ref, fu))
+    pl2 = c.payload_upload(shape[1], shape[0], bs, bs, 3, descs, px)
+    assert np.array_equal(pl2.expand(fu), O.expand(ref, fu))
+    pl2.free(); pl.free(); d.free()
+
+
+# ---------------------------------------------------------------------------------------------
 # resize_semantics = fir: the reference's default cargo feature (block.rs:292-333, data_types/mod.rs:65-107).  Integer
 # arithmetic: the GPU must equal the oracle's restatement bit for bit (which itself is "parity unpinned" against the crate)
 # ---------------------------------------------------------------------------------------------
