@@ -410,6 +410,42 @@ def run_nccl_parity(torch, dist, N, S, O_or_none, rank, world, local_rank, devic
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(torch, local_rank: int) -> dict:
+    """Run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned buffer exists:
+    pinned pages are placed where the allocating thread runs, and a DMA that crosses the socket interconnect gets a
+    fraction of the PCIe rate when all ranks copy at once.  A no-op (reported) when sysfs exposes no node for the GPU."""
+    info = {"bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        info["gpu_pci"] = bdf
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        info["nodes_online"] = len(nodes)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["node"] = node
+        if node < 0 or len(nodes) < 2:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound"], info["cpus"] = True, len(cpus)
+    except Exception as e:  # no sysfs entry, no permission: keep the default placement
+        info["error"] = repr(e)
+    return info
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -421,6 +457,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_numa = bind_to_gpu_numa_node(torch, local_rank) if args.numa_bind else {"bound": False, "off": True}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
@@ -691,7 +728,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     names = ClockSampler.NAMES
     reason_bits = sum(1 << i for i, n in enumerate(names) if n in (clocks.get("reasons") or []))
     times = torch.tensor([elapsed_ms, e2e_s * 1e3, (t_launched - t_wall0) * 1e3, clocks.get("sm_mhz") or -1.0, float(reason_bits),
-                          solo_plain_ms], dtype=torch.float64, device=dev)
+                          solo_plain_ms, float(host_numa.get("node", -1)), 1.0 if host_numa.get("bound") else 0.0],
+                         dtype=torch.float64, device=dev)
     per_rank_ms = [elapsed_ms / args.steps]
     per_rank_e2e = [batch * e2e_steps * IMG_W * IMG_H / 1e6 / e2e_s]
     per_rank_issue = [(t_launched - t_wall0) * 1e3 / args.steps]
@@ -703,6 +741,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         per_rank_e2e = [batch * e2e_steps * IMG_W * IMG_H / 1e6 / (float(t[1]) / 1e3) for t in gathered]
         per_rank_issue = [float(t[2]) / args.steps for t in gathered]
         per_rank_solo = [float(t[5]) / solo_steps for t in gathered]
+        host_numa["node_per_rank"] = [int(t[6]) for t in gathered]
+        host_numa["bound_per_rank"] = [bool(t[7]) for t in gathered]
         mhz = [float(t[3]) for t in gathered]
         bits = 0
         for t in gathered:
@@ -791,7 +831,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // e2e_steps),
                     "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps,
-                    "host_threads": n_workers, "per_rank_MPps": [round(x, 1) for x in per_rank_e2e], "pcie_ceiling": pcie,
+                    "host_threads": n_workers, "host_numa": host_numa, "per_rank_MPps": [round(x, 1) for x in per_rank_e2e], "pcie_ceiling": pcie,
                     "path": "pxz_image_upload -> pxz_shrink -> pxz_payload_download -> pxz_payload_upload -> pxz_expand, pinned host buffers"},
             "gpu_launches": int(launches),
             # host wall time to issue one step's launches (per rank): the step is launch-bound when this nears ms_per_step
@@ -831,6 +871,8 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads (contexts) of the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=2, help="steps of the end-to-end leg")
     ap.add_argument("--no-pcie-probe", dest="pcie_probe", action="store_false")
+    ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false",
+                    help="leave the host threads and pinned buffers wherever the OS puts them")
     ap.add_argument("--skip-extras", action="store_true", help="only the C3 headline: no sharded (C4) / batch (C5) blocks")
     ap.add_argument("--c4-side", type=int, default=65536)
     ap.add_argument("--c5-images", type=int, default=4096)
