@@ -164,7 +164,8 @@ uint32_t pxz_image_batch_count(const pxz_image* img);
 pxz_status pxz_grid(uint32_t w, uint32_t h, uint32_t bw, uint32_t bh, uint32_t* cols, uint32_t* rows);
 
 /* ---- analysis: get_block_variance / get_block_variance_directionally ---------------------
- * Raw per-block metric (before `after`), row-major; host arrays of cols*rows floats.
+ * Raw per-block metric (before `after`), row-major; host arrays of cols*rows floats (a batch image:
+ * cols*rows*pxz_image_batch_count(img), image after image).
  * OKLAB_MAD fills values_x (values_y, if given, gets a copy); SOBEL_DIR fills (hz, vr).
  * flags: PXZ_FLAG_EXACT_VALUES for reference-order f32 sums. */
 pxz_status pxz_analyze(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t bh, pxz_metric metric, uint32_t flags,

@@ -335,8 +335,8 @@ class Image:
 
     def analyze(self, bw: int, bh: int, metric: int, flags: int = 0):
         cols, rows = grid(self.w, self.h, bw, bh)
-        vx = np.empty(cols * rows, np.float32)
-        vy = np.empty(cols * rows, np.float32)
+        vx = np.empty(cols * rows * self.n, np.float32)  # a batch: image after image
+        vy = np.empty(cols * rows * self.n, np.float32)
         self.ctx.check(lib().pxz_analyze(self.ctx.handle, self._h, bw, bh, metric, flags, ptr(vx), ptr(vy)))
         return vx, vy
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("PXZ_OUT") or os.path.join(HERE, "libpixlzr_b200.so")
 SOURCES = ["kernels.cu", "qoi_device.cu", "abi.cpp", "tables.cpp", "container.cpp", "nccl_dyn.cpp"]
-HEADERS = ["pxz_internal.h", "pxz_host.h", "srgb_lut.inc", "resample_warp.cuh", "resample_tma.cuh", os.path.join("..", "..", "include", "pixlzr_b200.h")]
+HEADERS = ["pxz_internal.h", "pxz_host.h", "srgb_lut.inc", "resample_warp.cuh", "resample_tma.cuh", "analyze_sobel_tma.cuh", os.path.join("..", "..", "include", "pixlzr_b200.h")]
 NVCC = os.environ.get("PXZ_NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = [

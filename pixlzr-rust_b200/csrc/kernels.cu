@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "pxz_internal.h"
 
@@ -2046,6 +2048,7 @@ __global__ void __launch_bounds__(kThreads) k_resample_fir(int direction, uint8_
 #endif
 #include "resample_warp.cuh"
 #include "resample_tma.cuh"
+#include "analyze_sobel_tma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // launchers
@@ -2146,10 +2149,57 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
   return cudaGetLastError();
 }
 
+// cuTensorMapEncodeTiled through the runtime (the library links cudart statically and has no libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// the pitched RGBA8 image as a 2-D tensor of 32-bit pixels, box = 64 px x box_rows rows
+static bool make_image_tmap(const uint8_t* img, size_t pitch, uint32_t W, uint32_t H, CUtensorMap* tm, uint32_t box_rows = kTBoxRows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {W, H};
+  const cuuint64_t strides[1] = {pitch};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// PXZ_SOBEL_KERNEL=tile64 keeps the shared-memory kernel (A/B timing and a fallback that needs no tensor map)
+static bool sobel_tma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PXZ_SOBEL_KERNEL");
+    return !(e && strcmp(e, "tile64") == 0);
+  }();
+  return on;
+}
+
 cudaError_t launch_analyze_sobel(const uint8_t* img, size_t pitch, const Geom& g, float* vx, float* vy, cudaStream_t s,
                                  int sm_count, uint64_t* launches) {
   const uint32_t ntiles = g.cols * g.rows;
   ++*launches;
+  // RGBA, 64x64 tiles, rows a tensor copy can address: tiles streamed by TMA, dp4a row terms (analyze_sobel_tma.cuh)
+  if (g.C == 4 && g.bw == 64 && g.bh == 64 && (pitch % 16 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && sobel_tma_enabled()) {
+    CUtensorMap tm;
+    if (make_image_tmap(img, pitch, g.W, g.nimg > 1 ? (g.nimg - 1) * g.img_rows + g.H : g.H, &tm, 64)) {
+      cudaError_t e = set_smem(k_analyze_sobel_tma, (size_t)kSobSmemBytes);
+      if (e != cudaSuccess) return e;
+      k_analyze_sobel_tma<<<clamp_grid(ntiles, (long long)sm_count * PXZ_SOBEL_CTAS), 256, kSobSmemBytes, s>>>(tm, g, vx, vy);
+      return cudaGetLastError();
+    }
+  }
   const bool small = g.bw <= 64 && g.bh <= 64 && (g.C == 3 || ((pitch & 3u) == 0 && (reinterpret_cast<uintptr_t>(img) & 3u) == 0));
   if (small) {
     if (g.C == 4)
@@ -2218,34 +2268,6 @@ size_t resample_smem_bytes(uint32_t max_src_px, uint32_t max_tmp_px, uint32_t C)
 }
 
 int resample_grid(int sm_count, uint32_t nblocks) { return clamp_grid(nblocks, (long long)sm_count * 8); }
-
-// cuTensorMapEncodeTiled through the runtime (the library links cudart statically and has no libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
-      cudaGetLastError();
-      p = nullptr;
-    }
-    return (EncodeTiledFn)p;
-  }();
-  return fn;
-}
-// the pitched RGBA8 image as a 2-D tensor of 32-bit pixels, box = 64 px x kTBoxRows rows
-static bool make_image_tmap(const uint8_t* img, size_t pitch, uint32_t W, uint32_t H, CUtensorMap* tm) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn) return false;
-  const cuuint64_t dims[2] = {W, H};
-  const cuuint64_t strides[1] = {pitch};
-  const cuuint32_t box[2] = {64, (cuuint32_t)kTBoxRows};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 cudaError_t launch_resample(int direction, uint8_t* img, size_t pitch, const Geom& g, const pxz_block_desc* descs,
                             const uint32_t* tabidx, uint8_t* payload, const AxisTab* tabs, const uint32_t* pool,

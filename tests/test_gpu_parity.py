@@ -114,7 +114,8 @@ def test_mad_values_ragged_shapes(ctx, w, h, c, bw, bh):
 
 
 @pytest.mark.parametrize("w,h,c,bw,bh", [(1920, 1080, 3, 32, 32), (258, 131, 3, 32, 32), (260, 132, 4, 64, 64), (99, 70, 4, 16, 8),
-                                         (300, 300, 3, 200, 100), (66, 66, 4, 64, 64)])
+                                         (300, 300, 3, 200, 100), (66, 66, 4, 64, 64), (4096, 2115, 4, 64, 64),
+                                         (67, 200, 4, 64, 64)])
 def test_sobel_values_bit_exact(ctx, w, h, c, bw, bh):
     img = load_png("Big-Ruscher.png") if (w, h) == (1920, 1080) else synth(w, h, c, seed=w + h)
     hz, vr = O.analyze(img, bw, bh, O.METRIC_SOBEL_DIR, nthreads=8)
@@ -122,6 +123,40 @@ def test_sobel_values_bit_exact(ctx, w, h, c, bw, bh):
     ghz, gvr = d.analyze(bw, bh, N.METRIC_SOBEL_DIR)
     d.free()
     assert np.array_equal(ghz.view("<u4"), hz.view("<u4")) and np.array_equal(gvr.view("<u4"), vr.view("<u4"))
+
+
+def test_sobel_tensor_copy_kernel_matches_shared_memory_kernel(ctx):
+    """RGBA + 64x64 tiles take k_analyze_sobel_tma (tiles streamed by tensor copies); PXZ_SOBEL_KERNEL=tile64 keeps the
+    round-1 kernel.  Both against the oracle, on a stacked batch too (a tile's box then runs into the next image)."""
+    import subprocess, sys, textwrap
+    imgs = np.stack([synth(323, 150, 4, seed=70 + i) for i in range(3)])
+    want = [O.analyze(im, 64, 64, O.METRIC_SOBEL_DIR, nthreads=8) for im in imgs]
+    b = ctx.image_upload_batch(imgs)
+    ghz, gvr = b.analyze(64, 64, N.METRIC_SOBEL_DIR)
+    b.free()
+    per = want[0][0].size
+    for i, (hz, vr) in enumerate(want):
+        assert np.array_equal(ghz.reshape(-1)[i * per:(i + 1) * per].view("<u4"), hz.reshape(-1).view("<u4")), i
+        assert np.array_equal(gvr.reshape(-1)[i * per:(i + 1) * per].view("<u4"), vr.reshape(-1).view("<u4")), i
+    # the other kernel needs a fresh process (the switch is read once)
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        import pixlzr_b200 as P
+        N = P.native
+        img = np.load(sys.argv[1])
+        c = N.Context(0)
+        d = c.image_upload(img)
+        hz, vr = d.analyze(64, 64, N.METRIC_SOBEL_DIR)
+        np.save(sys.argv[2], np.stack([hz, vr]))
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        np.save(os.path.join(td, "in.npy"), imgs[0])
+        env = dict(os.environ, PXZ_SOBEL_KERNEL="tile64")
+        subprocess.run([sys.executable, "-c", code, os.path.join(td, "in.npy"), os.path.join(td, "out.npy")], check=True, env=env)
+        other = np.load(os.path.join(td, "out.npy"))
+    assert np.array_equal(other[0].view("<u4"), want[0][0].view("<u4")) and np.array_equal(other[1].view("<u4"), want[0][1].view("<u4"))
 
 
 def test_sobel_rejects_blocks_thinner_than_two(ctx):
