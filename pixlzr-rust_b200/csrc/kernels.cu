@@ -1430,6 +1430,23 @@ __device__ __forceinline__ uint32_t pack_bits(uint32_t r, uint32_t g, uint32_t b
   return __byte_perm(__byte_perm(r, g, 0x0040), __byte_perm(b, a, 0x0040), 0x5410);
 }
 
+__device__ __forceinline__ uint32_t pack_sat_u8x2(int32_t hi_byte, int32_t lo_byte, uint32_t upper16) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi_byte), "r"(lo_byte), "r"(upper16));
+  return d;
+}
+// Round-half-away + clamp of two values per instruction.  For t >= 0 the reference's rounding is floor(t + 0.5): the sum
+// is rounded toward zero (it never crosses an integer upwards), then the product with 2^-149, again toward zero, is the
+// subnormal whose BIT PATTERN is that integer (one ulp of a subnormal is 2^-149; the packed pipe does not flush).  A
+// negative sum comes out with the sign bit set, i.e. as a negative s32, so cvt.pack.sat sends it to 0 and anything
+// above 255 to 255: two packed FP32 instructions per channel PAIR instead of three scalar ones per channel.
+__device__ __forceinline__ u64 round_away_bits2(u64 t2) {
+  u64 h, d;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(h) : "l"(t2), "l"(0x3f0000003f000000ull));  // + (0.5, 0.5)
+  asm("mul.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(h), "l"(0x0000000100000001ull));   // * (2^-149, 2^-149)
+  return d;
+}
+
 // Four outputs that share one walk over the source samples: per channel the accumulators of outputs (0,1) and (2,3)
 // sit in one f32x2 register pair each, the sample is broadcast and the weights of the four outputs arrive as one
 // 16-byte row — 2 FFMA2 issue slots per channel and sample in fused mode, 4 in exact mode (8 scalar before).
@@ -1459,6 +1476,19 @@ struct Acc4 {
     }
     return make_float4(v[0], v[1], v[2], v[3]);
   }
+  // the four outputs as packed RGBA8 pixels (alpha 255 when it is not computed)
+  __device__ __forceinline__ uint4 pack4() const {
+    u64 q01[NC], q23[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { q01[c] = round_away_bits2(a01[c]); q23[c] = round_away_bits2(a23[c]); }
+    auto px = [&](const u64 (&q)[NC], bool hi) -> uint32_t {
+      const int32_t r = (int32_t)(hi ? (uint32_t)(q[0] >> 32) : (uint32_t)q[0]), g = (int32_t)(hi ? (uint32_t)(q[1] >> 32) : (uint32_t)q[1]);
+      const int32_t b = (int32_t)(hi ? (uint32_t)(q[2] >> 32) : (uint32_t)q[2]);
+      const int32_t a = (NC > 3) ? (int32_t)(hi ? (uint32_t)(q[NC > 3 ? 3 : 0] >> 32) : (uint32_t)q[NC > 3 ? 3 : 0]) : 255;
+      return pack_sat_u8x2(g, r, pack_sat_u8x2(a, b, 0u));
+    };
+    return make_uint4(px(q01, false), px(q01, true), px(q23, false), px(q23, true));
+  }
 };
 
 // One output: channels paired as (r, g) and (b, a); without alpha the blue channel stays scalar.
@@ -1487,11 +1517,6 @@ struct Acc1 {
 // t < -0.5; cvt.pack.sat clamps n to [0, 255] and packs two channels per instruction (|t| < 2^22 here).
 __device__ __forceinline__ int32_t round_away_int(float t) {
   return (int32_t)(__float_as_uint(__fadd_rz(__fadd_rz(t, 0.5f), 12582912.0f)) - 0x4B400000u);
-}
-__device__ __forceinline__ uint32_t pack_sat_u8x2(int32_t hi_byte, int32_t lo_byte, uint32_t upper16) {
-  uint32_t d;
-  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi_byte), "r"(lo_byte), "r"(upper16));
-  return d;
 }
 template <int MODE>
 __device__ __forceinline__ uint32_t pack_px(const float4& a) {
@@ -1592,7 +1617,8 @@ __device__ __forceinline__ void horizontal_blocked(const float4* tmp, uint32_t t
     if (c < n) acc.step(trow[(c0 + c) ^ s7], wp[c], k);
     const uint32_t ox = ob * 4;
     const uint32_t nvalid = min(4u, dw - ox);
-    uint32_t px[4] = {pack_px<MODE>(acc.out(0)), pack_px<MODE>(acc.out(1)), pack_px<MODE>(acc.out(2)), pack_px<MODE>(acc.out(3))};
+    const uint4 pk = acc.pack4();
+    uint32_t px[4] = {pk.x, pk.y, pk.z, pk.w};
     put(oy, ox, nvalid, px);
   }
 }

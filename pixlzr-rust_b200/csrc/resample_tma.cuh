@@ -93,7 +93,8 @@ struct TQueue {
   uint32_t* counter;
   uint32_t ntiles;
   TileOrder ord;
-  uint32_t raw;        // lane 0: the drawn index (atomic in flight)
+  bool back;           // this warp draws from the back of the order list (draws_from_back)
+  uint32_t raw;        // lane 0: the drawn position (atomic in flight)
   bool drawing;        // this warp has not yet drawn an index >= ntiles
   TDesc q;             // the tile being fetched
   uint32_t step;       // 0: drawn | 1: list entry requested | 2: descriptor requested
@@ -101,7 +102,10 @@ struct TQueue {
 };
 __device__ __forceinline__ void tq_start(TQueue& q) {
   q.raw = 0xFFFFFFFFu;
-  if (q.drawing && (threadIdx.x & 31u) == 0) q.raw = atomicAdd(q.counter, 1u);
+  if (q.drawing && (threadIdx.x & 31u) == 0) {
+    uint32_t n;
+    q.raw = draw_position(q.counter, q.back, q.ntiles, n);
+  }
   q.step = 0; q.tick = 0; q.next_at = 4;
 }
 __device__ __forceinline__ void tq_advance(TQueue& q) {
@@ -225,10 +229,11 @@ __device__ __forceinline__ void tma_horizontal_body(const float4* strip, uint32_
       if (c) acc.step(pa[0], wp[0], k);
       const uint32_t ox = ob * 4, nvalid = min(4u, dw - ox);
       uint32_t* o = dst + (size_t)(row0 + r) * dw + ox;
-      o[0] = pack_px<MODE>(acc.out(0));
-      if (nvalid > 1) o[1] = pack_px<MODE>(acc.out(1));
-      if (nvalid > 2) o[2] = pack_px<MODE>(acc.out(2));
-      if (nvalid > 3) o[3] = pack_px<MODE>(acc.out(3));
+      const uint4 pk = acc.pack4();
+      o[0] = pk.x;
+      if (nvalid > 1) o[1] = pk.y;
+      if (nvalid > 2) o[2] = pk.z;
+      if (nvalid > 3) o[3] = pk.w;
     }
   } else {
     // few outputs: one scalar chain per (row, output, channel)
@@ -532,6 +537,7 @@ __global__ void __launch_bounds__(kTWarps * 32, PXZ_SHRINK_TMA_CTAS) k_shrink_tm
   q.descs = descs; q.tabidx = tabidx; q.opaque = opaque_flags; q.counter = counter; q.ntiles = ntiles;
   q.ord.init(lists, cap);
   q.drawing = true;
+  q.back = draws_from_back(PXZ_SHRINK_TMA_CTAS);
   tq_start(q);
   TDesc P0 = tq_finish(q);
   tq_start(q);
@@ -646,11 +652,12 @@ __global__ void __launch_bounds__(kTWarps * 32, PXZ_SHRINK_TMA_CTAS) k_shrink_tm
     f.cx = f.nx; f.cy = f.ny; f.cnb = f.nnb; f.cpb = f.npb;
     f.nnb = 0; f.npb = 0;
   }
-  // the last warp out puts both counters back for the next launch on this stream
+  // the last warp out puts the draw counts (one 64-bit word) and the exit count back for the next launch on this stream
   if (lane == 0) {
-    if (atomicAdd(counter + 1, 1u) == total_warps - 1) {
+    if (atomicAdd(counter + 2, 1u) == total_warps - 1) {
       counter[0] = 0u;
       counter[1] = 0u;
+      counter[2] = 0u;
     }
   }
 }

@@ -5,7 +5,7 @@ import io
 import subprocess
 import sys
 
-out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv', '--kernel-id', ':::' + sys.argv[2]],
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv', *(['--kernel-id', ':::' + sys.argv[2]] if sys.argv[2].isdigit() else ['--kernel-name', 'regex:' + sys.argv[2]])],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if 'Instructions Executed' in r)

@@ -1,7 +1,7 @@
 """Instruction counts / stall samples of one kernel by opcode and by contiguous SASS region:
     python tools/ncu_regions.py file.ncu-rep <kernel-id> [region-size]"""
 import csv, io, subprocess, sys, collections
-out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv', ] + (['--kernel-id', ':::' + sys.argv[2]] if sys.argv[2] != '-' else []), capture_output=True, text=True).stdout
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv', ] + (([] if sys.argv[2] == '-' else ['--kernel-id', ':::' + sys.argv[2]]) if not sys.argv[2].isalpha() and '_' not in sys.argv[2] else ['--kernel-name', 'regex:' + sys.argv[2]]), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if 'Instructions Executed' in r)
 h = rows[hi]
