@@ -214,10 +214,21 @@ __device__ __forceinline__ u64 cbrt_fast2(u64 x) {
 struct OklabFast2 {
   u64 l, m, s;
 };
-__device__ __forceinline__ OklabFast2 lms_fast_pair2(uint32_t px0, uint32_t px1, uint32_t lut_lane_addr) {
-  const u64 r = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4440) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4440) << 7)));
-  const u64 g = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4441) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4441) << 7)));
-  const u64 b = pk2(lds_f32(lut_lane_addr + (__byte_perm(px0, 0, 0x4442) << 7)), lds_f32(lut_lane_addr + (__byte_perm(px1, 0, 0x4442) << 7)));
+#ifndef PXZ_MAD_LUT_STRIDE
+#define PXZ_MAD_LUT_STRIDE 64  // floats per table entry: 64 = one byte permute builds the whole offset, 32 = half the shared memory
+#endif
+constexpr int kMadLutStride = PXZ_MAD_LUT_STRIDE;
+// offset of entry `byte BYTE of px` in this lane's column of the table.  With 256-byte entries the offset is
+// {lane * 4, value, 0, 0} as bytes: one PRMT, and the table base rides in a uniform register (LDS [R + UR]).
+template <int BYTE>
+__device__ __forceinline__ float lut_fetch(uint32_t px, uint32_t lut_base, uint32_t lane4) {
+  if (kMadLutStride == 64) return lds_f32(lut_base + __byte_perm(px, lane4, 0x7704 | (BYTE << 4)));
+  return lds_f32(lut_base + lane4 + (__byte_perm(px, 0, 0x4440 | BYTE) << 7));
+}
+__device__ __forceinline__ OklabFast2 lms_fast_pair2(uint32_t px0, uint32_t px1, uint32_t lut_base, uint32_t lane4) {
+  const u64 r = pk2(lut_fetch<0>(px0, lut_base, lane4), lut_fetch<0>(px1, lut_base, lane4));
+  const u64 g = pk2(lut_fetch<1>(px0, lut_base, lane4), lut_fetch<1>(px1, lut_base, lane4));
+  const u64 b = pk2(lut_fetch<2>(px0, lut_base, lane4), lut_fetch<2>(px1, lut_base, lane4));
 #define PXZ_ROW2(c0, c1, c2) fma2(pk2(c2, c2), b, fma2(pk2(c1, c1), g, mul2(pk2(c0, c0), r)))
   OklabFast2 o;
   o.l = cbrt_fast2(PXZ_ROW2(M1_00, M1_01, M1_02));
@@ -236,15 +247,15 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
                                                                   uint32_t* __restrict__ zero_word) {
   constexpr int TPC = kThreads / G;  // tiles per CTA iteration
   constexpr int WPG = G / 32;        // warps per group
-  extern __shared__ float s_lut[];   // [256][32]
+  extern __shared__ float s_lut[];   // [256][kMadLutStride], columns 0..31 used: bank == lane for any pixel data
   __shared__ float s_r1[2][kThreads / 32][4];
   __shared__ float s_r2[2][kThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = tid / G, gt = tid % G, gwarp0 = grp * WPG;
-  for (int i = tid; i < 256 * 32; i += kThreads) s_lut[i] = c_srgb_lut[i >> 5];
+  for (int i = tid; i < 256 * 32; i += kThreads) s_lut[(i >> 5) * kMadLutStride + (i & 31)] = c_srgb_lut[i >> 5];
   __syncthreads();
-  const uint32_t lut_lane_addr = (uint32_t)__cvta_generic_to_shared(s_lut + lane);
+  const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut), lane4 = (uint32_t)lane * 4u;
 
   const uint32_t ntiles = g.cols * g.rows;
   const uint32_t qpr = g.bw >> 2;  // quads (4 px = 16 B) per full tile row
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
       const uint32_t w4[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
       for (int k = 0; k < 4; k += 2) {
-        OklabFast2 o = lms_fast_pair2(w4[k], w4[k + 1], lut_lane_addr);
+        OklabFast2 o = lms_fast_pair2(w4[k], w4[k + 1], lut_base, lane4);
         if (MASK && !inq) { o.l = 0ull; o.m = 0ull; o.s = 0ull; }
         c[j * 2 + (k >> 1)] = o;
         sl2 = add2(sl2, o.l); sm2 = add2(sm2, o.m); ss2 = add2(ss2, o.s);
@@ -2106,7 +2117,8 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, uint8_t* opaque,
                                     uint32_t* zero_word, cudaStream_t s, int sm_count, uint64_t* launches) {
   const uint32_t ntiles = g.cols * g.rows;
-  const size_t smem = 256 * 32 * sizeof(float);
+  const size_t smem_any = 256 * 32 * sizeof(float);
+  size_t smem = 256 * kMadLutStride * sizeof(float);  // k_analyze_mad_rgba
   const bool aligned = g.C == 4 && (g.bw % 4 == 0) && (g.W % 4 == 0) && (pitch % 16 == 0) &&
                        ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
   const uint32_t quads = (g.bw / 4) * g.bh;
@@ -2132,10 +2144,12 @@ cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom
       e = launch_pdl(k_analyze_mad_rgba<32, 4>, clamp_grid((ntiles + 7) / 8, sm_count * PXZ_MAD_MINBLOCKS), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
     }
   } else if (g.C == 4) {
+    smem = smem_any;
     e = set_smem(k_analyze_mad_any<4>, smem);
     if (e != cudaSuccess) return e;
     e = launch_pdl(k_analyze_mad_any<4>, clamp_grid(ntiles, sm_count * 3), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);
   } else {
+    smem = smem_any;
     e = set_smem(k_analyze_mad_any<3>, smem);
     if (e != cudaSuccess) return e;
     e = launch_pdl(k_analyze_mad_any<3>, clamp_grid(ntiles, sm_count * 3), kThreads, smem, s, img, pitch, g, vx, opaque, zero_word);

@@ -434,40 +434,31 @@ __device__ __forceinline__ void tma_shrink_tile(TFeed& f, TQueue& q, const CUten
         if (A > 4) w45 = lds_u64x2(wrow + 32);
       }
     }
-    // output row o is complete in accumulator slot `slot`
-    u64 v[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = 0ull;
-#define PXZ_TAKE(S)                                        \
-  case S:                                                  \
-    if (S < A) {                                           \
-      _Pragma("unroll") for (int c = 0; c < NC; ++c) {     \
-        v[c] = acc[S < A ? S : 0][c];                      \
-        acc[S < A ? S : 0][c] = 0ull;                      \
-      }                                                    \
-    }                                                      \
-    break;
-    switch (slot) {
-      PXZ_TAKE(0)
-      PXZ_TAKE(1)
-      PXZ_TAKE(2)
-      PXZ_TAKE(3)
-      PXZ_TAKE(4)
-      default:
-        if (5 < A) {
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            v[c] = acc[5 < A ? 5 : 0][c];
-            acc[5 < A ? 5 : 0][c] = 0ull;
-          }
-        }
-        break;
-    }
-#undef PXZ_TAKE
+    // output row o is complete in accumulator slot `slot`: to the strip, slot cleared
     {
-      float4* srow = strip + (o - batch0) * kTStripStride + lane;
-      srow[0] = make_float4(lo2(v[0]), lo2(v[1]), lo2(v[2]), NC > 3 ? lo2(v[NC > 3 ? 3 : 0]) : 0.f);
-      srow[32] = make_float4(hi2(v[0]), hi2(v[1]), hi2(v[2]), NC > 3 ? hi2(v[NC > 3 ? 3 : 0]) : 0.f);
+      // one short block per slot behind a real branch: the stores and the clears are volatile asm, so the compiler cannot
+      // turn the switch into selects over all six slots (it did: 88 instructions per finished row)
+      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(strip + (o - batch0) * kTStripStride + lane);
+#define PXZ_TAKE(S)                                                                                                   \
+  case S:                                                                                                             \
+    if (S < A) {                                                                                                      \
+      constexpr int S_ = S < A ? S : 0;                                                                               \
+      asm volatile("{\n.reg .f32 l<4>, h<4>;\nmov.b64 {l0, h0}, %1;\nmov.b64 {l1, h1}, %2;\nmov.b64 {l2, h2}, %3;\nmov.b64 {l3, h3}, %4;\n" \
+                   "st.shared.v4.f32 [%0], {l0, l1, l2, l3};\nst.shared.v4.f32 [%0 + 512], {h0, h1, h2, h3};\n}"    \
+                   ::"r"(sa), "l"(acc[S_][0]), "l"(acc[S_][1]), "l"(acc[S_][2]), "l"(NC > 3 ? acc[S_][NC > 3 ? 3 : 0] : 0ull) : "memory"); \
+      _Pragma("unroll") for (int c = 0; c < NC; ++c) asm volatile("mov.b64 %0, 0;" : "=l"(acc[S_][c]));               \
+    }                                                                                                                 \
+    break;
+      switch (slot) {
+        PXZ_TAKE(0)
+        PXZ_TAKE(1)
+        PXZ_TAKE(2)
+        PXZ_TAKE(3)
+        PXZ_TAKE(4)
+        default:
+          PXZ_TAKE(5)
+      }
+#undef PXZ_TAKE
     }
     ++o;
     slot = slot + 1 == (uint32_t)A ? 0u : slot + 1;
