@@ -388,6 +388,10 @@ __device__ __forceinline__ void tma_shrink_tile(TFeed& f, TQueue& q, const CUten
   for (int s = 0; s < A; ++s)
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[s][c] = 0ull;
+  // shared-space address of this lane's column of the strip, made opaque: derived from the thread index, the compiler
+  // would otherwise rebuild it (two S2R and an IMAD) for every finished row
+  uint32_t strip_lane_sa = (uint32_t)__cvta_generic_to_shared(strip + lane);
+  asm volatile("mov.u32 %0, %0;" : "+r"(strip_lane_sa));
   const u64 magic = pk2(-8388608.0f, -8388608.0f);
   const uint32_t endp = vtab + sh * (A * 8);  // end[o], after the table rows
   // row 0: pixels and weights
@@ -401,44 +405,46 @@ __device__ __forceinline__ void tma_shrink_tile(TFeed& f, TQueue& q, const CUten
   uint32_t r = 0, o = 0, slot = 0, batch0 = 0;
   uint32_t e = lds_u32(endp);
   const uint32_t nbox = (sh + kTBoxRows - 1) / kTBoxRows;
-  for (;;) {
-    while (r <= e) {
-      // this row's operands
-      u64 pp[NC];
-      pp[0] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7440))), magic);
-      pp[1] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7441)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7441))), magic);
-      pp[2] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7442))), magic);
-      if (NC > 3) pp[NC > 3 ? 3 : 0] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7443)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7443))), magic);
-      {
-        const u64 w[6] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
+  // one source row: its taps into the live accumulators, then the next row's operands
+  auto one_row = [&]() {
+    // this row's operands
+    u64 pp[NC];
+    pp[0] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7440))), magic);
+    pp[1] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7441)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7441))), magic);
+    pp[2] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7442))), magic);
+    if (NC > 3) pp[NC > 3 ? 3 : 0] = add2(pk2(__uint_as_float(__byte_perm(px.x, 0x4B000000u, 0x7443)), __uint_as_float(__byte_perm(px.y, 0x4B000000u, 0x7443))), magic);
+    {
+      const u64 w[6] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
 #pragma unroll
-        for (int s = 0; s < A; ++s)
+      for (int s = 0; s < A; ++s)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) mac2_acc<MODE>(acc[s][c], pp[c], w[s], k);
-      }
-      // next row's operands, into the registers this row's just left (the pixels of row r are converted: a box whose
-      // last row that was is free)
-      ++r;
-      ++rib;
-      if (r < sh) {
-        if (rib == (uint32_t)kTBoxRows) {
-          tfeed_release(f, tm, q);
-          box = tfeed_wait(f) + lane * 8;
-          ++boxes_read;
-          rib = 0;
-        }
-        px = lds_u32x2(box + rib * 256);
-        wrow += A * 8;
-        w01 = lds_u64x2(wrow);
-        if (A > 2) w23 = lds_u64x2(wrow + 16);
-        if (A > 4) w45 = lds_u64x2(wrow + 32);
-      }
+        for (int c = 0; c < NC; ++c) mac2_acc<MODE>(acc[s][c], pp[c], w[s], k);
     }
+    // next row's operands, into the registers this row's just left (the pixels of row r are converted: a box whose
+    // last row that was is free)
+    ++r;
+    ++rib;
+    if (r < sh) {
+      if (rib == (uint32_t)kTBoxRows) {
+        tfeed_release(f, tm, q);
+        box = tfeed_wait(f) + lane * 8;
+        ++boxes_read;
+        rib = 0;
+      }
+      px = lds_u32x2(box + rib * 256);
+      wrow += A * 8;
+      w01 = lds_u64x2(wrow);
+      if (A > 2) w23 = lds_u64x2(wrow + 16);
+      if (A > 4) w45 = lds_u64x2(wrow + 32);
+    }
+  };
+  for (;;) {
+    while (r <= e) one_row();  // (two rows per trip: no gain per level, and the larger code cost 5 us on the mixed frame)
     // output row o is complete in accumulator slot `slot`: to the strip, slot cleared
     {
       // one short block per slot behind a real branch: the stores and the clears are volatile asm, so the compiler cannot
       // turn the switch into selects over all six slots (it did: 88 instructions per finished row)
-      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(strip + (o - batch0) * kTStripStride + lane);
+      const uint32_t sa = strip_lane_sa + (o - batch0) * (kTStripStride * 16);
 #define PXZ_TAKE(S)                                                                                                   \
   case S:                                                                                                             \
     if (S < A) {                                                                                                      \
