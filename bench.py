@@ -65,27 +65,56 @@ def synth_image_np(seed: int, w: int, h: int) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], -1))
 
 
-def synth_rows_device(torch, y0, y1, width, seed, device, chunk=512):
-    """uint8 [y1-y0, width, 4] on the device: smooth base + per-64x64-tile noise whose amplitude is a hash of the tile
-    (independent of the sharding), alpha 255.  Used for the frames that are too large to cross PCIe (C4) or too many (C5)."""
-    out = torch.empty((y1 - y0, width, 4), dtype=torch.uint8, device=device)
-    out[..., 3] = 255
-    xx = torch.arange(width, device=device, dtype=torch.float32)
-    tx = (torch.arange(width, device=device) // 64).to(torch.int64)
-    amps = torch.tensor([0, 1, 2, 4, 8, 16, 32, 64], device=device, dtype=torch.float32)
-    for g0 in range((y0 // chunk) * chunk, y1, chunk):  # chunks are aligned globally: the pixels do not depend on the sharding
-        yy = torch.arange(g0, g0 + chunk, device=device, dtype=torch.float32)[:, None]
-        ty = (torch.arange(g0, g0 + chunk, device=device) // 64).to(torch.int64)[:, None]
-        h = (ty * 73856093 + tx[None, :] * 19349663 + seed * 83492791) & 0x7FFFFFFF
-        amp = amps[(h >> 7) % 8]
-        g = torch.Generator(device=device)
+class DeviceSynth:
+    """Frames generated on the device: smooth base + per-64x64-tile noise whose amplitude is a hash of the tile, alpha 255.
+    The generator is seeded per 64-row band of the FRAME, so the pixels depend neither on the sharding nor on its layout
+    (contiguous runs or interleaved block rows).  Used for the frames that are too large to cross PCIe (C4) or too many (C5)."""
+
+    BAND = 64
+
+    def __init__(self, torch, width, seed, device):
+        self.torch, self.width, self.seed, self.device = torch, width, seed, device
+        self.xx = torch.arange(width, device=device, dtype=torch.float32)
+        self.tx = (torch.arange(width, device=device) // 64).to(torch.int64)
+        self.amps = torch.tensor([0, 1, 2, 4, 8, 16, 32, 64], device=device, dtype=torch.float32)
+
+    def band(self, g0, out):
+        """rows [g0, g0 + out.shape[0]) of the frame (g0 a multiple of 64, at most 64 rows) into out[:, :, 0:3]"""
+        torch, seed, n = self.torch, self.seed, self.BAND
+        yy = torch.arange(g0, g0 + n, device=self.device, dtype=torch.float32)[:, None]
+        ty = (torch.arange(g0, g0 + n, device=self.device) // 64).to(torch.int64)[:, None]
+        h = (ty * 73856093 + self.tx[None, :] * 19349663 + seed * 83492791) & 0x7FFFFFFF
+        amp = self.amps[(h >> 7) % 8]
+        g = torch.Generator(device=self.device)
         g.manual_seed(seed * 1000003 + g0)
-        a, b = max(y0, g0), min(y1, g0 + chunk)
+        xx = self.xx
         for ch, base in enumerate((128 + 96 * torch.sin(xx[None, :] / 9700.0 + seed), 128 + 96 * torch.cos(yy / 13100.0),
                                    128 + 64 * torch.sin((xx[None, :] + yy) / 6100.0))):
-            noise = (torch.rand((chunk, width), device=device, generator=g) - 0.5) * 2 * amp
+            noise = (torch.rand((n, self.width), device=self.device, generator=g) - 0.5) * 2 * amp
             full = torch.clamp(torch.round(base + noise), 0, 255).to(torch.uint8)
-            out[a - y0:b - y0, :, ch] = full[a - g0:b - g0]
+            out[:, :, ch] = full[:out.shape[0]]
+
+
+def synth_rows_device(torch, y0, y1, width, seed, device):
+    """uint8 [y1-y0, width, 4] on the device: rows [y0, y1) of the synthetic frame (y0 a multiple of 64)."""
+    out = torch.empty((y1 - y0, width, 4), dtype=torch.uint8, device=device)
+    out[..., 3] = 255
+    syn = DeviceSynth(torch, width, seed, device)
+    for g0 in range(y0, y1, DeviceSynth.BAND):
+        syn.band(g0, out[g0 - y0:min(y1, g0 + DeviceSynth.BAND) - y0])
+    return out
+
+
+def synth_block_rows_device(torch, rows_idx, height, width, seed, device):
+    """The same frame's block rows `rows_idx` (64 px each) stacked: a rank's local image in the interleaved layout."""
+    hs = [min(height, (g + 1) * 64) - g * 64 for g in rows_idx]
+    out = torch.empty((sum(hs), width, 4), dtype=torch.uint8, device=device)
+    out[..., 3] = 255
+    syn = DeviceSynth(torch, width, seed, device)
+    y = 0
+    for g, n in zip(rows_idx, hs):
+        syn.band(g * 64, out[y:y + n])
+        y += n
     return out
 
 
@@ -290,10 +319,42 @@ def run_sharded_c4(torch, dist, N, S, args, rank, world, local_rank, device):
         res[name] = {"MPps": round(side * side / (ms / 1e3) / 1e6, 1), "ms": round(ms, 3), "ms_per_rank": per_rank_ms,
                      "payload_fraction": round(int(chk[2]) / (side * side * 4), 4),
                      "checksum": [int(chk[0]), int(chk[1])]}
+    del src, dst, img, out
+    torch.cuda.empty_cache()
+    # the default mode again with INTERLEAVED block rows (row g of the frame on rank g mod N, sharding.cyclic_block_rows):
+    # the cost of a block row follows the frame's content, which changes slowly down the frame, so contiguous runs are
+    # uneven (two of eight ranks carry 40 % more work above) while every N-th row gives each rank the same level mix
+    rows_idx = S.cyclic_block_rows(-(-side // BS), world, rank)
+    src = synth_block_rows_device(torch, rows_idx, side, side, 7, device)
+    dst = torch.empty_like(src)
+    img = ctx.image_wrap(src.data_ptr(), side, src.shape[0], 4, side * 4)
+    out = ctx.image_wrap(dst.data_ptr(), side, src.shape[0], 4, side * 4)
+
+    def step_i():
+        pl = img.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+        pl.expand_to_image(FILTER_UP, out)
+        pl.free()
+    ms, mine = timed_region(torch, dist, world, device, step_i, args.extra_reps)
+    pl = img.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, 0)
+    descs, px = pl.download()
+    pl.free()
+    chk = torch.tensor([int(descs["w"].astype(np.uint64).sum() * 65537 + descs["h"].astype(np.uint64).sum()),
+                        int(px.astype(np.uint64).sum()), int(px.size)], device=device, dtype=torch.int64)
+    per_rank = torch.tensor([mine], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(chk)
+        g = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(g, per_rank)
+        per_rank_ms = [round(float(t.item()), 3) for t in g]
+    else:
+        per_rank_ms = [round(mine, 3)]
+    res["default_interleaved"] = {"MPps": round(side * side / (ms / 1e3) / 1e6, 1), "ms": round(ms, 3), "ms_per_rank": per_rank_ms,
+                                  "payload_fraction": round(int(chk[2]) / (side * side * 4), 4), "checksum": [int(chk[0]), int(chk[1])],
+                                  "same_result_as_contiguous": [int(chk[0]), int(chk[1])] == res["default"]["checksum"]}
     res["note"] = ("normalise_global = the extension of BASELINE config 4: reference-order Oklab values for every block + one NCCL "
                    "min all-reduce of {min, -max} per shrink (the only exchange); checksum = sum over ranks of descriptor dims and "
-                   "payload bytes: it must be the same at every N")
-    res["config"] = f"C4 synthetic {side}x{side} RGBA8 generated on the device, 64x64 blocks, contiguous block-row shards, Oklab-MAD k=1, Lanczos3 / Lanczos3, encode+decode, device-resident"
+                   "payload bytes: it must be the same at every N and in both layouts; default_interleaved = block row g of the frame on rank g mod N")
+    res["config"] = f"C4 synthetic {side}x{side} RGBA8 generated on the device, 64x64 blocks, block-row shards (contiguous runs; default_interleaved: every N-th row), Oklab-MAD k=1, Lanczos3 / Lanczos3, encode+decode, device-resident"
     res["blocks"] = (side // BS) ** 2
     del src, dst
     torch.cuda.empty_cache()
@@ -315,7 +376,7 @@ def run_batch_c5(torch, dist, N, S, args, rank, world, local_rank, device):
     for k in range(distinct_stacks):
         t = torch.empty((stack, h, w, 4), dtype=torch.uint8, device=device)
         for i in range(stack):
-            t[i] = synth_rows_device(torch, 0, h, w, 100 + mine[(k * stack + i) % len(mine)], device, chunk=h)
+            t[i] = synth_rows_device(torch, 0, h, w, 100 + mine[(k * stack + i) % len(mine)], device)
         srcs.append(t)
     outs = [torch.empty((stack, h, w, 4), dtype=torch.uint8, device=device) for _ in ctxs]
     imgs = [[c.image_wrap_batch(t.data_ptr(), w, h, 4, w * 4, stack) for t in srcs] for c in ctxs]

@@ -284,3 +284,47 @@ def test_merge_shard_containers_host():
         S.merge_shard_containers([b"", b""], w, h)
     with pytest.raises(ValueError):
         S.merge_shard_containers(files[::-1], w, h)         # the partial row must come last
+
+
+def test_interleaved_block_row_shards_host():
+    """Interleaved layout (block row g -> rank g mod world): merged descriptors / payload / container file equal the
+    single-process result, for worlds with and without empty ranks and a partial last block row."""
+    S = P.sharding
+    assert S.cyclic_block_rows(10, 4, 1) == [1, 5, 9] and S.cyclic_block_rows(3, 8, 5) == []
+    assert sorted(sum((S.cyclic_block_rows(1024, 8, r) for r in range(8)), [])) == list(range(1024))
+    rng = np.random.default_rng(4)
+    w, h, bs = 150, 210, 32  # 7 block rows, the last one partial
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[40:120, 10:90] = (9, 200, 77)
+    whole = O.shrink(img, bs, bs, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3)
+    whole_file = O.container_encode(whole, 4)
+    cols, rows = O.grid(w, h, bs, bs)[0], -(-h // bs)
+    for world in (1, 2, 3, 7, 9):
+        parts, files = [], []
+        back = np.zeros_like(img)
+        for rank in range(world):
+            idx = S.cyclic_block_rows(rows, world, rank)
+            local = S.gather_block_rows(img, bs, idx)
+            S.scatter_block_rows(local, back, bs, idx)
+            if local.shape[0]:
+                sh = O.shrink(local, bs, bs, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3)
+                parts.append((sh.descs, sh.payload))
+                files.append(O.container_encode(sh, 4))
+            else:
+                parts.append((np.zeros(0, P.native.DESC_DTYPE), np.zeros(0, np.uint8)))
+                files.append(b"")
+        assert np.array_equal(back, img)
+        descs, pixels = S.merge_shards_cyclic(parts, cols)
+        assert np.array_equal(descs, whole.descs.astype(descs.dtype)) and np.array_equal(pixels, whole.payload), world
+        assert S.merge_shard_containers_cyclic(files, w, h) == whole_file, world
+    with pytest.raises(ValueError):
+        S.merge_shard_containers_cyclic([files[0]], w, h)
+    with pytest.raises(ValueError):
+        S.merge_shard_containers_cyclic([b"garbage" * 5], w, h)
+    # 7 rows over 3 ranks = 3 + 2 + 2: with ranks 0 and 2 swapped the first rank runs out of rows
+    p3 = []
+    for rank in range(3):
+        sh = O.shrink(S.gather_block_rows(img, bs, S.cyclic_block_rows(rows, 3, rank)), bs, bs, O.METRIC_OKLAB_MAD, 0.02, O.LANCZOS3)
+        p3.append((sh.descs, sh.payload))
+    with pytest.raises(ValueError):
+        S.merge_shards_cyclic([p3[2], p3[1], p3[0]], cols)

@@ -100,6 +100,17 @@ def _worker(rank, world, port, out_dir):
             dist.all_gather_object(files, mine_file)
             assert S.merge_shard_containers(files, w, h) == a
 
+    # 2b. the interleaved layout (block row g -> rank g mod world) stitches to the same frame and the same file
+    rows = -(-h // bs)
+    idx = S.cyclic_block_rows(rows, world, rank)
+    local = O.shrink(S.gather_block_rows(img, bs, idx), bs, bs, O.METRIC_OKLAB_MAD, 0.7, O.LANCZOS3)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (local.descs, local.payload, O.container_encode(local, 4)))
+    whole = O.shrink(img, bs, bs, O.METRIC_OKLAB_MAD, 0.7, O.LANCZOS3)
+    descs, pixels = S.merge_shards_cyclic([(d, p) for d, p, _ in gathered], O.grid(w, h, bs, bs)[0])
+    assert np.array_equal(descs, whole.descs.astype(descs.dtype)) and np.array_equal(pixels, whole.payload)
+    assert S.merge_shard_containers_cyclic([f for _, _, f in gathered], w, h) == O.container_encode(whole, 4)
+
     # 3. batch round-robin: every image is processed by exactly one rank
     mine_idx = S.round_robin(7, world, rank)
     allidx = [None] * world
