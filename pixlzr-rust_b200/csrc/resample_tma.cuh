@@ -31,7 +31,10 @@ constexpr int kTWarps = PXZ_TMA_WARPS;         // warps (= tiles in flight) per 
 constexpr int kTBoxRows = PXZ_TMA_BOXROWS;     // source rows per tensor copy
 constexpr int kTSlots = PXZ_TMA_SLOTS;         // ring slots per warp
 constexpr int kTBoxBytes = kTBoxRows * 64 * 4; // 1 KB
-constexpr int kTStripRows = 8;
+#ifndef PXZ_TMA_STRIPROWS
+#define PXZ_TMA_STRIPROWS 8
+#endif
+constexpr int kTStripRows = PXZ_TMA_STRIPROWS;  // output rows per horizontal batch (a power of two)
 constexpr int kTStripStride = 65;              // float4 per strip row
 constexpr int kTVtabWords = 64 * 12 + 64;      // slide2 table of a 64-sample axis with 6 slots + end[64]
 constexpr int kTHtabWords = 512;

@@ -965,6 +965,43 @@ def test_device_container_api_equals_three_calls():
     assert P.Pixlzr.encode_image_to_vec(img, 48, 24, P.FilterType.Triangle, 2.0, directionally=True) == pix.encode_to_vec()
 
 
+def test_interleaved_block_row_shards_equal_the_whole_frame(ctx):
+    """§8(e), interleaved layout: block row g of the frame on rank g mod N (here 3 ranks, one GPU).  Descriptors, payload,
+    the decoded frame and the stitched container file equal the single-GPU result."""
+    S = P.sharding
+    w, h, bs = 333, 407, 32   # 13 block rows, the last one partial
+    img = _spread_image(w, h, 4, bs, seed=22)
+    cols, rows = -(-w // bs), -(-h // bs)
+    d = ctx.image_upload(img)
+    pl = d.shrink(bs, bs, 0, 0.3, O.LANCZOS3, N.FLAG_EXACT_VALUES)
+    wd, wp = pl.download()
+    whole_file = pl.to_container(4, True)
+    whole_out = ctx.image_alloc(w, h, 4)
+    pl.expand_to_image(O.LANCZOS3, whole_out)
+    whole_px = whole_out.download()
+    pl.free(); d.free(); whole_out.free()
+    parts, files = [], []
+    back = np.zeros_like(img)
+    for rank in range(3):
+        idx = S.cyclic_block_rows(rows, 3, rank)
+        local = S.gather_block_rows(img, bs, idx)
+        ds = ctx.image_upload(local)
+        ps = ds.shrink(bs, bs, 0, 0.3, O.LANCZOS3, N.FLAG_EXACT_VALUES)
+        parts.append(ps.download())
+        files.append(ps.to_container(4, True))
+        do = ctx.image_alloc(w, local.shape[0], 4)
+        ps.expand_to_image(O.LANCZOS3, do)
+        S.scatter_block_rows(do.download(), back, bs, idx)
+        ps.free(); ds.free(); do.free()
+    descs, pixels = S.merge_shards_cyclic(parts, cols)
+    nb = cols * rows
+    for f in ("w", "h", "offset", "value"):
+        assert np.array_equal(descs[f][:nb], wd[f][:nb]), f
+    assert pixels.size == wp.size and np.array_equal(pixels, wp)
+    assert np.array_equal(back, whole_px)
+    assert S.merge_shard_containers_cyclic(files, w, h) == whole_file
+
+
 def test_device_container_of_block_row_shards_stitches_to_the_whole_file(ctx):
     """§8(e): every rank writes the file of its own block rows on its GPU; the host stitches them (here: 3 shards, one GPU)."""
     S = P.sharding
