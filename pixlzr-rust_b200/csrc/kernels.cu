@@ -786,7 +786,14 @@ __global__ void __launch_bounds__(kThreads) k_band_list(const float* __restrict_
 }
 
 // list == nullptr: every tile (PXZ_FLAG_EXACT_VALUES); else the *count tiles of the list, one per CTA round-robin
-constexpr int kExactThreads = 1024;  // wide CTA: the per-pixel conversion is parallel, only the sums are sequential
+// Threads of the CTA that recomputes one guard-band tile.  The per-pixel conversion is parallel and bound by the FP64 pipe,
+// the sums are a sequential chain on four lanes, so the CTA mostly waits — and while it does, a 1024-thread CTA holds a whole
+// SM's registers against the kernels of the other streams.  Measured on the bench (4 streams): 1024 threads 132.6 GP/s /
+// 48.2 us single-stream, 512: 138.0 / 41.4, 384: 139.9 / 44.2, 256: 139.2 / 50.6, 128: 136.2 / 70.0.
+#ifndef PXZ_EXACT_THREADS
+#define PXZ_EXACT_THREADS 384
+#endif
+constexpr int kExactThreads = PXZ_EXACT_THREADS;
 template <int C>
 __global__ void __launch_bounds__(kExactThreads) k_mad_exact(const uint8_t* __restrict__ img, size_t pitch, Geom g, float* vx,
                                                              const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
