@@ -935,24 +935,54 @@ pxz_status pxz_shrink(pxz_ctx* ctx, const pxz_image* img, uint32_t bw, uint32_t 
 
   // with global normalisation every value depends on the exact min and max, so the Oklab path
   // runs in reference order for all blocks
-  const bool exact_all = (flags & PXZ_FLAG_EXACT_VALUES) != 0 || (normalise && metric == PXZ_METRIC_OKLAB_MAD);
-  st = run_analysis(ctx, img, g, metric, exact_all, (metric == PXZ_METRIC_OKLAB_MAD && !exact_all) ? &vm : nullptr);
+  const bool exact_all = (flags & PXZ_FLAG_EXACT_VALUES) != 0;
+  // Global normalisation of the Oklab values on the fast path: the exact extremes come from the few tiles that can hold
+  // them, and the guard band (scaled by 1 / range) then decides as in the default mode which tiles need their
+  // reference-order value; with PXZ_FLAG_EXACT_VALUES every tile is computed in reference order as before.
+  const bool fast_norm = normalise && metric == PXZ_METRIC_OKLAB_MAD && !exact_all;
+  st = run_analysis(ctx, img, g, metric, exact_all, (metric == PXZ_METRIC_OKLAB_MAD && !exact_all && !normalise) ? &vm : nullptr);
   if (st != PXZ_OK) return bail(st);
 
   if (normalise) {
-    {
+    auto minmax = [&]() -> pxz_status {
       ProfScope prof(ctx, K_MINMAX);
       cudaError_t me = launch_minmax(ctx->d_vx, metric == PXZ_METRIC_SOBEL_DIR ? ctx->d_vy : nullptr, nblocks, ctx->d_minmax,
                                      ctx->stream, &ctx->launches);
       if (me != cudaSuccess) {
         cudaGetLastError();
-        return bail(fail(ctx, PXZ_E_CUDA, std::string("minmax: ") + cudaGetErrorString(me)));
+        return fail(ctx, PXZ_E_CUDA, std::string("minmax: ") + cudaGetErrorString(me));
       }
+      return PXZ_OK;
+    };
+    if ((st = minmax()) != PXZ_OK) return bail(st);
+    if (fast_norm) {
+      {
+        ProfScope prof(ctx, K_MAD_EXACT);
+        cudaError_t ee = launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, ctx->d_vx, ctx->d_opaque, nullptr, &ctx->thr, &ctx->band,
+                                                  ctx->d_minmax, ctx->d_list, ctx->d_list + nblocks, ctx->stream, ctx->sm_count,
+                                                  &ctx->launches);
+        if (ee != cudaSuccess) {
+          cudaGetLastError();
+          return bail(fail(ctx, PXZ_E_CUDA, std::string("extremes: ") + cudaGetErrorString(ee)));
+        }
+      }
+      if ((st = minmax()) != PXZ_OK) return bail(st);  // over the patched values: the exact extremes
     }
     bool peers_ok = true;
     st = exchange_minmax(ctx, true, &peers_ok);
     if (st != PXZ_OK) return st;
     if (!peers_ok) return fail(ctx, PXZ_E_NCCL, "another rank failed before the min/max exchange");
+    if (fast_norm) {
+      ProfScope prof(ctx, K_MAD_EXACT);
+      cudaError_t ee = cudaMemsetAsync(ctx->d_list + nblocks, 0, sizeof(uint32_t), ctx->stream);  // the list counter
+      if (ee == cudaSuccess)
+        ee = launch_analyze_mad_exact(img->d, img->pitch, g, ctx->d_vx, ctx->d_vx, ctx->d_opaque, &vm, &ctx->thr, &ctx->band, ctx->d_minmax,
+                                      ctx->d_list, ctx->d_list + nblocks, ctx->stream, ctx->sm_count, &ctx->launches);
+      if (ee != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, PXZ_E_CUDA, std::string("guard band: ") + cudaGetErrorString(ee));
+      }
+    }
   }
 
   pxz_payload* p = nullptr;

@@ -740,18 +740,31 @@ __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, c
 //   with max L <= 1, max|a| <= 0.276, max|b| <= 0.312 over the sRGB gamut, max alpha <= 1 (0 if the tile is opaque:
 //   its alpha sum is exact);  shifting a mean by delta moves that channel's MAD by at most |delta|;
 //   sequential f32 sum of the deviations: relative n * 2^-24;  fast arithmetic (SFU cube roots, tree sums): band.abs_raw.
+// bound of |reference-order value - fast value| of a tile of npx pixels, raw-metric units
+__device__ __forceinline__ float guard_tol_raw(float raw, bool opaque, int C, uint32_t npx, const GuardBand& band) {
+  const float nu = (float)npx * 5.9604645e-8f;  // n * 2^-24
+  const float gamut = (C == 4 && !opaque) ? 2.588f : 1.588f;
+  return 0.375f * nu * gamut + (nu + band.rel) * fabsf(raw) + band.abs_raw;
+}
+
 __device__ __forceinline__ bool in_guard_band(float raw, bool opaque, int C, const Tile& t, const ValueMap& vm,
                                               const LevelThresholds& thr, const GuardBand& band, const float* minmax) {
   float v0, v1;
   map_values(vm, minmax, raw, raw, v0, v1);
   const float pv = parse_value_dev(v0);
   if (pv != pv) return true;
-  const float n = (float)(t.tw * t.th);
-  const float nu = n * 5.9604645e-8f;  // n * 2^-24
-  const float gamut = (C == 4 && !opaque) ? 2.588f : 1.588f;
-  const float tol_raw = 0.375f * nu * gamut + (nu + band.rel) * fabsf(raw) + band.abs_raw;
-  const float scale = (vm.mode == 0) ? fabsf(vm.factor) * 10.0f : 1.0f;
-  const float tol = tol_raw * scale * 1.0001f + 1e-30f;
+  const float tol_raw = guard_tol_raw(raw, opaque, C, t.tw * t.th, band);
+  float scale = (vm.mode == 0) ? fabsf(vm.factor) * 10.0f : 1.0f;
+  float slack = 1e-30f;
+  if (vm.normalise) {
+    // v' = (v - min) / (max - min) with the EXACT min and max (k_extreme_list + recompute): an error of the raw value is
+    // divided by the range; the subtraction, the division and the two products of the map round once each
+    const float rg = __fsub_rn(-minmax[1], minmax[0]);
+    if (!(rg > 0.f)) return false;  // empty range: every value maps to 0
+    scale /= rg;
+    slack += 5e-7f * fabsf(pv);
+  }
+  const float tol = tol_raw * scale * 1.0001f + slack;
   // only thresholds that change the size of this tile matter
   uint32_t nmax = max(t.tw, t.th);
   int kmax = 0;
@@ -783,6 +796,28 @@ __global__ void __launch_bounds__(kThreads) k_band_list(const float* __restrict_
   if (tile >= ntiles) return;
   const Tile t = tile_of(g, tile);
   if (in_guard_band(vx_fast[tile], opaque[tile] != 0, C, t, vm, thr, band, minmax)) list[atomicAdd(count, 1u)] = tile;
+}
+
+// Global normalisation on the fast path: the tiles whose reference-order value could be the minimum or the maximum of the
+// image.  minmax = {min, -max} of the FAST values.  The exact minimum is at most fast_min + T (T = the bound at the
+// minimum, taken for a full non-opaque tile), so a tile with raw - tol > fast_min + T cannot hold it — and its fast value
+// stays above the exact minimum, so a second k_minmax over the patched values returns the exact extremes.
+__global__ void __launch_bounds__(kThreads) k_extreme_list(const float* __restrict__ vx_fast, const uint8_t* __restrict__ opaque,
+                                                           Geom g, int C, GuardBand band, const float* __restrict__ minmax,
+                                                           uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t ntiles = g.cols * g.rows;
+  const uint32_t tile = blockIdx.x * kThreads + threadIdx.x;
+  if (tile >= ntiles) return;
+  const Tile t = tile_of(g, tile);
+  const float raw = vx_fast[tile];
+  if (raw != raw) return;  // NaNs are ignored by the extension
+  const float mn = minmax[0], mx = -minmax[1];
+  const float tol = guard_tol_raw(raw, opaque[tile] != 0, C, t.tw * t.th, band) * 1.0001f;
+  const float t_min = guard_tol_raw(mn, false, C, g.bw * g.bh, band) * 1.0001f;
+  const float t_max = guard_tol_raw(mx, false, C, g.bw * g.bh, band) * 1.0001f;
+  if (raw - tol <= mn + t_min || raw + tol >= mx - t_max) list[atomicAdd(count, 1u)] = tile;
 }
 
 // list == nullptr: every tile (PXZ_FLAG_EXACT_VALUES); else the *count tiles of the list, one per CTA round-robin
@@ -2173,15 +2208,20 @@ cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geo
   cudaError_t e;
   const bool banded = vx_fast != nullptr;
   if (banded) {
-    // *count was zeroed by the fast analysis kernel that produced vx_fast (launch_analyze_mad_fast's zero_word)
+    // *count was zeroed by the fast analysis kernel that produced vx_fast (launch_analyze_mad_fast's zero_word), or by the
+    // caller between two lists of one image
     ++*launches;
-    e = launch_pdl(k_band_list, (ntiles + kThreads - 1) / kThreads, kThreads, 0, s, vx_fast, opaque, g, (int)g.C, *vm, *thr, *band, minmax,
-                                                                       list, count);
+    if (vm == nullptr)  // candidates for the image's extremes (global normalisation on the fast path)
+      e = launch_pdl(k_extreme_list, (ntiles + kThreads - 1) / kThreads, kThreads, 0, s, vx_fast, opaque, g, (int)g.C, *band, minmax, list, count);
+    else
+      e = launch_pdl(k_band_list, (ntiles + kThreads - 1) / kThreads, kThreads, 0, s, vx_fast, opaque, g, (int)g.C, *vm, *thr, *band, minmax,
+                     list, count);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   ++*launches;
-  // few banded tiles: one wide CTA per tile (latency); every tile: three narrow CTAs per SM (throughput)
+  // few listed tiles: one CTA per tile (latency); every tile: three narrow CTAs per SM (throughput).  A list can hold
+  // anything between a handful and all tiles (an image whose values all sit at the extremes): the grid covers both.
   const int threads = banded ? kExactThreads : kThreads;
   const int grid = clamp_grid(ntiles, (long long)sm_count * (banded ? 2 : 3));
   if (g.C == 4) {

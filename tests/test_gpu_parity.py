@@ -327,8 +327,33 @@ def test_normalise_global_extension(ctx):
     img = synth(512, 384, 4, seed=11)
     for metric, factor in ((O.METRIC_OKLAB_MAD, 0.05), (O.METRIC_SOBEL_DIR, 1.0)):
         ref = O.shrink(img, 64, 64, metric, factor, O.TRIANGLE, normalise_global=True, nthreads=8)
-        descs, pixels, _ = gpu_shrink(ctx, img, 64, 64, metric, factor, O.TRIANGLE, N.FLAG_NORMALISE_GLOBAL)
+        descs, pixels, _ = gpu_shrink(ctx, img, 64, 64, metric, factor, O.TRIANGLE, N.FLAG_NORMALISE_GLOBAL | N.FLAG_EXACT_VALUES)
         assert_same_payload(descs, pixels, ref, exact_values=True)
+        # without PXZ_FLAG_EXACT_VALUES the Oklab values take the fast path: exact extremes from the tiles that can hold them,
+        # reference-order values inside the guard band — dims, offsets and pixels stay bit-exact, stored values within tolerance
+        descs, pixels, _ = gpu_shrink(ctx, img, 64, 64, metric, factor, O.TRIANGLE, N.FLAG_NORMALISE_GLOBAL)
+        if metric == O.METRIC_SOBEL_DIR:
+            assert_same_payload(descs, pixels, ref, exact_values=True)
+        else:
+            assert np.array_equal(descs["w"], ref.descs["w"]) and np.array_equal(descs["h"], ref.descs["h"])
+            assert np.array_equal(descs["offset"], ref.descs["offset"]) and np.array_equal(pixels, ref.payload)
+            assert np.allclose(descs["value"], ref.descs["value"], rtol=2e-3, atol=2e-3 * float(np.max(ref.descs["value"])))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_normalise_global_fast_path_on_many_levels(ctx, seed):
+    """Global normalisation, fast path, on frames with many tiles per level and both extremes shared by several tiles
+    (flat tiles): the dims must equal the reference-order run of the same library (PXZ_FLAG_EXACT_VALUES) and the oracle."""
+    w, h = 1024, 768
+    img = _spread_image(w, h, 4, 64, seed=40 + seed)
+    img[0:128, 0:256] = (12, 200, 40, 255)      # flat tiles: several candidates for the minimum
+    rng = np.random.default_rng(seed)
+    img[640:768, 512:768, :3] = rng.integers(0, 256, (128, 256, 3), dtype=np.uint8)  # white noise: candidates for the maximum
+    for factor in (0.02, 0.05, 0.11):
+        ref = O.shrink(img, 64, 64, O.METRIC_OKLAB_MAD, factor, O.LANCZOS3, normalise_global=True, nthreads=8)
+        fast_d, fast_p, _ = gpu_shrink(ctx, img, 64, 64, O.METRIC_OKLAB_MAD, factor, O.LANCZOS3, N.FLAG_NORMALISE_GLOBAL)
+        assert np.array_equal(fast_d["w"], ref.descs["w"]) and np.array_equal(fast_d["h"], ref.descs["h"]), factor
+        assert np.array_equal(fast_d["offset"], ref.descs["offset"]) and np.array_equal(fast_p, ref.payload), factor
 
 
 # ---------------------------------------------------------------------------------------------

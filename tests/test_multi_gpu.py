@@ -42,7 +42,9 @@ def _worker(rank, world, port, out_dir):
     img = np.ascontiguousarray(np.concatenate([rgb, np.full((h, w, 1), 255, np.uint8)], -1))
     y0, y1 = S.shard_pixel_rows(h, bs, world, rank)
     for metric, factor in ((N.METRIC_SOBEL_DIR, 1.0), (N.METRIC_OKLAB_MAD, 0.05)):
-        descs, pixels = S.shrink_sharded(ctx, img[y0:y1], bs, bs, metric, factor, O.CATMULLROM, N.FLAG_NORMALISE_GLOBAL)
+        # PXZ_FLAG_EXACT_VALUES: the stored values are compared bit for bit below (without it the Oklab values take the
+        # fast path and only dims, offsets and pixels are exact; bench.py's nccl_parity block runs that variant)
+        descs, pixels = S.shrink_sharded(ctx, img[y0:y1], bs, bs, metric, factor, O.CATMULLROM, N.FLAG_NORMALISE_GLOBAL | N.FLAG_EXACT_VALUES)
         gathered = [None] * world
         dist.all_gather_object(gathered, (descs, pixels))
         if rank == 0:
