@@ -56,7 +56,9 @@ typedef enum {
 #define PXZ_FLAG_AFTER_IDENTITY 0x1u   /* `after = |x| x` as process() does (process/mod.rs:107-121)
                                           instead of `x * factor * 10` (pixlzr.rs:15,162)            */
 #define PXZ_FLAG_NORMALISE_GLOBAL 0x2u /* EXTENSION: v' = (v-min)/(max-min) over all blocks of the
-                                          image (all ranks of the communicator) before `after`       */
+                                          image (all ranks of the communicator) before `after`.  min
+                                          and max are the reference-order values of the extreme blocks
+                                          in every mode; dims and pixels are bit-exact in every mode  */
 #define PXZ_FLAG_EXACT_VALUES 0x4u     /* Oklab-MAD: run the reference-order (sequential f32) path on
                                           EVERY block, so stored values are bit-exact too.  Without
                                           it only blocks whose value lies near a level boundary are
