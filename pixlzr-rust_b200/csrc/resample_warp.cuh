@@ -613,10 +613,9 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
   ulonglong2 hwr[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) hwr[c] = (hact && (uint32_t)c < bpad) ? __ldg(hw + c) : make_ulonglong2(0ull, 0ull);
-  auto horizontal = [&](uint32_t oy0, uint32_t nrows, uint32_t pr) {  // pr: pair of strip rows (0 / 1)
+  auto horizontal = [&](uint32_t oy0, uint32_t nrows, const float4* tp) {  // tp: this lane's first sample of the row pair
     if (hact && hr < nrows) {
       Acc4<MODE> acc;
-      const float4* tp = htp + pr * kExpandPairPx;
       if (bpad == 8) expand_walk<MODE, 8>(acc, tp, hwr, k);
       else if (bpad == 4) expand_walk<MODE, 4>(acc, tp, hwr, k);
       else if (bpad == 2) expand_walk<MODE, 2>(acc, tp, hwr, k);
@@ -635,7 +634,57 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
     }
   };
 
-  if (sw <= 32) {
+  if (sw <= 4 && sh <= 4) {
+    // Tiny source (a block reduced to at most 4 x 4: three of the eight classes of the bench frame).  The whole vertical
+    // pass is done at once — lane = output rows 2 lane, 2 lane + 1 (the two lanes of the f32x2 operations), one source
+    // column at a time, every tap of the column (taps before a row's first one get weight +0, which leaves the sum as it
+    // is) — into a compact [row][4] array of intermediates; the horizontal pass then runs down the tile without the
+    // per-pair window / table-request bookkeeping of the general path (6.4 K -> 3 K instructions per tile).
+    const uint32_t y0 = 2 * lane;
+    u64 wp[4];  // (weight of row y0, weight of row y0 + 1) for source rows 0..3
+    {
+      float wa[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t y = min(y0 + r, dh - 1);
+        const float4 w4 = __ldg(g8 + 2 * y);
+        const uint32_t l = __ldg(gleft + y);
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = 0.f;
+#pragma unroll
+          for (int t = 0; t <= j; ++t) v = (l + t == (uint32_t)j) ? w[t] : v;
+          wa[r][j] = v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wp[j] = pk2(wa[0][j], wa[1][j]);
+    }
+    for (uint32_t x = 0; x < sw; ++x) {
+      u64 a[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) a[c] = 0ull;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((uint32_t)j < sh) {
+          const float4 pf = px_to_f4<MODE>(__ldg(src + (size_t)j * sw + x));
+          const float pc[4] = {pf.x, pf.y, pf.z, pf.w};
+#pragma unroll
+          for (int c = 0; c < NC; ++c) mac2_acc<MODE>(a[c], pk2(pc[c], pc[c]), wp[j], k);
+        }
+      }
+      float lo_[4] = {0.f, 0.f, 0.f, 0.f}, hi_[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < NC; ++c) unpk2(a[c], lo_[c], hi_[c]);
+      if (y0 < dh) strip[y0 * 4 + x] = make_float4(lo_[0], lo_[1], lo_[2], lo_[3]);
+      if (y0 + 1 < dh) strip[(y0 + 1) * 4 + x] = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
+    }
+    __syncwarp();
+    const float4* tp = strip + hr * 4 + hlo;  // the lane's first sample as in the general path, rows 4 samples apart
+    for (uint32_t oy0 = 0; oy0 < dh; oy0 += 2, tp += 8) horizontal(oy0, min(2u, dh - oy0), tp);
+    __syncwarp();
+  } else if (sw <= 32) {
     // vertical: lane = source column; a 7-row window of converted samples lives in registers and moves down with the
     // outputs' first tap.  Two output rows with the same first tap are the two lanes of one f32x2 accumulator.  Blocks
     // at most 16 wide use the upper half warp for the next pair of rows (own window, own table rows): 4 rows per pass.
@@ -727,8 +776,8 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
       }
       request(my + 2 * nh);
       __syncwarp();
-      horizontal(oy0, min(2u, dh - oy0), 0u);
-      if (nh == 2 && oy0 + 2 < dh) horizontal(oy0 + 2, min(2u, dh - oy0 - 2), 1u);
+      horizontal(oy0, min(2u, dh - oy0), htp);
+      if (nh == 2 && oy0 + 2 < dh) horizontal(oy0 + 2, min(2u, dh - oy0 - 2), htp + kExpandPairPx);
       __syncwarp();
     }
   } else {
@@ -756,7 +805,7 @@ __device__ __forceinline__ void expand_tile_warp(uint8_t* __restrict__ img, size
         if (has1) put(0u, r, lane + 32, a1);
       }
       __syncwarp();
-      horizontal(oy0, nrows, 0u);
+      horizontal(oy0, nrows, htp);
       __syncwarp();
     }
   }
