@@ -106,6 +106,10 @@ struct GuardBand {
 // appends to next (saves a memset launch per image)
 cudaError_t launch_analyze_mad_fast(const uint8_t* img, size_t pitch, const Geom& g, float* vx, uint8_t* opaque,
                                     uint32_t* zero_word, cudaStream_t s, int sm_count, uint64_t* launches);
+// Reference-order Oklab values.  vx_fast == NULL: every tile.  vx_fast != NULL: the tiles of a list built first from the
+// fast values — with vm != NULL the guard band of the level thresholds (k_band_list), with vm == NULL the tiles that can
+// hold the minimum or the maximum of the image (k_extreme_list; minmax = {min, -max} of the fast values).  *count must be
+// zero when the list is built (launch_analyze_mad_fast's zero_word, or a memset between two lists of one image).
 cudaError_t launch_analyze_mad_exact(const uint8_t* img, size_t pitch, const Geom& g, float* vx, const float* vx_fast,
                                      const uint8_t* opaque, const ValueMap* vm, const LevelThresholds* thr, const GuardBand* band,
                                      const float* minmax, uint32_t* list, uint32_t* count, cudaStream_t s, int sm_count,
