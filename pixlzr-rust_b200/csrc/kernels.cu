@@ -319,8 +319,9 @@ __global__ void __launch_bounds__(kThreads, PXZ_MAD_MINBLOCKS) k_analyze_mad_rgb
     load_tile(next_tile, nxt);
     // ---- group reduction 1 ----
     float sl = lo2(sl2) + hi2(sl2), sm = lo2(sm2) + hi2(sm2), ss = lo2(ss2) + hi2(ss2);
-    float sa = (float)asum;
-    sl = warp_sum(sl); sm = warp_sum(sm); ss = warp_sum(ss); sa = warp_sum(sa);
+    // the alpha bytes are summed as integers: one REDUX instead of five shuffle / add steps
+    float sa = (float)__reduce_add_sync(0xffffffffu, asum);
+    sl = warp_sum(sl); sm = warp_sum(sm); ss = warp_sum(ss);
     if (WPG > 1) {
       if (lane == 0) { s_r1[buf][warp][0] = sl; s_r1[buf][warp][1] = sm; s_r1[buf][warp][2] = ss; s_r1[buf][warp][3] = sa; }
       __syncthreads();
