@@ -328,3 +328,32 @@ def test_interleaved_block_row_shards_host():
         p3.append((sh.descs, sh.payload))
     with pytest.raises(ValueError):
         S.merge_shards_cyclic([p3[2], p3[1], p3[0]], cols)
+
+
+def test_bench_device_frames_do_not_depend_on_the_shard_layout():
+    """bench.py generates the gigapixel frame of C4 per rank: rows [y0, y1) in the contiguous layout, the rank's own block
+    rows in the interleaved one.  Both must be cuts of ONE frame (the checksum comparison across layouts and rank counts
+    relies on it) — checked here on the CPU device with a small frame whose last block row is partial."""
+    import sys
+
+    import torch
+
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+
+    S = P.sharding
+    w, h = 192, 64 * 5 + 24
+    whole = bench.synth_rows_device(torch, 0, h, w, 7, "cpu").numpy()
+    assert whole.shape == (h, w, 4) and (whole[..., 3] == 255).all()
+    a = bench.synth_rows_device(torch, 128, 256, w, 7, "cpu").numpy()
+    assert np.array_equal(a, whole[128:256])
+    rows = -(-h // 64)
+    for world in (2, 3):
+        back = np.zeros_like(whole)
+        for rank in range(world):
+            idx = S.cyclic_block_rows(rows, world, rank)
+            local = bench.synth_block_rows_device(torch, idx, h, w, 7, "cpu").numpy()
+            assert np.array_equal(local, S.gather_block_rows(whole, 64, idx))
+            S.scatter_block_rows(local, back, 64, idx)
+        assert np.array_equal(back, whole)
