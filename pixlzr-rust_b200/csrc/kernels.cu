@@ -625,6 +625,9 @@ __device__ __forceinline__ void oklab_ref(const float* lut, uint32_t r8, uint32_
   B = __fsub_rn(__fadd_rn(__fmul_rn(M2_20, l_), __fmul_rn(M2_21, m_)), __fmul_rn(0.8086757660f, s_));
 }
 
+#ifndef PXZ_EXACT_PIPELINE
+#define PXZ_EXACT_PIPELINE 1
+#endif
 constexpr int kExactChunk = 4096;             // pixels staged per pass
 constexpr int kExactStride = kExactChunk + 4; // +4 floats: 16-byte aligned rows, and the 4 channel lanes hit different banks
 
@@ -696,6 +699,29 @@ __device__ float mad_exact_tile(const uint8_t* __restrict__ img, size_t pitch, c
   float run = 0.0f;  // lane c of warp 0 carries channel c: 0 = a, 1 = b, 2 = l, 3 = alpha
   for (int pass = 0; pass < 2; ++pass) {
     run = 0.0f;
+#if PXZ_EXACT_PIPELINE
+    if (pass == 0 && npx <= (uint32_t)kExactChunk && blockDim.x >= 128) {
+      // The first pass in quarters of the tile: while warp 0 runs the sequential sums of quarter k, the other warps convert
+      // quarter k + 1 (the conversion is bound by the FP64 pipe, the sums by the latency of dependent adds; with a
+      // 384-thread CTA the adding warp shares its scheduler with two converting warps only).  Same values, same order.
+      constexpr uint32_t kSub = 1024;
+      auto stage = [&](uint32_t s0, uint32_t cnt, uint32_t first, uint32_t nthr) {
+        if ((uint32_t)tid >= first) {
+          uint32_t i = (uint32_t)tid - first;
+          for (; i + nthr < cnt; i += 2 * nthr) stage_exact_px2<C>(base, pitch, t, s0 + i, s0 + i + nthr, s0 + i, s0 + i + nthr, s_val, s_lut256);
+          if (i < cnt) stage_exact_px<C>(base, pitch, t, s0 + i, s0 + i, s_val, s_lut256);
+        }
+      };
+      stage(0, min(kSub, npx), 0, blockDim.x);
+      __syncthreads();
+      for (uint32_t s0 = 0; s0 < npx; s0 += kSub) {
+        const uint32_t cnt = min(kSub, npx - s0);
+        if (s0 + kSub < npx) stage(s0 + kSub, min(kSub, npx - s0 - kSub), 32, blockDim.x - 32);
+        if (warp == 0 && lane < C) run = chain_sum(s_val + lane * kExactStride + s0, cnt, run);
+        __syncthreads();
+      }
+    } else
+#endif
     for (uint32_t c0 = 0; c0 < npx; c0 += kExactChunk) {
       const uint32_t n = min((uint32_t)kExactChunk, npx - c0);
       // stage the chunk (skipped in pass 2 when the whole tile is still resident)
