@@ -286,18 +286,19 @@ def timed_region(torch, dist, world, device, fn, reps):
 
 
 def run_sharded_c4(torch, dist, N, S, args, rank, world, local_rank, device):
-    """C4: one side x side frame in contiguous block-row shards; global normalisation = the only exchange."""
+    """C4: one side x side frame in block-row shards, contiguous runs and interleaved rows; global normalisation = the only
+    exchange."""
     side = args.c4_side
     ctx = N.Context(local_rank, cuda_stream=torch.cuda.current_stream(device).cuda_stream)
     if world > 1:
         S.init_comm(ctx, dist, rank, world, device=device)
-    y0, y1 = S.shard_pixel_rows(side, BS, world, rank)
-    src = synth_rows_device(torch, y0, y1, side, 7, device)
-    dst = torch.empty_like(src)
-    img = ctx.image_wrap(src.data_ptr(), side, y1 - y0, 4, side * 4)
-    out = ctx.image_wrap(dst.data_ptr(), side, y1 - y0, 4, side * 4)
-    res = {}
-    for name, flags in (("normalise_global", N.FLAG_NORMALISE_GLOBAL), ("default", 0)):
+
+    def measure(src, flags):
+        """encode+decode of this rank's rows `src` [rows, side, 4]: whole-job MP/s, per-rank ms, checksum over all ranks"""
+        dst = torch.empty_like(src)
+        img = ctx.image_wrap(src.data_ptr(), side, src.shape[0], 4, side * 4)
+        out = ctx.image_wrap(dst.data_ptr(), side, src.shape[0], 4, side * 4)
+
         def step():
             pl = img.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, flags)
             pl.expand_to_image(FILTER_UP, out)
@@ -316,48 +317,31 @@ def run_sharded_c4(torch, dist, N, S, args, rank, world, local_rank, device):
             per_rank_ms = [round(float(t.item()), 3) for t in g]
         else:
             per_rank_ms = [round(mine, 3)]
-        res[name] = {"MPps": round(side * side / (ms / 1e3) / 1e6, 1), "ms": round(ms, 3), "ms_per_rank": per_rank_ms,
-                     "payload_fraction": round(int(chk[2]) / (side * side * 4), 4),
-                     "checksum": [int(chk[0]), int(chk[1])]}
-    del src, dst, img, out
+        return {"MPps": round(side * side / (ms / 1e3) / 1e6, 1), "ms": round(ms, 3), "ms_per_rank": per_rank_ms,
+                "payload_fraction": round(int(chk[2]) / (side * side * 4), 4), "checksum": [int(chk[0]), int(chk[1])]}
+
+    modes = (("normalise_global", N.FLAG_NORMALISE_GLOBAL), ("default", 0))
+    res = {}
+    y0, y1 = S.shard_pixel_rows(side, BS, world, rank)
+    src = synth_rows_device(torch, y0, y1, side, 7, device)
+    for name, flags in modes:
+        res[name] = measure(src, flags)
+    del src
     torch.cuda.empty_cache()
     # both modes again with INTERLEAVED block rows (row g of the frame on rank g mod N, sharding.cyclic_block_rows):
     # the cost of a block row follows the frame's content, which changes slowly down the frame, so contiguous runs are
     # uneven (two of eight ranks carry 40 % more work above) while every N-th row gives each rank the same level mix
-    rows_idx = S.cyclic_block_rows(-(-side // BS), world, rank)
-    src = synth_block_rows_device(torch, rows_idx, side, side, 7, device)
-    dst = torch.empty_like(src)
-    img = ctx.image_wrap(src.data_ptr(), side, src.shape[0], 4, side * 4)
-    out = ctx.image_wrap(dst.data_ptr(), side, src.shape[0], 4, side * 4)
-
-    for name, flags in (("normalise_global", N.FLAG_NORMALISE_GLOBAL), ("default", 0)):
-        def step_i():
-            pl = img.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, flags)
-            pl.expand_to_image(FILTER_UP, out)
-            pl.free()
-        ms, mine = timed_region(torch, dist, world, device, step_i, args.extra_reps)
-        pl = img.shrink(BS, BS, N.METRIC_OKLAB_MAD, FACTOR, FILTER_DOWN, flags)
-        descs, px = pl.download()
-        pl.free()
-        chk = torch.tensor([int(descs["w"].astype(np.uint64).sum() * 65537 + descs["h"].astype(np.uint64).sum()),
-                            int(px.astype(np.uint64).sum()), int(px.size)], device=device, dtype=torch.int64)
-        per_rank = torch.tensor([mine], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(chk)
-            g = [torch.zeros_like(per_rank) for _ in range(world)]
-            dist.all_gather(g, per_rank)
-            per_rank_ms = [round(float(t.item()), 3) for t in g]
-        else:
-            per_rank_ms = [round(mine, 3)]
-        res[name + "_interleaved"] = {"MPps": round(side * side / (ms / 1e3) / 1e6, 1), "ms": round(ms, 3), "ms_per_rank": per_rank_ms,
-                                      "payload_fraction": round(int(chk[2]) / (side * side * 4), 4), "checksum": [int(chk[0]), int(chk[1])],
-                                      "same_result_as_contiguous": [int(chk[0]), int(chk[1])] == res[name]["checksum"]}
+    src = synth_block_rows_device(torch, S.cyclic_block_rows(-(-side // BS), world, rank), side, side, 7, device)
+    for name, flags in modes:
+        r = measure(src, flags)
+        r["same_result_as_contiguous"] = r["checksum"] == res[name]["checksum"]
+        res[name + "_interleaved"] = r
     res["note"] = ("normalise_global = the extension of BASELINE config 4: v' = (v - min) / (max - min) over the whole frame, one NCCL "
                    "min all-reduce of {min, -max} per shrink (the only exchange), min and max in reference order; checksum = sum over ranks of descriptor dims and "
                    "payload bytes: it must be the same at every N and in both layouts; *_interleaved = block row g of the frame on rank g mod N")
     res["config"] = f"C4 synthetic {side}x{side} RGBA8 generated on the device, 64x64 blocks, block-row shards (contiguous runs; *_interleaved: every N-th row), Oklab-MAD k=1, Lanczos3 / Lanczos3, encode+decode, device-resident"
     res["blocks"] = (side // BS) ** 2
-    del src, dst
+    del src
     torch.cuda.empty_cache()
     return res
 
